@@ -1,0 +1,197 @@
+/*
+ * mda_chisq.h -- C ABI of the B200-native chi-square log-likelihood library.
+ *
+ * Drop-in boundary: the first seven functions are exactly the exports of the
+ * reference's libChiSq.so (reference C/ChiSquare.h:31-49; ctypes mirror in
+ * mda.py:1161-1189 and C/so_py_tester.py:14-24), same names ("Liklihood"
+ * spelling included), same argument meaning, same ownership rules.  mda.py
+ * loads this library through CONFIG["Shared Lib Path"] (mda_config0.py:16)
+ * without modification.  Everything after them is additive: an error side
+ * channel (the reference defines none) and the batched, device-resident
+ * surface the reference does not have.
+ *
+ * All arithmetic is IEEE fp64 on the GPU (sm_100a).  There is no CPU
+ * fallback: without a usable CUDA device every compute entry point fails
+ * loudly (NaN / non-zero status + mdaLastError()).
+ *
+ * Threading: as in the reference a handle is not re-entrant (reference
+ * C/ChiSquare.c:121,183 share one scratch array per struct); different
+ * handles may be used from different threads.  The error channel is
+ * thread-local.
+ */
+#ifndef MDA_CHISQ_H
+#define MDA_CHISQ_H
+
+#include <stddef.h>
+
+/* Exported with default visibility; everything else in the library is hidden. */
+#if defined(__GNUC__)
+#define MDA_API __attribute__((visibility("default")))
+#else
+#define MDA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * 1. The reference's seven symbols (one Ex bin per handle, scalar calls)
+ * --------------------------------------------------------------------- */
+
+/* replaces makeMdaStruct, C/ChiSquare.h:31, C/ChiSquare.c:18-44.
+ * Allocates host mirror + device storage for numPts angles and numL
+ * distributions.  CUDA is first touched here (never at dlopen), so forking
+ * before the first call is safe (mda.py:186,1109).  NULL on failure. */
+MDA_API void *makeMdaStruct(int numPts, int numL);
+
+/* replaces freeMdaStruct, C/ChiSquare.h:34, C/ChiSquare.c:46-65. */
+MDA_API void freeMdaStruct(void *strPtr);
+
+/* replaces setMdaData, C/ChiSquare.h:37, C/ChiSquare.c:67-83.
+ * Copies numPts doubles (data already divided by its error, mda.py:176). */
+MDA_API void setMdaData(void *strPtr, double *divData);
+
+/* replaces setMdaDist, C/ChiSquare.h:40, C/ChiSquare.c:85-112.
+ * Copies numPts doubles into row distIndex; distIndex >= numL is silently
+ * ignored exactly as in the reference (C/ChiSquare.c:88-89); negative
+ * indices (undefined behaviour there) are ignored too and flagged in
+ * mdaLastError(). */
+MDA_API void setMdaDist(void *strPtr, int distIndex, double *dist);
+
+/* replaces calculateChi, C/ChiSquare.h:43, C/ChiSquare.c:114-172.
+ * chi^2 = sum_j (d_j - sum_l a_l D_lj)^2.  params: numL doubles, borrowed. */
+MDA_API double calculateChi(void *strPtr, double *params);
+
+/* replaces calculateLnLiklihood, C/ChiSquare.h:46, C/ChiSquare.c:176-213.
+ * Returns chi^2 / (-2).  NaN + mdaLastError() on a CUDA failure. */
+MDA_API double calculateLnLiklihood(void *strPtr, double *params);
+
+/* replaces calculateLnLiklihoodResids, C/ChiSquare.h:49, C/ChiSquare.c:216-252.
+ * As above; residArray (numPts doubles, caller-owned) receives the residuals. */
+MDA_API double calculateLnLiklihoodResids(void *strPtr, double *params, double *residArray);
+
+/* ------------------------------------------------------------------------
+ * 2. Error side channel (additive; thread-local; sticky until cleared)
+ * --------------------------------------------------------------------- */
+#define MDA_OK                 0
+#define MDA_ERR_CUDA           1   /* a CUDA runtime call failed            */
+#define MDA_ERR_NO_DEVICE      2   /* no usable sm_100 device / bad index   */
+#define MDA_ERR_BAD_ARGUMENT   3   /* NULL handle, negative size, ...       */
+#define MDA_ERR_OUT_OF_MEMORY  4
+#define MDA_ERR_BAD_STATE      5   /* e.g. evaluating an un-filled store    */
+
+MDA_API int         mdaLastError(void);
+MDA_API const char *mdaLastErrorString(void);
+MDA_API void        mdaClearError(void);
+MDA_API const char *mdaVersion(void);
+
+/* ------------------------------------------------------------------------
+ * 3. Device selection and raw memory helpers
+ * --------------------------------------------------------------------- */
+
+/* Number of CUDA devices (0 if none / driver missing). */
+MDA_API int mdaDeviceCount(void);
+/* Select the device used by handles created afterwards by this process.
+ * Default: $MDA_DEVICE, else $LOCAL_RANK, else 0.  One process per GPU. */
+MDA_API int mdaSetDevice(int device);
+MDA_API int mdaGetDevice(void);
+/* Fills name (<= nameLen bytes), SM count and compute capability major*10+minor. */
+MDA_API int mdaDeviceInfo(char *name, int nameLen, int *smCount, int *cc);
+
+/* Page-locked host memory: buffers handed to the batched calls DMA at full
+ * PCIe rate only if they come from here (or are otherwise pinned). */
+MDA_API void *mdaHostAlloc(size_t bytes);
+MDA_API void  mdaHostFree(void *p);
+MDA_API void *mdaDeviceAlloc(size_t bytes);
+MDA_API void  mdaDeviceFree(void *p);
+MDA_API int   mdaMemcpyH2D(void *dst, const void *src, size_t bytes);
+MDA_API int   mdaMemcpyD2H(void *dst, const void *src, size_t bytes);
+MDA_API int   mdaDeviceSynchronize(void);
+
+/* ------------------------------------------------------------------------
+ * 4. Device-resident multi-bin store (B Ex bins, uniform numL, ragged numPts)
+ *
+ * Callers hand bins over in the reference's layout (data[numPts] and
+ * dists[l*numPts + j], C/ChiSquare.c:97-102); the store keeps them in HBM
+ * angle-pair-major, consts[bin][nPad/2][1 + numL][2] doubles (for each pair
+ * of angles: the data pair, then the pair of every distribution), zero
+ * padded to nPad = maxPts rounded up to even, so that one bulk copy brings a
+ * bin into shared memory in the order the kernel consumes it.  The internal
+ * layout is not part of the ABI.  Bounds are per distribution and shared
+ * by all bins: the reference's (0, 1/EWSR_l) of mda.py:1124.
+ * --------------------------------------------------------------------- */
+MDA_API void *mdaStoreCreate(int numBins, int numL, int maxPts);
+MDA_API void  mdaStoreFree(void *store);
+/* divData[numPts], dists[numL][numPts] dense (reference layout). Copies. */
+MDA_API int   mdaStoreSetBin(void *store, int bin, int numPts, const double *divData, const double *dists);
+/* Fill bin from a handle made with makeMdaStruct/setMdaData/setMdaDist. */
+MDA_API int   mdaStoreSetBinFromStruct(void *store, int bin, void *mdaStruct);
+/* lo[numL], hi[numL], inclusive.  Default: lo = 0, hi = 1. */
+MDA_API int   mdaStoreSetBounds(void *store, const double *lo, const double *hi);
+/* Push the host mirror to HBM (done lazily by the first evaluation too). */
+MDA_API int   mdaStoreUpload(void *store);
+MDA_API int   mdaStoreNumBins(void *store);
+MDA_API int   mdaStoreNumL(void *store);
+MDA_API int   mdaStoreMaxPts(void *store);
+/* Force the kernel tiling (threads per CTA in {32,64,128,256}, walkers per
+ * thread in {1,2,4}); 0,0 restores the built-in heuristic. */
+MDA_API int   mdaStoreSetTile(void *store, int threads, int walkersPerThread);
+/* Reports the tiling the next call with walkersPerBin walkers would use. */
+MDA_API int   mdaStoreGetTile(void *store, int walkersPerBin, int *threads, int *walkersPerThread, int *gridSize);
+
+/* ------------------------------------------------------------------------
+ * 5. Batched evaluation: all bins x walkersPerBin walkers in ONE launch
+ *
+ * params[bin][walker][l] (C-contiguous, the [W, L] blocks emcee hands to a
+ * vectorised log-prob function, one per bin), out[bin][walker].
+ * LnPost = flat box prior of mda.py:1574-1576 (-inf outside, NaN falls
+ * through) then calculateLnLiklihood; Chi = calculateChi, no prior.
+ * Per (bin, walker) the operation order is the reference's
+ * (C/ChiSquare.c:188-212), so a result does not depend on batch shape,
+ * tiling or GPU count.  All return MDA_OK or an error code.
+ * --------------------------------------------------------------------- */
+
+/* Host pointers; copies in, launches, copies out, synchronises. */
+MDA_API int mdaBatchLnPost(void *store, int walkersPerBin, const double *params, double *lnPost);
+MDA_API int mdaBatchChi(void *store, int walkersPerBin, const double *params, double *chi);
+
+/* Pinned staging owned by the store, valid until the next call with a larger
+ * walkersPerBin or mdaStoreFree: fill HostParams, call Staged, read HostOut.
+ * The per-step work {H2D params, kernel, D2H results} is one CUDA graph
+ * captured once per walkersPerBin and replayed on every call. */
+MDA_API double *mdaStoreHostParams(void *store, int walkersPerBin);
+MDA_API double *mdaStoreHostOut(void *store, int walkersPerBin);
+MDA_API int     mdaBatchLnPostStaged(void *store, int walkersPerBin);
+MDA_API int     mdaBatchChiStaged(void *store, int walkersPerBin);
+
+/* Device pointers, asynchronous on the store's stream (no copies, no sync). */
+MDA_API int mdaBatchLnPostDevice(void *store, int walkersPerBin, const double *dParams, double *dLnPost);
+MDA_API int mdaBatchChiDevice(void *store, int walkersPerBin, const double *dParams, double *dChi);
+/* Enqueue `count` independent blocks: block i reads dParams[i % nBlocks] and
+ * writes dOut[i % nBlocks]. */
+MDA_API int mdaBatchLnPostDeviceMany(void *store, int walkersPerBin, const double *const *dParams,
+                             double *const *dOut, int nBlocks, int count);
+MDA_API int mdaStoreSynchronize(void *store);
+
+/* CUDA events on the store's stream, for device-side timing. */
+MDA_API void *mdaEventCreate(void);
+MDA_API void  mdaEventDestroy(void *event);
+MDA_API int   mdaEventRecord(void *event, void *store);
+MDA_API int   mdaEventSynchronize(void *event);
+MDA_API int   mdaEventElapsedMs(void *start, void *stop, float *ms);
+/* Kernels launched by this process through this library so far. */
+MDA_API unsigned long long mdaKernelLaunchCount(void);
+
+/* ------------------------------------------------------------------------
+ * 6. Roofline denominators measured on the device this process uses
+ * --------------------------------------------------------------------- */
+/* Dependent-free DFMA stream on every SM; best of `repeats`. TFLOP/s (2/FMA). */
+MDA_API int mdaMeasureFp64Peak(int repeats, double *tflops);
+/* Device-to-device copy of `bytes` bytes; GB/s counting read + write. */
+MDA_API int mdaMeasureHbmCopy(size_t bytes, int repeats, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDA_CHISQ_H */

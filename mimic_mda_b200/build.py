@@ -1,0 +1,65 @@
+"""Builds mimic_mda_b200/libChiSq.so in-tree with nvcc for sm_100a only.
+
+The output is a plain C-ABI shared library (include/mda_chisq.h) with the CUDA
+runtime linked statically: ``ctypes.cdll.LoadLibrary`` (mda.py:1161) needs
+nothing else on the library path.  It is git-ignored but travels to the GPU box
+with the repo snapshot.
+
+    python -m mimic_mda_b200.build [--force] [--verbose]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libChiSq.so")
+SOURCES = ["chisq_abi.cu", "lnpost_kernel.cu", "scalar_kernel.cu", "peaks.cu"]
+HEADERS = [os.path.join(CSRC, "mda_kernels.cuh"),
+           os.path.join(HERE, "..", "include", "mda_chisq.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden",
+    "-fmad=true",
+    "-shared", "-cudart", "static",
+]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libChiSq.so")
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into libChiSq.so (no-op when up to date)."""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [nvcc_path()] + NVCC_FLAGS
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

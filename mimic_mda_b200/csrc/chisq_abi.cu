@@ -1,0 +1,711 @@
+// chisq_abi.cu -- the C ABI of include/mda_chisq.h on top of the sm_100a kernels.
+//
+// Host-side runtime: handles, HBM store, pinned staging, per-shape CUDA graphs,
+// error side channel.  No torch types, no CPU arithmetic path: every evaluation is a
+// kernel launch, and without a usable device every entry point fails loudly.
+#include "../../include/mda_chisq.h"
+#include "mda_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+using namespace mda;
+
+// ---- error side channel -------------------------------------------------------------
+thread_local int t_err_code = MDA_OK;
+thread_local char t_err_msg[512] = "no error";
+
+int set_error(int code, const char *fmt, ...) {
+    t_err_code = code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err_msg, sizeof(t_err_msg), fmt, ap);
+    va_end(ap);
+    if (getenv("MDA_VERBOSE")) fprintf(stderr, "[mda_chisq] error %d: %s\n", code, t_err_msg);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    const int code = (e == cudaErrorMemoryAllocation) ? MDA_ERR_OUT_OF_MEMORY
+                     : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+                         ? MDA_ERR_NO_DEVICE
+                         : MDA_ERR_CUDA;
+    return set_error(code, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define MDA_CUDA(call, what)                                   \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what);   \
+    } while (0)
+
+std::atomic<unsigned long long> g_launches{0};
+
+// ---- per-process runtime ------------------------------------------------------------
+struct Runtime {
+    std::mutex mu;
+    bool ready = false;
+    int requested = -1;      // mdaSetDevice
+    int device = -1;
+    int sm_count = 0;
+    int cc = 0;
+    size_t smem_optin = 0;
+    char name[128] = {0};
+};
+Runtime g_rt;
+
+int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    if (!v || !*v) return fallback;
+    char *end = nullptr;
+    long x = strtol(v, &end, 10);
+    return (end && *end == 0) ? (int)x : fallback;
+}
+
+// Brings CUDA up on the chosen device the first time any handle is made -- never at
+// library load (workers dlopen after fork, mda.py:1109).
+int ensure_runtime() {
+    std::lock_guard<std::mutex> lock(g_rt.mu);
+    if (g_rt.ready) {
+        cudaError_t e = cudaSetDevice(g_rt.device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        return MDA_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDeviceCount (this library has no CPU fallback)");
+        return t_err_code = MDA_ERR_NO_DEVICE;
+    }
+    if (count <= 0) return set_error(MDA_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    int dev = g_rt.requested;
+    if (dev < 0) dev = env_int("MDA_DEVICE", -1);
+    if (dev < 0) {
+        const int lr = env_int("LOCAL_RANK", -1);
+        dev = lr >= 0 ? lr % count : 0;
+    }
+    if (dev >= count) return set_error(MDA_ERR_NO_DEVICE, "device %d requested but only %d visible", dev, count);
+    MDA_CUDA(cudaSetDevice(dev), "cudaSetDevice");
+    cudaDeviceProp prop;
+    MDA_CUDA(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return set_error(MDA_ERR_NO_DEVICE, "device %d (%s, sm_%d%d) is not Blackwell; kernels are built for sm_100a only",
+                         dev, prop.name, prop.major, prop.minor);
+    g_rt.device = dev;
+    g_rt.sm_count = prop.multiProcessorCount;
+    g_rt.cc = prop.major * 10 + prop.minor;
+    g_rt.smem_optin = prop.sharedMemPerBlockOptin;
+    snprintf(g_rt.name, sizeof(g_rt.name), "%s", prop.name);
+    MDA_CUDA(configure_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem)");
+    g_rt.ready = true;
+    return MDA_OK;
+}
+
+// ---- legacy single-bin handle ---------------------------------------------------------
+constexpr uint32_t kStructMagic = 0x4D444131u;  // "MDA1"
+constexpr uint32_t kStoreMagic = 0x4D444153u;   // "MDAS"
+
+struct MdaHandle {
+    uint32_t magic = kStructMagic;
+    int n = 0, n_l = 0;
+    std::vector<double> host;        // [1+L][n]: row 0 data, rows 1..L dists (reference row layout)
+    double *d_consts = nullptr;      // same layout in HBM
+    double *d_resid = nullptr;       // [n]
+    double *h_io = nullptr;          // mapped pinned: [0..L) params, [L] result
+    double *d_io = nullptr;          // device alias of h_io
+    cudaStream_t stream = nullptr;
+    bool dirty = true;
+};
+
+MdaHandle *as_struct(void *p, const char *fn) {
+    MdaHandle *h = static_cast<MdaHandle *>(p);
+    if (!h || h->magic != kStructMagic) {
+        set_error(MDA_ERR_BAD_ARGUMENT, "%s: not a handle from makeMdaStruct", fn);
+        return nullptr;
+    }
+    return h;
+}
+
+void destroy_struct(MdaHandle *h) {
+    if (h->d_consts) cudaFree(h->d_consts);
+    if (h->d_resid) cudaFree(h->d_resid);
+    if (h->h_io) cudaFreeHost(h->h_io);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    h->magic = 0;
+    delete h;
+}
+
+double scalar_eval(void *p, double *params, double *resid_out, int mode, const char *fn) {
+    MdaHandle *h = as_struct(p, fn);
+    if (!h) return NAN;
+    if (!params) { set_error(MDA_ERR_BAD_ARGUMENT, "%s: params is NULL", fn); return NAN; }
+    if (ensure_runtime() != MDA_OK) return NAN;
+    cudaError_t e;
+    if (h->dirty) {
+        e = cudaMemcpyAsync(h->d_consts, h->host.data(), sizeof(double) * h->host.size(), cudaMemcpyHostToDevice,
+                            h->stream);
+        if (e != cudaSuccess) { cuda_fail(e, "upload of struct constants"); return NAN; }
+        h->dirty = false;
+    }
+    memcpy(h->h_io, params, sizeof(double) * (size_t)h->n_l);
+    h->h_io[h->n_l] = NAN;
+    e = launch_scalar(h->d_consts, h->n, h->n_l, h->d_io, h->d_io + h->n_l, h->d_resid, mode, h->stream);
+    if (e != cudaSuccess) { cuda_fail(e, "scalar kernel launch"); return NAN; }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (resid_out && h->n > 0) {
+        e = cudaMemcpyAsync(resid_out, h->d_resid, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) { cuda_fail(e, "residual read-back"); return NAN; }
+    }
+    e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cuda_fail(e, fn); return NAN; }
+    return h->h_io[h->n_l];
+}
+
+// ---- multi-bin device store ---------------------------------------------------------
+struct GraphKey {
+    int walkers, mode;
+    bool operator<(const GraphKey &o) const { return walkers != o.walkers ? walkers < o.walkers : mode < o.mode; }
+};
+
+struct MdaStore {
+    uint32_t magic = kStoreMagic;
+    int bins = 0, n_l = 0, max_pts = 0, n_pad = 0;
+    std::vector<double> host;        // [bins][n_pad/2][1+L][2]  (the HBM layout)
+    std::vector<int> n_pts;          // [bins]
+    std::vector<double> lo, hi;      // [L]
+    double *d_consts = nullptr;
+    int *d_npts = nullptr;
+    double *d_lo = nullptr, *d_hi = nullptr;
+    bool dirty = true;
+    cudaStream_t stream = nullptr;
+    int force_threads = 0, force_wpt = 0;
+    // staging for the host-pointer and staged entry points
+    size_t cap_walkers = 0;          // walkers per bin the buffers below can hold
+    double *h_params = nullptr, *h_out = nullptr;   // pinned
+    double *d_params = nullptr, *d_out = nullptr;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+};
+
+MdaStore *as_store(void *p, const char *fn) {
+    MdaStore *s = static_cast<MdaStore *>(p);
+    if (!s || s->magic != kStoreMagic) {
+        set_error(MDA_ERR_BAD_ARGUMENT, "%s: not a handle from mdaStoreCreate", fn);
+        return nullptr;
+    }
+    return s;
+}
+
+void drop_graphs(MdaStore *s) {
+    for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
+    s->graphs.clear();
+}
+
+size_t bin_stride(const MdaStore *s) { return (size_t)s->n_pad * (size_t)(s->n_l + 1); }
+
+void write_bin(MdaStore *s, int bin, int n, const double *data, const double *dists, size_t dist_stride) {
+    double *blk = s->host.data() + (size_t)bin * bin_stride(s);
+    std::fill(blk, blk + bin_stride(s), 0.0);
+    const int row = s->n_l + 1;
+    for (int j = 0; j < n; ++j) {
+        double *cell = blk + ((size_t)(j >> 1) * row) * 2 + (j & 1);
+        cell[0] = data[j];
+        for (int l = 0; l < s->n_l; ++l) cell[(size_t)(1 + l) * 2] = dists[(size_t)l * dist_stride + j];
+    }
+    s->n_pts[bin] = n;
+    s->dirty = true;
+}
+
+int upload_store(MdaStore *s) {
+    if (!s->dirty) return MDA_OK;
+    MDA_CUDA(cudaMemcpyAsync(s->d_consts, s->host.data(), sizeof(double) * s->host.size(), cudaMemcpyHostToDevice,
+                             s->stream), "store upload (constants)");
+    MDA_CUDA(cudaMemcpyAsync(s->d_npts, s->n_pts.data(), sizeof(int) * s->n_pts.size(), cudaMemcpyHostToDevice,
+                             s->stream), "store upload (angle counts)");
+    MDA_CUDA(cudaMemcpyAsync(s->d_lo, s->lo.data(), sizeof(double) * s->lo.size(), cudaMemcpyHostToDevice, s->stream),
+             "store upload (bounds)");
+    MDA_CUDA(cudaMemcpyAsync(s->d_hi, s->hi.data(), sizeof(double) * s->hi.size(), cudaMemcpyHostToDevice, s->stream),
+             "store upload (bounds)");
+    // the host mirror is pageable: make sure the DMA engine is done with it before it can change
+    MDA_CUDA(cudaStreamSynchronize(s->stream), "store upload");
+    s->dirty = false;
+    return MDA_OK;
+}
+
+int ensure_staging(MdaStore *s, int walkers) {
+    if ((size_t)walkers <= s->cap_walkers) return MDA_OK;
+    MDA_CUDA(cudaStreamSynchronize(s->stream), "staging resize");
+    drop_graphs(s);
+    if (s->h_params) cudaFreeHost(s->h_params);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->d_params) cudaFree(s->d_params);
+    if (s->d_out) cudaFree(s->d_out);
+    s->h_params = s->h_out = s->d_params = s->d_out = nullptr;
+    s->cap_walkers = 0;
+    const size_t n_eval = (size_t)s->bins * (size_t)walkers;
+    const size_t pbytes = sizeof(double) * n_eval * (size_t)s->n_l, obytes = sizeof(double) * n_eval;
+    MDA_CUDA(cudaHostAlloc((void **)&s->h_params, pbytes ? pbytes : 8, cudaHostAllocDefault), "pinned params staging");
+    MDA_CUDA(cudaHostAlloc((void **)&s->h_out, obytes ? obytes : 8, cudaHostAllocDefault), "pinned result staging");
+    MDA_CUDA(cudaMalloc((void **)&s->d_params, pbytes ? pbytes : 8), "device params block");
+    MDA_CUDA(cudaMalloc((void **)&s->d_out, obytes ? obytes : 8), "device result block");
+    s->cap_walkers = (size_t)walkers;
+    return MDA_OK;
+}
+
+TileShape tile_for(const MdaStore *s, int walkers) {
+    return choose_tile(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, s->force_threads,
+                       s->force_wpt);
+}
+
+// Enqueue one evaluation of device-resident params on the store's stream.
+int enqueue_eval(MdaStore *s, int walkers, const double *d_params, double *d_out, int mode) {
+    BatchArgs args;
+    memset(&args, 0, sizeof(args));
+    args.consts = s->d_consts;
+    args.n_pts = s->d_npts;
+    args.params = d_params;
+    args.out = d_out;
+    args.bins = s->bins;
+    args.walkers = walkers;
+    args.n_l = s->n_l;
+    args.n_pad = s->n_pad;
+    args.mode = mode;
+    if (s->n_l <= kMaxRegL)
+        for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
+    const TileShape tile = tile_for(s, walkers);
+    if (tile.smem_bytes > g_rt.smem_optin)
+        return set_error(MDA_ERR_BAD_ARGUMENT, "tile needs %zu bytes of shared memory, device offers %zu",
+                         tile.smem_bytes, g_rt.smem_optin);
+    MDA_CUDA(launch_batch(args, tile, s->stream, s->d_lo, s->d_hi), "batched likelihood launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return MDA_OK;
+}
+
+int check_eval_args(MdaStore *s, int walkers, const void *a, const void *b, const char *fn) {
+    if (walkers < 0) return set_error(MDA_ERR_BAD_ARGUMENT, "%s: walkersPerBin < 0", fn);
+    if (walkers > 0 && s->bins > 0 && (!a || !b)) return set_error(MDA_ERR_BAD_ARGUMENT, "%s: NULL buffer", fn);
+    return MDA_OK;
+}
+
+int eval_host(void *store, int walkers, const double *params, double *out, int mode, const char *fn) {
+    MdaStore *s = as_store(store, fn);
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    int rc = check_eval_args(s, walkers, params, out, fn);
+    if (rc) return rc;
+    if ((rc = ensure_runtime())) return rc;
+    if (walkers == 0 || s->bins == 0) return MDA_OK;
+    if ((rc = upload_store(s))) return rc;
+    if ((rc = ensure_staging(s, walkers))) return rc;
+    const size_t n_eval = (size_t)s->bins * (size_t)walkers;
+    MDA_CUDA(cudaMemcpyAsync(s->d_params, params, sizeof(double) * n_eval * s->n_l, cudaMemcpyHostToDevice, s->stream),
+             "params H2D");
+    if ((rc = enqueue_eval(s, walkers, s->d_params, s->d_out, mode))) return rc;
+    MDA_CUDA(cudaMemcpyAsync(out, s->d_out, sizeof(double) * n_eval, cudaMemcpyDeviceToHost, s->stream), "results D2H");
+    MDA_CUDA(cudaStreamSynchronize(s->stream), fn);
+    return MDA_OK;
+}
+
+// {H2D params, kernel, D2H results} captured once per (walkers, mode), replayed per call.
+int eval_staged(void *store, int walkers, int mode, const char *fn) {
+    MdaStore *s = as_store(store, fn);
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    if (walkers < 0) return set_error(MDA_ERR_BAD_ARGUMENT, "%s: walkersPerBin < 0", fn);
+    int rc;
+    if ((rc = ensure_runtime())) return rc;
+    if (walkers == 0 || s->bins == 0) return MDA_OK;
+    if ((size_t)walkers > s->cap_walkers)
+        return set_error(MDA_ERR_BAD_STATE, "%s: call mdaStoreHostParams(store, %d) and fill it first", fn, walkers);
+    if ((rc = upload_store(s))) return rc;
+    const GraphKey key{walkers, mode};
+    auto it = s->graphs.find(key);
+    if (it == s->graphs.end()) {
+        const size_t n_eval = (size_t)s->bins * (size_t)walkers;
+        cudaGraph_t graph = nullptr;
+        MDA_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal), "graph capture begin");
+        cudaError_t e = cudaMemcpyAsync(s->d_params, s->h_params, sizeof(double) * n_eval * s->n_l,
+                                        cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) rc = enqueue_eval(s, walkers, s->d_params, s->d_out, mode);
+        if (e == cudaSuccess && rc == MDA_OK)
+            e = cudaMemcpyAsync(s->h_out, s->d_out, sizeof(double) * n_eval, cudaMemcpyDeviceToHost, s->stream);
+        cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
+        if (rc != MDA_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(e, "graph capture"); }
+        if (e2 != cudaSuccess) return cuda_fail(e2, "graph capture end");
+        g_launches.fetch_sub(1, std::memory_order_relaxed);   // the captured launch did not run
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cuda_fail(e, "graph instantiate");
+        it = s->graphs.emplace(key, exec).first;
+    }
+    MDA_CUDA(cudaGraphLaunch(it->second, s->stream), "graph launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    MDA_CUDA(cudaStreamSynchronize(s->stream), fn);
+    return MDA_OK;
+}
+
+int eval_device(void *store, int walkers, const double *d_params, double *d_out, int mode, const char *fn) {
+    MdaStore *s = as_store(store, fn);
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    int rc = check_eval_args(s, walkers, d_params, d_out, fn);
+    if (rc) return rc;
+    if ((rc = ensure_runtime())) return rc;
+    if (walkers == 0 || s->bins == 0) return MDA_OK;
+    if ((rc = upload_store(s))) return rc;
+    return enqueue_eval(s, walkers, d_params, d_out, mode);
+}
+
+}  // namespace
+
+// =====================================================================================
+// exported C ABI
+// =====================================================================================
+extern "C" {
+
+// ---- the reference's seven symbols ---------------------------------------------------
+void *makeMdaStruct(int numPts, int numL) {
+    if (numPts < 0 || numL < 0) { set_error(MDA_ERR_BAD_ARGUMENT, "makeMdaStruct(%d, %d): negative size", numPts, numL); return nullptr; }
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    MdaHandle *h = new MdaHandle();
+    h->n = numPts;
+    h->n_l = numL;
+    h->host.assign((size_t)(1 + numL) * (size_t)numPts, 0.0);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_consts, sizeof(double) * (h->host.size() ? h->host.size() : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_resid, sizeof(double) * (size_t)(numPts > 0 ? numPts : 1));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->h_io, sizeof(double) * (size_t)(numL + 1), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&h->d_io, h->h_io, 0);
+    if (e != cudaSuccess) { cuda_fail(e, "makeMdaStruct"); destroy_struct(h); return nullptr; }
+    return h;
+}
+
+void freeMdaStruct(void *strPtr) {
+    MdaHandle *h = as_struct(strPtr, "freeMdaStruct");
+    if (!h) return;
+    if (g_rt.ready) cudaSetDevice(g_rt.device);
+    destroy_struct(h);
+}
+
+void setMdaData(void *strPtr, double *divData) {
+    MdaHandle *h = as_struct(strPtr, "setMdaData");
+    if (!h) return;
+    if (!divData) { set_error(MDA_ERR_BAD_ARGUMENT, "setMdaData: divData is NULL"); return; }
+    memcpy(h->host.data(), divData, sizeof(double) * (size_t)h->n);
+    h->dirty = true;
+}
+
+void setMdaDist(void *strPtr, int distIndex, double *dist) {
+    MdaHandle *h = as_struct(strPtr, "setMdaDist");
+    if (!h) return;
+    if (distIndex >= h->n_l) return;                       // silently ignored, C/ChiSquare.c:88-89
+    if (distIndex < 0) { set_error(MDA_ERR_BAD_ARGUMENT, "setMdaDist: negative distIndex %d ignored", distIndex); return; }
+    if (!dist) { set_error(MDA_ERR_BAD_ARGUMENT, "setMdaDist: dist is NULL"); return; }
+    memcpy(h->host.data() + (size_t)(1 + distIndex) * (size_t)h->n, dist, sizeof(double) * (size_t)h->n);
+    h->dirty = true;
+}
+
+double calculateChi(void *strPtr, double *params) { return scalar_eval(strPtr, params, nullptr, kChi, "calculateChi"); }
+
+double calculateLnLiklihood(void *strPtr, double *params) {
+    return scalar_eval(strPtr, params, nullptr, kLnLike, "calculateLnLiklihood");
+}
+
+double calculateLnLiklihoodResids(void *strPtr, double *params, double *residArray) {
+    if (!residArray) { set_error(MDA_ERR_BAD_ARGUMENT, "calculateLnLiklihoodResids: residArray is NULL"); return NAN; }
+    return scalar_eval(strPtr, params, residArray, kLnLike, "calculateLnLiklihoodResids");
+}
+
+// ---- error channel -------------------------------------------------------------------
+int mdaLastError(void) { return t_err_code; }
+const char *mdaLastErrorString(void) { return t_err_msg; }
+void mdaClearError(void) { t_err_code = MDA_OK; snprintf(t_err_msg, sizeof(t_err_msg), "no error"); }
+const char *mdaVersion(void) { return "mimic_mda_b200 0.1 (sm_100a, fp64 DFMA path)"; }
+
+// ---- device and memory helpers ---------------------------------------------------------
+int mdaDeviceCount(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+int mdaSetDevice(int device) {
+    std::lock_guard<std::mutex> lock(g_rt.mu);
+    if (g_rt.ready && device != g_rt.device)
+        return set_error(MDA_ERR_BAD_STATE, "mdaSetDevice(%d): device %d already in use by this process", device, g_rt.device);
+    if (device < 0) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaSetDevice(%d)", device);
+    g_rt.requested = device;
+    return MDA_OK;
+}
+
+int mdaGetDevice(void) { return g_rt.ready ? g_rt.device : g_rt.requested; }
+
+int mdaDeviceInfo(char *name, int nameLen, int *smCount, int *cc) {
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    if (name && nameLen > 0) snprintf(name, (size_t)nameLen, "%s", g_rt.name);
+    if (smCount) *smCount = g_rt.sm_count;
+    if (cc) *cc = g_rt.cc;
+    return MDA_OK;
+}
+
+void *mdaHostAlloc(size_t bytes) {
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cuda_fail(e, "mdaHostAlloc"); return nullptr; }
+    return p;
+}
+void mdaHostFree(void *p) { if (p) cudaFreeHost(p); }
+
+void *mdaDeviceAlloc(size_t bytes) {
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+    if (e != cudaSuccess) { cuda_fail(e, "mdaDeviceAlloc"); return nullptr; }
+    return p;
+}
+void mdaDeviceFree(void *p) { if (p) cudaFree(p); }
+
+int mdaMemcpyH2D(void *dst, const void *src, size_t bytes) {
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MDA_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice), "mdaMemcpyH2D");
+    return MDA_OK;
+}
+int mdaMemcpyD2H(void *dst, const void *src, size_t bytes) {
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MDA_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost), "mdaMemcpyD2H");
+    return MDA_OK;
+}
+int mdaDeviceSynchronize(void) {
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MDA_CUDA(cudaDeviceSynchronize(), "mdaDeviceSynchronize");
+    return MDA_OK;
+}
+
+// ---- store ---------------------------------------------------------------------------
+void *mdaStoreCreate(int numBins, int numL, int maxPts) {
+    if (numBins < 0 || numL < 1 || maxPts < 0) {
+        set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreCreate(%d, %d, %d): need numBins >= 0, numL >= 1, maxPts >= 0", numBins, numL, maxPts);
+        return nullptr;
+    }
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    MdaStore *s = new MdaStore();
+    s->bins = numBins;
+    s->n_l = numL;
+    s->max_pts = maxPts;
+    s->n_pad = maxPts + (maxPts & 1);
+    if (s->n_pad == 0) s->n_pad = 2;
+    s->host.assign((size_t)numBins * bin_stride(s), 0.0);
+    s->n_pts.assign((size_t)numBins, 0);
+    s->lo.assign((size_t)numL, 0.0);
+    s->hi.assign((size_t)numL, 1.0);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_consts, sizeof(double) * (s->host.size() ? s->host.size() : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_npts, sizeof(int) * (size_t)(numBins ? numBins : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_lo, sizeof(double) * (size_t)numL);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_hi, sizeof(double) * (size_t)numL);
+    if (e != cudaSuccess) { cuda_fail(e, "mdaStoreCreate"); mdaStoreFree(s); return nullptr; }
+    return s;
+}
+
+void mdaStoreFree(void *store) {
+    MdaStore *s = as_store(store, "mdaStoreFree");
+    if (!s) return;
+    if (g_rt.ready) cudaSetDevice(g_rt.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    drop_graphs(s);
+    if (s->h_params) cudaFreeHost(s->h_params);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->d_params) cudaFree(s->d_params);
+    if (s->d_out) cudaFree(s->d_out);
+    if (s->d_consts) cudaFree(s->d_consts);
+    if (s->d_npts) cudaFree(s->d_npts);
+    if (s->d_lo) cudaFree(s->d_lo);
+    if (s->d_hi) cudaFree(s->d_hi);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    s->magic = 0;
+    delete s;
+}
+
+int mdaStoreSetBin(void *store, int bin, int numPts, const double *divData, const double *dists) {
+    MdaStore *s = as_store(store, "mdaStoreSetBin");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    if (bin < 0 || bin >= s->bins) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetBin: bin %d outside [0, %d)", bin, s->bins);
+    if (numPts < 0 || numPts > s->max_pts)
+        return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetBin: numPts %d outside [0, %d]", numPts, s->max_pts);
+    if (numPts > 0 && (!divData || !dists)) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetBin: NULL buffer");
+    write_bin(s, bin, numPts, divData, dists, (size_t)numPts);
+    return MDA_OK;
+}
+
+int mdaStoreSetBinFromStruct(void *store, int bin, void *mdaStruct) {
+    MdaStore *s = as_store(store, "mdaStoreSetBinFromStruct");
+    MdaHandle *h = as_struct(mdaStruct, "mdaStoreSetBinFromStruct");
+    if (!s || !h) return MDA_ERR_BAD_ARGUMENT;
+    if (bin < 0 || bin >= s->bins) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetBinFromStruct: bin %d outside [0, %d)", bin, s->bins);
+    if (h->n_l != s->n_l) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetBinFromStruct: struct has %d dists, store %d", h->n_l, s->n_l);
+    if (h->n > s->max_pts) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetBinFromStruct: struct has %d angles, store holds %d", h->n, s->max_pts);
+    write_bin(s, bin, h->n, h->host.data(), h->host.data() + h->n, (size_t)h->n);
+    return MDA_OK;
+}
+
+int mdaStoreSetBounds(void *store, const double *lo, const double *hi) {
+    MdaStore *s = as_store(store, "mdaStoreSetBounds");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    if (!lo || !hi) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetBounds: NULL buffer");
+    s->lo.assign(lo, lo + s->n_l);
+    s->hi.assign(hi, hi + s->n_l);
+    s->dirty = true;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    drop_graphs(s);                                       // bounds are baked into captured launches
+    return MDA_OK;
+}
+
+int mdaStoreUpload(void *store) {
+    MdaStore *s = as_store(store, "mdaStoreUpload");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    return upload_store(s);
+}
+
+int mdaStoreNumBins(void *store) { MdaStore *s = as_store(store, "mdaStoreNumBins"); return s ? s->bins : -1; }
+int mdaStoreNumL(void *store) { MdaStore *s = as_store(store, "mdaStoreNumL"); return s ? s->n_l : -1; }
+int mdaStoreMaxPts(void *store) { MdaStore *s = as_store(store, "mdaStoreMaxPts"); return s ? s->max_pts : -1; }
+
+int mdaStoreSetTile(void *store, int threads, int walkersPerThread) {
+    MdaStore *s = as_store(store, "mdaStoreSetTile");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    const bool t_ok = threads == 0 || threads == 32 || threads == 64 || threads == 128 || threads == 256;
+    const bool w_ok = walkersPerThread == 0 || walkersPerThread == 1 || walkersPerThread == 2 || walkersPerThread == 4;
+    if (!t_ok || !w_ok) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaStoreSetTile(%d, %d): unsupported tiling", threads, walkersPerThread);
+    s->force_threads = threads;
+    s->force_wpt = walkersPerThread;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    drop_graphs(s);
+    return MDA_OK;
+}
+
+int mdaStoreGetTile(void *store, int walkersPerBin, int *threads, int *walkersPerThread, int *gridSize) {
+    MdaStore *s = as_store(store, "mdaStoreGetTile");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    const TileShape t = tile_for(s, walkersPerBin > 0 ? walkersPerBin : 1);
+    if (threads) *threads = t.threads;
+    if (walkersPerThread) *walkersPerThread = t.wpt;
+    if (gridSize) *gridSize = t.grid;
+    return MDA_OK;
+}
+
+// ---- batched evaluation -----------------------------------------------------------------
+int mdaBatchLnPost(void *store, int walkersPerBin, const double *params, double *lnPost) {
+    return eval_host(store, walkersPerBin, params, lnPost, kLnPost, "mdaBatchLnPost");
+}
+int mdaBatchChi(void *store, int walkersPerBin, const double *params, double *chi) {
+    return eval_host(store, walkersPerBin, params, chi, kChi, "mdaBatchChi");
+}
+
+double *mdaStoreHostParams(void *store, int walkersPerBin) {
+    MdaStore *s = as_store(store, "mdaStoreHostParams");
+    if (!s || walkersPerBin < 0) return nullptr;
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    if (ensure_staging(s, walkersPerBin > 0 ? walkersPerBin : 1) != MDA_OK) return nullptr;
+    return s->h_params;
+}
+double *mdaStoreHostOut(void *store, int walkersPerBin) {
+    MdaStore *s = as_store(store, "mdaStoreHostOut");
+    if (!s || walkersPerBin < 0) return nullptr;
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    if (ensure_staging(s, walkersPerBin > 0 ? walkersPerBin : 1) != MDA_OK) return nullptr;
+    return s->h_out;
+}
+int mdaBatchLnPostStaged(void *store, int walkersPerBin) { return eval_staged(store, walkersPerBin, kLnPost, "mdaBatchLnPostStaged"); }
+int mdaBatchChiStaged(void *store, int walkersPerBin) { return eval_staged(store, walkersPerBin, kChi, "mdaBatchChiStaged"); }
+
+int mdaBatchLnPostDevice(void *store, int walkersPerBin, const double *dParams, double *dLnPost) {
+    return eval_device(store, walkersPerBin, dParams, dLnPost, kLnPost, "mdaBatchLnPostDevice");
+}
+int mdaBatchChiDevice(void *store, int walkersPerBin, const double *dParams, double *dChi) {
+    return eval_device(store, walkersPerBin, dParams, dChi, kChi, "mdaBatchChiDevice");
+}
+int mdaBatchLnPostDeviceMany(void *store, int walkersPerBin, const double *const *dParams, double *const *dOut,
+                             int nBlocks, int count) {
+    MdaStore *s = as_store(store, "mdaBatchLnPostDeviceMany");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    if (nBlocks <= 0 || count < 0 || !dParams || !dOut) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaBatchLnPostDeviceMany: bad block list");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    if (walkersPerBin <= 0 || s->bins == 0) return MDA_OK;
+    if ((rc = upload_store(s))) return rc;
+    for (int i = 0; i < count; ++i)
+        if ((rc = enqueue_eval(s, walkersPerBin, dParams[i % nBlocks], dOut[i % nBlocks], kLnPost))) return rc;
+    return MDA_OK;
+}
+
+int mdaStoreSynchronize(void *store) {
+    MdaStore *s = as_store(store, "mdaStoreSynchronize");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MDA_CUDA(cudaStreamSynchronize(s->stream), "mdaStoreSynchronize");
+    return MDA_OK;
+}
+
+// ---- events -------------------------------------------------------------------------------
+void *mdaEventCreate(void) {
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) { cuda_fail(e, "mdaEventCreate"); return nullptr; }
+    return ev;
+}
+void mdaEventDestroy(void *event) { if (event) cudaEventDestroy(static_cast<cudaEvent_t>(event)); }
+int mdaEventRecord(void *event, void *store) {
+    MdaStore *s = as_store(store, "mdaEventRecord");
+    if (!s || !event) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEventRecord: NULL argument");
+    MDA_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), s->stream), "mdaEventRecord");
+    return MDA_OK;
+}
+int mdaEventSynchronize(void *event) {
+    if (!event) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEventSynchronize: NULL event");
+    MDA_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)), "mdaEventSynchronize");
+    return MDA_OK;
+}
+int mdaEventElapsedMs(void *start, void *stop, float *ms) {
+    if (!start || !stop || !ms) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEventElapsedMs: NULL argument");
+    MDA_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)), "mdaEventElapsedMs");
+    return MDA_OK;
+}
+unsigned long long mdaKernelLaunchCount(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- roofline denominators -------------------------------------------------------------------
+int mdaMeasureFp64Peak(int repeats, double *tflops) {
+    if (!tflops) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaMeasureFp64Peak: NULL result");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MDA_CUDA(measure_fp64_peak(repeats, g_rt.sm_count, tflops), "fp64 peak microbenchmark");
+    g_launches.fetch_add((unsigned long long)(repeats > 0 ? repeats : 1) + 1ull, std::memory_order_relaxed);
+    return MDA_OK;
+}
+int mdaMeasureHbmCopy(size_t bytes, int repeats, double *gbs) {
+    if (!gbs || bytes == 0) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaMeasureHbmCopy: bad argument");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MDA_CUDA(measure_hbm_copy(bytes, repeats, gbs), "HBM copy microbenchmark");
+    return MDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,413 @@
+// lnpost_kernel.cu -- the batched chi-square log-posterior kernel for sm_100a.
+//
+// Replaces, for every (Ex bin, walker) pair of one launch, the reference's
+//   ln_post_prob            mda.py:1540-1578      (flat box prior -> -inf)
+//   calculateLnLiklihood    C/ChiSquare.c:176-213 (r_j = d_j - sum_l a_l D_lj; -chi^2/2)
+//   calculateChi            C/ChiSquare.c:114-172
+//
+// Work decomposition (fp64 DFMA-pipe bound):
+//   * one CTA = one bin x one tile of walkers; a thread owns WPT walkers and keeps
+//     their L parameters in registers (L is a template parameter), so the inner loop
+//     is pure DFMA fed by broadcast LDS.128 (one 16-byte shared load feeds 2*WPT DFMAs);
+//   * the bin's constants live in HBM angle-pair-major: consts[bin][n_pad/2][1+L][2]
+//     (for an angle pair: data pair, then dist_0 pair ... dist_{L-1} pair).  That block
+//     (or a chunk of it when it does not fit) is brought into shared memory by ONE
+//     bulk-TMA copy (cp.async.bulk ... mbarrier::complete_tx) issued by one thread;
+//   * the tile's walker parameters [tile][L] are gathered with coalesced 8-byte
+//     cp.async into rows padded to an odd stride, so the per-thread row reads that
+//     follow are bank-conflict free for every L;
+//   * per walker the operation order is exactly the reference's: residual updates in
+//     ascending l, squares accumulated in ascending j from 0, one multiply by -1/2.
+//     No cross-lane reduction exists, so results are independent of the tiling.
+//
+// Tensor cores are deliberately not used: the contraction is K = L <= 16 deep in fp64.
+#include "mda_kernels.cuh"
+
+#include <math_constants.h>
+
+namespace mda {
+
+namespace {
+
+// ---- PTX helpers (sm_90+: mbarrier transactions, bulk async copies) ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MDA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MDA_DONE;\n"
+        "bra MDA_WAIT;\n"
+        "MDA_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ double finish(double chi, bool outside, int mode) {
+    if (mode == kChi) return chi;
+    const double lnl = chi * -0.5;                       // == chi / (-2.0) exactly
+    return (mode == kLnPost && outside) ? -CUDART_INF : lnl;
+}
+
+// Largest chunk of staged constants a single bulk copy may carry (tx-count limit is
+// 2^20-1 bytes per mbarrier phase); chunks are always far below this.
+constexpr uint32_t kMaxBulkBytes = 1u << 19;
+
+// ---- register-tiled kernel: L in registers --------------------------------------
+template <int L, int WPT>
+__global__ void __launch_bounds__(256) lnpost_tile_kernel(const BatchArgs args) {
+    constexpr int LP = L | 1;          // odd row stride (doubles) of the staged parameters
+    constexpr int ROW = L + 1;         // double2 entries per angle pair: data, dist_0..dist_{L-1}
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int tid = threadIdx.x;
+    const int T = blockDim.x;
+    const int tile_w = T * WPT;
+    const int bin = blockIdx.x / args.tiles_per_bin;
+    const int tile = blockIdx.x - bin * args.tiles_per_bin;
+    const int w0 = tile * tile_w;
+    const int nw = min(tile_w, args.walkers - w0);
+    const int chunk = args.chunk;                    // angle columns per staged chunk (even)
+    const int n_pad = args.n_pad;
+
+    double2 *sC = reinterpret_cast<double2 *>(smem_raw);                    // [chunk/2][ROW]
+    double *sP = reinterpret_cast<double *>(smem_raw) + (size_t)chunk * ROW;  // [tile_w][LP]
+
+    const double2 *gC = reinterpret_cast<const double2 *>(args.consts) + (size_t)bin * (n_pad / 2) * ROW;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // constants of the first chunk: one bulk copy, issued before anything else
+    const int first_cols = min(chunk, n_pad);
+    if (tid == 0 && first_cols > 0) {
+        const uint32_t bytes = (uint32_t)first_cols * ROW * 8u;
+        mbar_arrive_expect_tx(&mbar, bytes);
+        bulk_g2s(sC, gC, bytes, &mbar);
+    }
+
+    // this tile's walker parameters: coalesced 8-byte async copies into padded rows
+    {
+        const double *gP = args.params + ((size_t)bin * args.walkers + w0) * L;
+        const int count = nw * L;
+        for (int i = tid; i < count; i += T) {
+            const int w = i / L;
+            const int l = i - w * L;
+            cp_async_8(&sP[w * LP + l], gP + i);
+        }
+    }
+    const int n = args.n_pts[bin];                   // latency overlaps the copies above
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    double a[WPT][L];
+    bool outside[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+        const int w = min(tid + k * T, nw - 1);      // clamp: idle slots repeat the last walker
+        outside[k] = false;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            a[k][l] = sP[w * LP + l];
+            // mda.py:1575 -- "params[i] < lo or params[i] > hi"; NaN compares false
+            outside[k] = outside[k] || (a[k][l] < args.lo[l]) || (a[k][l] > args.hi[l]);
+        }
+    }
+
+    double chi[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) chi[k] = 0.0;
+
+    uint32_t parity = 0;
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+        if (c0 > 0) {
+            __syncthreads();                          // every thread is done with the old chunk
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)min(chunk, n_pad - c0) * ROW * 8u;
+                mbar_arrive_expect_tx(&mbar, bytes);
+                bulk_g2s(sC, gC + (size_t)(c0 / 2) * ROW, bytes, &mbar);
+            }
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1u;
+
+        const int valid = min(chunk, n - c0);         // real angles in this chunk
+        const int pairs = valid >> 1;
+        const double2 *p = sC;
+#pragma unroll 2
+        for (int j2 = 0; j2 < pairs; ++j2, p += ROW) {
+            const double2 dv = p[0];
+            double r0[WPT], r1[WPT];
+#pragma unroll
+            for (int k = 0; k < WPT; ++k) { r0[k] = dv.x; r1[k] = dv.y; }
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const double2 D = p[1 + l];
+#pragma unroll
+                for (int k = 0; k < WPT; ++k) {
+                    r0[k] = fma(-a[k][l], D.x, r0[k]);     // C/ChiSquare.c:190,200
+                    r1[k] = fma(-a[k][l], D.y, r1[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < WPT; ++k) {
+                chi[k] = fma(r0[k], r0[k], chi[k]);        // C/ChiSquare.c:209, ascending j
+                chi[k] = fma(r1[k], r1[k], chi[k]);
+            }
+        }
+        if (valid & 1) {                               // last, unpaired angle of the bin
+            const double dv = p[0].x;
+            double r0[WPT];
+#pragma unroll
+            for (int k = 0; k < WPT; ++k) r0[k] = dv;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const double Dx = p[1 + l].x;
+#pragma unroll
+                for (int k = 0; k < WPT; ++k) r0[k] = fma(-a[k][l], Dx, r0[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < WPT; ++k) chi[k] = fma(r0[k], r0[k], chi[k]);
+        }
+    }
+    // a bin with n == 0 never waited on the first chunk's copy: drain it before exit
+    if (n <= 0 && first_cols > 0) mbar_wait(&mbar, 0);
+
+    double *out = args.out + (size_t)bin * args.walkers + w0;
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+        const int w = tid + k * T;
+        if (w < nw) out[w] = finish(chi[k], outside[k], args.mode);
+    }
+}
+
+// ---- generic kernel: any L, parameters stay in shared memory ---------------------
+__global__ void __launch_bounds__(256) lnpost_generic_kernel(const BatchArgs args, const double *__restrict__ lo,
+                                                            const double *__restrict__ hi) {
+    const int L = args.n_l;
+    const int LP = L | 1;
+    const int ROW = L + 1;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int tid = threadIdx.x;
+    const int T = blockDim.x;
+    const int bin = blockIdx.x / args.tiles_per_bin;
+    const int tile = blockIdx.x - bin * args.tiles_per_bin;
+    const int w0 = tile * T;
+    const int nw = min(T, args.walkers - w0);
+    const int chunk = args.chunk;
+    const int n_pad = args.n_pad;
+
+    double2 *sC = reinterpret_cast<double2 *>(smem_raw);
+    double *sP = reinterpret_cast<double *>(smem_raw) + (size_t)chunk * ROW;
+    const double2 *gC = reinterpret_cast<const double2 *>(args.consts) + (size_t)bin * (n_pad / 2) * ROW;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int first_cols = min(chunk, n_pad);
+    if (tid == 0 && first_cols > 0) {
+        const uint32_t bytes = (uint32_t)first_cols * ROW * 8u;
+        mbar_arrive_expect_tx(&mbar, bytes);
+        bulk_g2s(sC, gC, bytes, &mbar);
+    }
+    {
+        const double *gP = args.params + ((size_t)bin * args.walkers + w0) * L;
+        const int count = nw * L;
+        for (int i = tid; i < count; i += T) {
+            const int w = i / L;
+            const int l = i - w * L;
+            cp_async_8(&sP[w * LP + l], gP + i);
+        }
+    }
+    const int n = args.n_pts[bin];
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    const double *my = sP + (size_t)min(tid, nw - 1) * LP;
+    bool outside = false;
+    for (int l = 0; l < L; ++l) outside = outside || (my[l] < lo[l]) || (my[l] > hi[l]);
+
+    double chi = 0.0;
+    uint32_t parity = 0;
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+        if (c0 > 0) {
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)min(chunk, n_pad - c0) * ROW * 8u;
+                mbar_arrive_expect_tx(&mbar, bytes);
+                bulk_g2s(sC, gC + (size_t)(c0 / 2) * ROW, bytes, &mbar);
+            }
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1u;
+        const int valid = min(chunk, n - c0);
+        const int pairs = valid >> 1;
+        const double2 *p = sC;
+        for (int j2 = 0; j2 < pairs; ++j2, p += ROW) {
+            double r0 = p[0].x, r1 = p[0].y;
+            for (int l = 0; l < L; ++l) {
+                const double al = my[l];
+                const double2 D = p[1 + l];
+                r0 = fma(-al, D.x, r0);
+                r1 = fma(-al, D.y, r1);
+            }
+            chi = fma(r0, r0, chi);
+            chi = fma(r1, r1, chi);
+        }
+        if (valid & 1) {
+            double r0 = p[0].x;
+            for (int l = 0; l < L; ++l) r0 = fma(-my[l], p[1 + l].x, r0);
+            chi = fma(r0, r0, chi);
+        }
+    }
+    if (n <= 0 && first_cols > 0) mbar_wait(&mbar, 0);
+    if (tid < nw) args.out[(size_t)bin * args.walkers + w0 + tid] = finish(chi, outside, args.mode);
+}
+
+// ---- dispatch ---------------------------------------------------------------------
+using TileKernel = void (*)(const BatchArgs);
+
+template <int L>
+TileKernel pick_wpt(int wpt) {
+    switch (wpt) {
+        case 1: return lnpost_tile_kernel<L, 1>;
+        case 2: return lnpost_tile_kernel<L, 2>;
+        case 4: return lnpost_tile_kernel<L, 4>;
+        default: return nullptr;
+    }
+}
+
+TileKernel pick_kernel(int n_l, int wpt) {
+    switch (n_l) {
+        case 1: return pick_wpt<1>(wpt);
+        case 2: return pick_wpt<2>(wpt);
+        case 3: return pick_wpt<3>(wpt);
+        case 4: return pick_wpt<4>(wpt);
+        case 5: return pick_wpt<5>(wpt);
+        case 6: return pick_wpt<6>(wpt);
+        case 7: return pick_wpt<7>(wpt);
+        case 8: return pick_wpt<8>(wpt);
+        case 9: return pick_wpt<9>(wpt);
+        case 10: return pick_wpt<10>(wpt);
+        case 11: return pick_wpt<11>(wpt);
+        case 12: return pick_wpt<12>(wpt);
+        case 13: return pick_wpt<13>(wpt);
+        case 14: return pick_wpt<14>(wpt);
+        case 15: return pick_wpt<15>(wpt);
+        case 16: return pick_wpt<16>(wpt);
+        default: return nullptr;
+    }
+}
+
+inline int round_down_even(long v) { return (int)(v & ~1L); }
+
+}  // namespace
+
+TileShape choose_tile(int bins, int walkers, int n_l, int n_pad, int sm_count, size_t smem_optin,
+                      int force_threads, int force_wpt) {
+    TileShape t{};
+    int threads = force_threads, wpt = force_wpt;
+    const bool generic = n_l > kMaxRegL;
+    if (generic) wpt = 1;
+    if (threads <= 0 || wpt <= 0) {
+        // Heuristic: the largest register tile that still leaves every SM a few CTAs
+        // to overlap staging with arithmetic; small launches fall back to small tiles
+        // so the work spreads over all 148 SMs.
+        static const int cand[][2] = {{128, 2}, {64, 2}, {64, 1}, {32, 1}};
+        const int walkers32 = (walkers + 31) / 32 * 32;
+        int pick = 3;
+        for (int c = 0; c < 4; ++c) {
+            const int tw = cand[c][0] * (generic ? 1 : cand[c][1]);
+            if (tw > walkers32 && c < 3) continue;
+            const long tiles = (long)bins * ((walkers + tw - 1) / tw);
+            if (tiles >= 2L * sm_count || c == 3) { pick = c; break; }
+        }
+        if (threads <= 0) threads = cand[pick][0];
+        if (wpt <= 0) wpt = generic ? 1 : cand[pick][1];
+    }
+    const int tile_w = threads * wpt;
+    const int lp = n_l | 1;
+    const size_t params_bytes = (size_t)tile_w * lp * 8;
+    const size_t row_bytes = (size_t)(n_l + 1) * 8;     // per angle column
+    // keep the staged constants <= 96 KB so at least two CTAs fit on an SM
+    size_t budget = 96u * 1024u;
+    if (params_bytes + budget + 64 > smem_optin) budget = smem_optin > params_bytes + 64 ? smem_optin - params_bytes - 64 : 0;
+    int chunk = round_down_even((long)(budget / row_bytes));
+    if (chunk > n_pad) chunk = n_pad;
+    if (chunk < 2) chunk = 2;
+    t.threads = threads;
+    t.wpt = wpt;
+    t.chunk = chunk;
+    t.grid = bins * ((walkers + tile_w - 1) / tile_w);
+    t.smem_bytes = (size_t)chunk * row_bytes + params_bytes;
+    return t;
+}
+
+cudaError_t configure_kernels(size_t smem_optin) {
+    static const int wpts[3] = {1, 2, 4};
+    for (int l = 1; l <= kMaxRegL; ++l)
+        for (int i = 0; i < 3; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(pick_kernel(l, wpts[i])),
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaFuncSetAttribute(reinterpret_cast<const void *>(lnpost_generic_kernel),
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+}
+
+cudaError_t launch_batch(BatchArgs &args, const TileShape &tile, cudaStream_t stream, const double *lo_dev,
+                         const double *hi_dev) {
+    if (args.bins <= 0 || args.walkers <= 0) return cudaSuccess;
+    const int tile_w = tile.threads * tile.wpt;
+    args.tiles_per_bin = (args.walkers + tile_w - 1) / tile_w;
+    args.chunk = tile.chunk;
+    if ((size_t)tile.chunk * (args.n_l + 1) * 8 > kMaxBulkBytes) return cudaErrorInvalidValue;
+    if (args.n_l <= kMaxRegL) {
+        TileKernel k = pick_kernel(args.n_l, tile.wpt);
+        if (!k) return cudaErrorInvalidValue;
+        k<<<tile.grid, tile.threads, tile.smem_bytes, stream>>>(args);
+    } else {
+        if (!lo_dev || !hi_dev) return cudaErrorInvalidValue;
+        lnpost_generic_kernel<<<tile.grid, tile.threads, tile.smem_bytes, stream>>>(args, lo_dev, hi_dev);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mda

@@ -1,0 +1,64 @@
+// mda_kernels.cuh -- internal launch interface between the C ABI (chisq_abi.cu)
+// and the sm_100a kernels (lnpost_kernel.cu, scalar_kernel.cu, peaks.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mda {
+
+constexpr int kMaxRegL = 16;        // largest numL the register-tiled kernel is instantiated for
+
+enum EvalMode : int {
+    kLnPost = 0,   // box prior (-inf outside) then chi^2 / -2   (mda.py:1574-1578)
+    kChi = 1,      // chi^2, no prior                            (C/ChiSquare.c:114-172)
+    kLnLike = 2    // chi^2 / -2, no prior                       (C/ChiSquare.c:176-213)
+};
+
+// One batched evaluation: every bin x walkers_per_bin walkers.
+struct BatchArgs {
+    const double *consts;   // [bins][n_pad/2][1+L][2]  per angle pair: data pair, dist_0 pair, ...
+    const int *n_pts;       // [bins]               real angle count per bin (<= n_pad)
+    const double *params;   // [bins][walkers][L]
+    double *out;            // [bins][walkers]
+    int bins;
+    int walkers;            // per bin in this launch
+    int n_l;
+    int n_pad;              // even
+    int tiles_per_bin;
+    int chunk;              // angle columns staged in shared memory at a time (even)
+    int mode;               // EvalMode
+    double lo[kMaxRegL];    // box prior, used by the register-tiled kernel (numL <= kMaxRegL)
+    double hi[kMaxRegL];
+};
+
+struct TileShape {
+    int threads;            // per CTA
+    int wpt;                // walkers per thread (register tile)
+    int grid;               // CTAs
+    int chunk;              // angle chunk (even)
+    size_t smem_bytes;      // dynamic shared memory
+};
+
+// Picks the tiling for a launch (force_threads / force_wpt = 0 -> heuristic).
+TileShape choose_tile(int bins, int walkers, int n_l, int n_pad, int sm_count,
+                      size_t smem_optin, int force_threads, int force_wpt);
+
+// Enqueue one batched evaluation.  args.tiles_per_bin / args.chunk are filled in.
+// lo_dev / hi_dev ([numL], device) are only read when numL > kMaxRegL.
+cudaError_t launch_batch(BatchArgs &args, const TileShape &tile, cudaStream_t stream,
+                         const double *lo_dev, const double *hi_dev);
+
+// One-time per device: raise the dynamic shared memory limit of every instantiation.
+cudaError_t configure_kernels(size_t smem_optin);
+
+// Legacy scalar path (one bin, one parameter vector), see scalar_kernel.cu.
+//   consts [1+L][n] dense (row 0 data, rows 1..L dists), params[L], result[0] = value,
+//   resid (may be null) [n]
+cudaError_t launch_scalar(const double *consts, int n, int n_l, const double *params,
+                          double *result, double *resid, int mode, cudaStream_t stream);
+
+// Roofline denominators, see peaks.cu.
+cudaError_t measure_fp64_peak(int repeats, int sm_count, double *tflops);
+cudaError_t measure_hbm_copy(size_t bytes, int repeats, double *gbs);
+
+}  // namespace mda
