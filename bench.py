@@ -1,0 +1,542 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood evals/s (walker x Ex-bin) of the batched chi-square
+log-posterior path, with its roofline and the reference's CPU path beside it.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Launched by the driver as ``python -m torch.distributed.run --nproc-per-node N ...
+bench.py --gpus N ...`` for N > 1: one process per GPU, Ex bins partitioned
+round-robin over ranks, no data-path collective; torch.distributed is
+used for the barrier and the max-over-ranks of the device timings only.
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): per GPU
+200 Ex bins x 512 walkers x 9 distributions x 60 angles, fp64, synthetic seeded inputs
+(mimic_mda_b200/synth.py).  A *step* is one ensemble step of every bin: two dependent
+half-ensemble launches of [bins][256][9] parameter vectors (the two halves of the
+stretch move, mda.py:1128-1131), i.e. bins x 512 likelihood evaluations.
+
+  value  evals/s with parameter blocks already resident in HBM (CUDA events on the
+         launching stream; a ring of distinct blocks larger than 2x L2 so that every
+         launch reads its parameters from HBM).
+  e2e    evals/s through the C-ABI staged call with HOST buffers: every half-step
+         copies its [bins][256][9] block from pinned host memory, runs the kernel
+         and copies [bins][256] results back (one captured CUDA graph per call).
+  roofline       the likelihood kernel against the fp64 FMA pipe (measured live by a
+                 DFMA microbenchmark) and against HBM (MEASURED_PEAKS.json).
+  cpu_baseline   the unmodified reference library (oracle/_ref) through the Python
+                 ctypes path of mda.py:1540-1578 on all host cores (N = 1, rank 0).
+"""
+import argparse
+import ctypes as ct
+import json
+import multiprocessing
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mimic_mda_b200 import shard, synth  # noqa: E402
+
+METRIC = "likelihood evals/sec (walker x Ex-bin)"
+UNIT = "evals/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", default="C4", help="C2 | C3 | C4 (default: the metric's config)")
+    ap.add_argument("--bins", type=int, default=0, help="override Ex bins per GPU")
+    ap.add_argument("--walkers", type=int, default=0, help="override walkers per bin")
+    ap.add_argument("--n-l", type=int, default=0)
+    ap.add_argument("--n-pts", type=int, default=0)
+    ap.add_argument("--tile", default="", help="force kernel tiling THREADSxWPT, e.g. 64x2")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 200-bins-total strong-scaling companion run")
+    return ap.parse_args()
+
+
+def workload_shape(args):
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.bins:
+        cfg["bins"] = args.bins
+    if args.walkers:
+        cfg["walkers"] = args.walkers
+    if args.n_l:
+        cfg["n_l"] = args.n_l
+    if args.n_pts:
+        cfg["n_pts"] = args.n_pts
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md, "clocks line")
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation of the path on the host cores
+# ------------------------------------------------------------------------------------------
+_CPU_STATE = {}
+
+
+def _cpu_worker_init(lib_path, consts, n_pts, lo, hi, params):
+    """Runs inside each pool worker: the library is loaded in the worker, as the
+    reference does (mda.py:1109), and one struct per bin is built on first use."""
+    from oracle import reflib
+    _CPU_STATE.update(lib=reflib.prepare_shared_object(lib_path), reflib=reflib, consts=consts, n_pts=n_pts,
+                      bounds=[(float(l), float(h)) for l, h in zip(lo, hi)], params=params)
+
+
+def _cpu_worker_bin(task):
+    """One Ex bin: emcee's per-walker calls of ln_post_prob (mda.py:1540-1578)."""
+    b, reps = task
+    st = _CPU_STATE
+    reflib, lib = st["reflib"], st["lib"]
+    n = int(st["n_pts"][b])
+    n_l = st["params"].shape[2]
+    struct = reflib.make_calc_struct(lib, st["consts"][b, 0, :n], [st["consts"][b, 1 + l, :n] for l in range(n_l)])
+    rows = [st["params"][b, w] for w in range(st["params"].shape[1])]
+    bounds = st["bounds"]
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(reps):
+        for row in rows:
+            v = reflib.ln_post_prob(row, lib, struct, bounds)
+            if v > -1e300:
+                acc += v
+    dt = time.perf_counter() - t0
+    lib.freeMdaStruct(struct)
+    return dt, acc
+
+
+def cpu_reference_arm(cfg, cpu_seconds, consts=None, n_pts=None, params=None):
+    """Times the reference path on a bounded sample of the workload.  Returns a dict."""
+    from oracle import reflib
+    if not os.path.exists(reflib.ORACLE_LIB) or not os.path.exists(reflib.REF_LOOP_LIB):
+        reflib.build()
+    lib_path = reflib.reference_lib_path()
+    kind = "reference"
+    if lib_path is None:                      # the reference build did not travel / does not run here
+        lib_path, kind = reflib.ORACLE_LIB, "port"
+    cores = os.cpu_count() or 1
+    n_l, n_ang, walkers = cfg["n_l"], cfg["n_pts"], cfg["walkers"]
+    sample_bins = min(cfg["bins"], max(cores, 8))
+    if consts is None:
+        consts, n_pts, a_true = synth.make_bins(sample_bins, n_l, n_ang)
+        params = synth.make_walkers(a_true, walkers, seed=7)
+    else:
+        consts, n_pts, params = consts[:sample_bins], n_pts[:sample_bins], params[:sample_bins]
+    lo, hi = synth.default_bounds(n_l)
+    # calibrate on one bin in this process, then size the sample to ~cpu_seconds of CPU work
+    _cpu_worker_init(lib_path, consts, n_pts, lo, hi, params)
+    dt1, _ = _cpu_worker_bin((0, 1))
+    per_eval = dt1 / walkers
+    reps = max(1, int(cpu_seconds / max(per_eval * walkers * sample_bins, 1e-9)))
+    tasks = [(b, reps) for b in range(sample_bins)]
+    ctx = multiprocessing.get_context("fork")
+    with ctx.Pool(processes=min(cores, sample_bins), initializer=_cpu_worker_init,
+                  initargs=(lib_path, consts, n_pts, lo, hi, params)) as pool:
+        pool.map(_cpu_worker_bin, [(b, 1) for b in range(sample_bins)])          # warm-up
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker_bin, tasks)
+        wall = time.perf_counter() - t0
+    evals = sample_bins * walkers * reps
+    # secondary honesty line: the same library in a tight C loop (no Python in the way)
+    loop = reflib.RefLoop(lib_path)
+    _, s1 = loop.run(consts, n_pts, lo, hi, params, n_threads=1, repeats=1)
+    c_reps = max(1, int(1.0 / max(s1, 1e-6)))
+    _, s_one = loop.run(consts, n_pts, lo, hi, params, n_threads=1, repeats=c_reps)
+    _, s_all = loop.run(consts, n_pts, lo, hi, params, n_threads=min(cores, sample_bins), repeats=c_reps * min(cores, sample_bins))
+    n_c = sample_bins * walkers
+    return {
+        "value": evals / wall, "unit": UNIT, "cores": min(cores, sample_bins), "kind": kind,
+        "sample": "%d of %d bins x %d walkers x %d passes, L=%d N=%d; per-walker ln_post_prob -> ctypes -> "
+                  "calculateLnLiklihood (mda.py:1540-1578), multiprocessing.Pool over bins (mda.py:186-188)"
+                  % (sample_bins, cfg["bins"], walkers, reps, n_l, n_ang),
+        "library": os.path.relpath(lib_path, ROOT),
+        "seconds": wall, "evals": evals,
+        "per_core_python_evals_per_s": 1.0 / per_eval,
+        "pure_c_evals_per_s_1core": n_c * c_reps / s_one,
+        "pure_c_evals_per_s_allcores": n_c * c_reps * min(cores, sample_bins) / s_all,
+        "host_cpu": _cpu_model(), "host_cores_total": cores,
+    }
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference_impl(args, cfg, rank, world):
+    """--impl reference: the reference's CPU implementation, same metric/config/JSON line."""
+    if rank != 0:
+        return
+    base = cpu_reference_arm(cfg, args.cpu_seconds)
+    evals_step = cfg["bins"] * cfg["walkers"] * world
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * evals_step / base["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(cfg, world, "reference CPU path on host cores; bounded sample, see cpu_baseline.sample"),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(cfg, world, note):
+    return {
+        "workload": "%s: %d Ex bins/GPU x %d walkers x %d dists x %d angles (BASELINE.json configs[%s])"
+                    % (cfg.get("name", "C4"), cfg["bins"], cfg["walkers"], cfg["n_l"], cfg["n_pts"],
+                       {"C1": 0, "C2": 1, "C3": 2, "C4": 3}.get(cfg.get("name", "C4"), "?")),
+        "bins_per_gpu": cfg["bins"], "bins_total": cfg["bins"] * world, "walkers": cfg["walkers"],
+        "dists": cfg["n_l"], "angles": cfg["n_pts"], "walkers_per_launch": cfg["walkers"] // 2,
+        "launches_per_step": 2, "partition": "bins round-robin over ranks, no collective",
+        "l2_policy": "inputs larger than L2: ring of distinct parameter blocks > 2x126 MB",
+        "note": note,
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed used as plumbing only: barrier + max over ranks."""
+
+    def __init__(self, world, local_rank):
+        self.world = world
+        self.torch = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            try:
+                torch.cuda.set_device(local_rank)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+                self.device = torch.device("cuda", local_rank)
+            except Exception:
+                dist.init_process_group("gloo")
+                self.device = torch.device("cpu")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max(self, value):
+        if self.world == 1:
+            return value
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, value):
+        if self.world == 1:
+            return value
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+class GpuWorkload:
+    """One rank's share: store in HBM, ring of resident parameter blocks, pinned staging."""
+
+    def __init__(self, lib, cfg, rank, world, n_bins_local, first_bin, bin_step, tile):
+        from mimic_mda_b200 import chisq
+        self.lib, self.chisq, self.cfg = lib, chisq, cfg
+        self.bins, self.n_l, self.n_ang = n_bins_local, cfg["n_l"], cfg["n_pts"]
+        self.walkers, self.half = cfg["walkers"], cfg["walkers"] // 2
+        self.consts, self.n_pts, self.a_true = synth.make_bins(self.bins, self.n_l, self.n_ang,
+                                                               first_bin=first_bin, bin_step=bin_step)
+        self.lo, self.hi = synth.default_bounds(self.n_l)
+        self.store = chisq.DeviceStore(self.consts, self.n_pts, (self.lo, self.hi), cs_lib=lib)
+        if tile:
+            t, w = tile.lower().split("x")
+            self.store.set_tile(int(t), int(w))
+        self.params = synth.make_walkers(self.a_true, self.walkers, seed=7 + rank)     # [B, W, L]
+        self.block_bytes = self.bins * self.half * self.n_l * 8
+        self.out_bytes = self.bins * self.half * 8
+        n_ring = max(4, int(2 * L2_BYTES / max(self.block_bytes, 1)) + 1)
+        self.n_ring = n_ring + (n_ring & 1)
+        self.d_params, self.d_out = [], []
+        rng = np.random.default_rng(99 + rank)
+        halves = [np.ascontiguousarray(self.params[:, :self.half]), np.ascontiguousarray(self.params[:, self.half:])]
+        for i in range(self.n_ring):
+            blk = halves[i & 1]
+            if i >= 2:      # distinct contents per block: jitter inside the box
+                blk = np.clip(blk + 1e-3 * rng.standard_normal(blk.shape), self.lo, self.hi)
+            dp = lib.mdaDeviceAlloc(self.block_bytes)
+            do = lib.mdaDeviceAlloc(self.out_bytes)
+            if not dp or not do:
+                raise chisq.MdaError(lib.mdaLastError(), lib.mdaLastErrorString().decode())
+            chisq.check(lib, lib.mdaMemcpyH2D(dp, blk.ctypes.data, self.block_bytes))
+            self.d_params.append(dp)
+            self.d_out.append(do)
+        self.ev0, self.ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
+        self.stage_p, self.stage_o = self.store.staging(self.half)
+        self.halves = halves
+
+    def evals_per_step(self):
+        return self.bins * self.walkers
+
+    def resident(self, steps):
+        """Enqueue 2*steps launches over the ring; returns elapsed ms (CUDA events)."""
+        lib = self.lib
+        self.chisq.check(lib, lib.mdaEventRecord(self.ev0, self.store.handle))
+        self.store.lnpost_device_many(self.half, self.d_params, self.d_out, 2 * steps)
+        self.chisq.check(lib, lib.mdaEventRecord(self.ev1, self.store.handle))
+        self.chisq.check(lib, lib.mdaEventSynchronize(self.ev1))
+        ms = ct.c_float()
+        self.chisq.check(lib, lib.mdaEventElapsedMs(self.ev0, self.ev1, ct.byref(ms)))
+        return float(ms.value)
+
+    def e2e(self, steps):
+        """steps x 2 staged calls (H2D from pinned host, kernel, D2H, sync); wall seconds."""
+        self.store.synchronize()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for _ in range(steps):
+            for h in (0, 1):
+                self.store.lnpost_staged(self.half)
+                acc += self.stage_o[0, 0]                 # the step's result is read on the host
+        self.store.synchronize()
+        return time.perf_counter() - t0, acc
+
+    def check_against(self, oracle):
+        """Parity gate in the same run: resident block 0/1 and the staged path vs the oracle."""
+        want = [oracle.lnpost_bins(self.consts, self.n_pts, self.lo, self.hi, h) for h in self.halves]
+        worst = 0.0
+        for i in (0, 1):
+            got = np.empty((self.bins, self.half))
+            self.chisq.check(self.lib, self.lib.mdaMemcpyD2H(got.ctypes.data, self.d_out[i], got.nbytes))
+            if not np.array_equal(np.isneginf(got), np.isneginf(want[i])):
+                raise AssertionError("-inf positions differ from the oracle")
+            fin = np.isfinite(want[i])
+            worst = max(worst, float(np.max(np.abs(got[fin] - want[i][fin]) / np.abs(want[i][fin]))))
+        return worst
+
+    def close(self):
+        for p in self.d_params + self.d_out:
+            self.lib.mdaDeviceFree(p)
+        self.lib.mdaEventDestroy(self.ev0)
+        self.lib.mdaEventDestroy(self.ev1)
+        self.store.close()
+
+
+def measure(work, dist, steps, warmup):
+    """Barrier + sync on both sides, exactly `steps` timed steps, max over ranks."""
+    work.resident(max(warmup, 3))
+    work.store.synchronize()
+    dist.barrier()
+    ms = work.resident(steps)
+    work.store.synchronize()
+    dist.barrier()
+    ms = dist.max(ms)
+    # end to end: fill staging once per half (what the sampler writes proposals into)
+    work.stage_p[...] = work.halves[0]
+    work.e2e(max(min(warmup, 20), 3))
+    dist.barrier()
+    e2e_steps = steps if steps <= 200 else max(200, steps // 10)
+    secs, _ = work.e2e(e2e_steps)
+    dist.barrier()
+    secs = dist.max(secs)
+    return ms, secs, e2e_steps
+
+
+def main():
+    args = parse_args()
+    rank, local_rank, world = shard.rank_and_world()
+    cfg = workload_shape(args)
+    cfg["name"] = args.workload
+    if cfg["walkers"] % 2:
+        raise SystemExit("walkers must be even (two half-ensembles)")
+    if args.impl == "reference":
+        run_reference_impl(args, cfg, rank, world)
+        return
+
+    os.environ.setdefault("LOCAL_RANK", str(local_rank))
+    from mimic_mda_b200 import chisq
+    lib = chisq.prepare_shared_object()               # raises if the CUDA library is missing
+    if lib.mdaDeviceCount() < 1:
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dist = Dist(world, local_rank)
+    name = ct.create_string_buffer(128)
+    sms, cc = ct.c_int(), ct.c_int()
+    chisq.check(lib, lib.mdaDeviceInfo(name, 128, ct.byref(sms), ct.byref(cc)))
+
+    # weak scaling: every GPU owns cfg["bins"] bins (global bin index = rank + k*world)
+    work = GpuWorkload(lib, cfg, rank, world, cfg["bins"], rank, world, args.tile)
+    tile = work.store.get_tile(work.half)
+
+    peak_tf = ct.c_double()
+    chisq.check(lib, lib.mdaMeasureFp64Peak(5, ct.byref(peak_tf)))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+
+    launches0 = lib.mdaKernelLaunchCount()
+    sampler = ClockSampler(lib.mdaGetDevice())
+    ms, e2e_secs, e2e_steps = measure(work, dist, args.steps, args.warmup)
+    timed_launches = 2 * args.steps
+    # keep the same load running while nvidia-smi samples (the timed region is milliseconds long)
+    t_end = time.perf_counter() + 1.0
+    while time.perf_counter() < t_end:
+        work.resident(500)
+    clocks = sampler.stop()
+    total_launches = lib.mdaKernelLaunchCount() - launches0
+
+    # parity gate on the very blocks that were timed
+    from oracle import reflib
+    if not os.path.exists(reflib.ORACLE_LIB):
+        reflib.build()
+    worst = work.check_against(reflib.OracleLib())
+    if worst > 1e-12:
+        raise SystemExit("bench.py: parity gate failed, max rel err %.3e" % worst)
+
+    evals_step = work.evals_per_step() * world
+    value = evals_step * args.steps / (ms * 1e-3)
+    e2e_value = evals_step * e2e_steps / e2e_secs
+    n_l, n_ang, bins, half = cfg["n_l"], cfg["n_pts"], cfg["bins"], work.half
+    dur_s = ms * 1e-3 / timed_launches                              # average launch duration
+    flops_launch = 2.0 * n_ang * (n_l + 1) * bins * half            # 2 N (L+1) per eval
+    bytes_launch = 8.0 * (n_l + 1) * bins * (half + n_ang)          # params in, lnL out, constants once
+    tf = flops_launch / dur_s / 1e12
+    gbs = bytes_launch / dur_s / 1e9
+    frac_fp64, frac_hbm = tf / peak_tf.value, gbs / hbm_peak
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",
+        "achieved": tf if frac_fp64 >= frac_hbm else gbs,
+        "peak": peak_tf.value if frac_fp64 >= frac_hbm else hbm_peak,
+        "unit": "TFLOP/s" if frac_fp64 >= frac_hbm else "GB/s",
+        "frac": max(frac_fp64, frac_hbm), "traffic": traffic,
+        "kernel": "lnpost_tile_kernel<L=%d,WPT=%d> %d threads x %d CTAs" % (n_l, tile[1], tile[0], tile[2]),
+        "launch_us": dur_s * 1e6, "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
+        "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf.value, "frac": frac_fp64,
+                 "peak_source": "DFMA microbenchmark measured in this run (mdaMeasureFp64Peak); MEASURED_PEAKS.json has no fp64 figure"},
+        "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": frac_hbm, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"},
+        "tensor_cores": "not used: skinny fp64 contraction (K = L = %d)" % n_l,
+    }
+
+    strong = None
+    if world > 1 and not args.no_strong:
+        # companion: BASELINE configs[3] literally -- 200 bins in total, sharded round-robin
+        mine = shard.bins_for_rank(cfg["bins"], rank, world)
+        sw = GpuWorkload(lib, cfg, rank, world, len(mine), rank, world, args.tile)
+        s_ms, s_secs, s_steps = measure(sw, dist, args.steps, args.warmup)
+        tot = cfg["bins"] * cfg["walkers"]
+        strong = {"bins_total": cfg["bins"], "value": tot * args.steps / (s_ms * 1e-3), "unit": UNIT,
+                  "e2e": tot * s_steps / s_secs, "ms_per_step": s_ms / args.steps}
+        sw.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_arm(cfg, args.cpu_seconds, work.consts, work.n_pts, work.params)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(cfg, world, "fp64 chi-square log-posterior, box prior in-kernel"),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bins * cfg["walkers"] * n_l * 8,
+                    "d2h_bytes_per_step": bins * cfg["walkers"] * 8, "steps": e2e_steps,
+                    "ensemble_steps_per_s": e2e_steps / e2e_secs,
+                    "path": "mdaBatchLnPostStaged: pinned host block -> H2D -> kernel -> D2H -> sync, one CUDA graph per call"},
+            "gpu_launches": timed_launches,
+            "gpu_launches_total_in_run": int(total_launches),
+            "ensemble_steps_per_s": args.steps / (ms * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "parity_max_rel_err": worst,
+            "device": {"name": name.value.decode(), "sms": sms.value, "cc": cc.value},
+        }
+        if strong is not None:
+            line["strong_200_bins_total"] = strong
+        print(json.dumps(line))
+    work.close()
+    dist.close()
+
+
+if __name__ == "__main__":
+    main()

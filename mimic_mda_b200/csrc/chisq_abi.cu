@@ -104,7 +104,8 @@ int ensure_runtime() {
     g_rt.device = dev;
     g_rt.sm_count = prop.multiProcessorCount;
     g_rt.cc = prop.major * 10 + prop.minor;
-    g_rt.smem_optin = prop.sharedMemPerBlockOptin;
+    // dynamic limit: the opt-in maximum minus room for the kernels' static shared memory (mbarrier)
+    g_rt.smem_optin = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;
     snprintf(g_rt.name, sizeof(g_rt.name), "%s", prop.name);
     MDA_CUDA(configure_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem)");
     g_rt.ready = true;

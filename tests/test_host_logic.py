@@ -1,0 +1,104 @@
+"""Host-side logic that needs no GPU: synthetic inputs, bin sharding (including a
+world_size-2 gloo run), and the batched stretch-move sampler driven by the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from mimic_mda_b200 import shard, synth
+from mimic_mda_b200.sampler import BatchedEnsembleSampler, summarize_chain
+from oracle import numpy_oracle
+
+
+def test_synth_shapes_and_padding():
+    consts, n_pts, a_true = synth.make_bins(7, 5, 31, ragged=True)
+    assert consts.shape == (7, 6, 32) and n_pts.tolist() == [31, 30, 29, 28, 27, 31, 30]
+    for b in range(7):
+        assert np.all(consts[b, :, n_pts[b]:] == 0.0) and np.all(consts[b, 1:, :n_pts[b]] > 0.0)
+    assert np.all((a_true >= 0) & (a_true <= 0.3))
+    lo, hi = synth.default_bounds(5)
+    p = synth.make_walkers(a_true, 200, oob_frac=0.05)
+    outside = numpy_oracle.outside_box(p.reshape(-1, 5), lo, hi)
+    assert 0 < outside.mean() < 0.15
+    # a rank of a round-robin partition generates exactly its own bins
+    mine, _, _ = synth.make_bins(4, 5, 31, ragged=True, first_bin=1, bin_step=2)
+    np.testing.assert_array_equal(mine[1], consts[3])
+
+
+def test_round_robin_partition_and_merge():
+    for n_bins, world in ((200, 8), (7, 2), (3, 4), (0, 2)):
+        seen = np.concatenate([shard.bins_for_rank(n_bins, r, world) for r in range(world)]) if world else []
+        assert sorted(seen.tolist()) == list(range(n_bins))
+        per_rank = [[("bin", int(b)) for b in shard.bins_for_rank(n_bins, r, world)] for r in range(world)]
+        merged = shard.merge_by_bin(n_bins, world, per_rank)
+        assert merged == [("bin", b) for b in range(n_bins)]
+    assert shard.owner_of_bin(13, 8) == 5
+    with pytest.raises(ValueError):
+        shard.bins_for_rank(10, 3, 2)
+
+
+def _oracle_logprob(consts, n_pts, lo, hi):
+    return lambda params: numpy_oracle.lnpost_bins(consts, n_pts, lo, hi, params)
+
+
+def test_sampler_bins_are_independent_streams():
+    """Running bins together must give each bin the chain of a single-bin run with the
+    same seed: only the likelihood call is batched."""
+    consts, n_pts, a_true = synth.make_bins(3, 4, 20)
+    lo, hi = synth.default_bounds(4)
+    p0 = synth.make_walkers(a_true, 16, seed=3, oob_frac=0.0)
+    both = BatchedEnsembleSampler(3, 16, 4, _oracle_logprob(consts, n_pts, lo, hi), seeds=[5, 6, 7])
+    both.run_mcmc(p0, 12)
+    for b in range(3):
+        solo = BatchedEnsembleSampler(1, 16, 4, _oracle_logprob(consts[b:b + 1], n_pts[b:b + 1], lo, hi), seeds=[5 + b])
+        solo.run_mcmc(p0[b:b + 1], 12)
+        np.testing.assert_array_equal(solo.chain[0], both.chain[b])
+        np.testing.assert_array_equal(solo.naccepted[0], both.naccepted[b])
+
+
+def test_sampler_recovers_truth_and_respects_prior():
+    consts, n_pts, a_true = synth.make_bins(2, 3, 40)
+    lo, hi = synth.default_bounds(3)
+    p0 = synth.make_walkers(a_true, 32, seed=9, oob_frac=0.0)
+    smp = BatchedEnsembleSampler(2, 32, 3, _oracle_logprob(consts, n_pts, lo, hi), seeds=100)
+    smp.run_mcmc(p0, 300)
+    assert smp.chain.shape == (2, 32, 300, 3)
+    assert np.all(smp.chain >= lo) and np.all(smp.chain <= hi)       # -inf proposals are never accepted
+    acc = smp.acceptance_fraction
+    assert 0.2 < acc.mean() < 0.9
+    summ = summarize_chain(smp.chain, burn_in=100)
+    assert np.all(np.abs(summ["p50"] - a_true) < 6 * summ["std"] + 1e-3)
+    assert np.all(np.isfinite(smp.lnprobability))
+
+
+def test_sampler_argument_checks():
+    fn = lambda p: np.zeros(p.shape[:2])
+    with pytest.raises(ValueError):
+        BatchedEnsembleSampler(1, 7, 2, fn)
+    with pytest.raises(ValueError):
+        BatchedEnsembleSampler(1, 4, 3, fn)
+    smp = BatchedEnsembleSampler(1, 8, 2, lambda p: np.full(p.shape[:2], np.nan), seeds=1)
+    with pytest.raises(ValueError):
+        smp.run_mcmc(np.random.default_rng(0).random((1, 8, 2)), 1)
+
+
+def test_two_rank_gloo_sharded_run_matches_single_process(tmp_path):
+    """world_size 2 over gloo on CPU: each rank samples its round-robin share of the
+    bins with the oracle likelihood; the gathered chains equal the 1-process run."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    out = str(tmp_path / "gloo")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, script, out], env=dict(env, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2"))
+             for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    merged = np.load(out + "_rank0.npy")
+    consts, n_pts, a_true = synth.make_bins(5, 3, 16)
+    lo, hi = synth.default_bounds(3)
+    p0 = synth.make_walkers(a_true, 12, seed=2, oob_frac=0.0)
+    ref = BatchedEnsembleSampler(5, 12, 3, _oracle_logprob(consts, n_pts, lo, hi), seeds=[40 + b for b in range(5)])
+    ref.run_mcmc(p0, 8)
+    np.testing.assert_array_equal(merged, ref.chain)
