@@ -184,7 +184,47 @@ MDA_API int   mdaEventElapsedMs(void *start, void *stop, float *ms);
 MDA_API unsigned long long mdaKernelLaunchCount(void);
 
 /* ------------------------------------------------------------------------
- * 6. Roofline denominators measured on the device this process uses
+ * 6. Device-resident ensemble sampling (replaces the per-step host loop of
+ *    emcee.EnsembleSampler.run_mcmc + ln_post_prob, mda.py:1128-1131,1540-1578)
+ *
+ * One persistent launch advances every bin's ensemble of nWalkers walkers by
+ * nSteps stretch-move steps (two half-ensemble updates per step, emcee 2.x
+ * semantics); positions, log-probabilities and the bin's constants stay in
+ * shared memory, random numbers come from Philox4x32-10 with counter
+ * (walker, bin id, 2*step+half, draw) and key = seed, so a chain depends only
+ * on (seed, bin id, start positions) -- not on launch shape or GPU count.
+ * Kept samples are appended to a chain held in HBM.
+ * --------------------------------------------------------------------- */
+MDA_API void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, double stretchA);
+MDA_API void  mdaEnsembleFree(void *ens);
+/* Global bin index of every local bin (default 0..bins-1): set it to the
+ * bin's index in the whole spectrum when bins are sharded over GPUs. */
+MDA_API int   mdaEnsembleSetBinIds(void *ens, const int *binIds);
+/* p0[bin][walker][l] (host).  Evaluates the starting log-posteriors, zeroes
+ * the acceptance counters and the step counter.  Rejects NaN/inf positions. */
+MDA_API int   mdaEnsembleSetState(void *ens, const double *p0);
+/* Room for `capacity` kept samples per bin: chain[bin][kept][walker][l] and
+ * lnprob[bin][kept][walker] in HBM.  Resets the kept count. */
+MDA_API int   mdaEnsembleReserveChain(void *ens, long long capacity);
+/* Asynchronous: advance nSteps steps, keeping every thin-th (if a chain is reserved). */
+MDA_API int   mdaEnsembleAdvance(void *ens, int nSteps, int thin);
+/* Waits; MDA_ERR_BAD_STATE if a log-probability was NaN (emcee raises there). */
+MDA_API int   mdaEnsembleSynchronize(void *ens);
+MDA_API long long mdaEnsembleSteps(void *ens);
+MDA_API long long mdaEnsembleKept(void *ens);
+/* Host copies; any pointer may be NULL.  nAccepted[bin][walker]. */
+MDA_API int   mdaEnsembleGetState(void *ens, double *pos, double *lnProb, long long *nAccepted);
+/* chain[bin][count][walker][l], lnProb[bin][count][walker] for kept samples first..first+count-1. */
+MDA_API int   mdaEnsembleGetChain(void *ens, long long first, long long count, double *chain, double *lnProb);
+/* Device pointers of the chain / state, for device-side consumers. */
+MDA_API const double *mdaEnsembleDeviceChain(void *ens);
+MDA_API const double *mdaEnsembleDevicePositions(void *ens);
+/* The generator itself, evaluated on the host from the same source the kernels compile
+ * (csrc/philox.cuh): out[4] = Philox4x32-10(counter[4], key[2]).  For known-answer tests. */
+MDA_API void mdaPhilox4x32(const unsigned int *counter, const unsigned int *key, unsigned int *out);
+
+/* ------------------------------------------------------------------------
+ * 7. Roofline denominators measured on the device this process uses
  * --------------------------------------------------------------------- */
 /* Dependent-free DFMA stream on every SM; best of `repeats`. TFLOP/s (2/FMA). */
 MDA_API int mdaMeasureFp64Peak(int repeats, double *tflops);

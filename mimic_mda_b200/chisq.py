@@ -106,6 +106,7 @@ def prepare_shared_object(path=None):
         "mdaEventSynchronize": (ct.c_int, [_VP]),
         "mdaEventElapsedMs": (ct.c_int, [_VP, _VP, ct.POINTER(ct.c_float)]),
         "mdaKernelLaunchCount": (ct.c_ulonglong, []),
+        "mdaPhilox4x32": (None, [ct.POINTER(ct.c_uint), ct.POINTER(ct.c_uint), ct.POINTER(ct.c_uint)]),
         "mdaMeasureFp64Peak": (ct.c_int, [ct.c_int, _DP]),
         "mdaMeasureHbmCopy": (ct.c_int, [ct.c_size_t, ct.c_int, _DP]),
     }

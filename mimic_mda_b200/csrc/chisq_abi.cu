@@ -5,7 +5,9 @@
 // kernel launch, and without a usable device every entry point fails loudly.
 #include "../../include/mda_chisq.h"
 #include "mda_kernels.cuh"
+#include "philox.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -108,6 +110,7 @@ int ensure_runtime() {
     g_rt.smem_optin = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;
     snprintf(g_rt.name, sizeof(g_rt.name), "%s", prop.name);
     MDA_CUDA(configure_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem)");
+    MDA_CUDA(configure_ensemble_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, ensemble)");
     g_rt.ready = true;
     return MDA_OK;
 }
@@ -115,6 +118,7 @@ int ensure_runtime() {
 // ---- legacy single-bin handle ---------------------------------------------------------
 constexpr uint32_t kStructMagic = 0x4D444131u;  // "MDA1"
 constexpr uint32_t kStoreMagic = 0x4D444153u;   // "MDAS"
+constexpr uint32_t kEnsembleMagic = 0x4D444145u; // "MDAE"
 
 struct MdaHandle {
     uint32_t magic = kStructMagic;
@@ -363,6 +367,30 @@ int eval_device(void *store, int walkers, const double *d_params, double *d_out,
     if (walkers == 0 || s->bins == 0) return MDA_OK;
     if ((rc = upload_store(s))) return rc;
     return enqueue_eval(s, walkers, d_params, d_out, mode);
+}
+
+// ---- device-resident ensemble -----------------------------------------------------------
+struct MdaEnsemble {
+    uint32_t magic = kEnsembleMagic;
+    MdaStore *store = nullptr;
+    int walkers = 0;
+    unsigned long long seed = 0;
+    double a = 2.0;
+    double *d_pos = nullptr, *d_lnp = nullptr;
+    unsigned int *d_nacc = nullptr;
+    int *d_bin_ids = nullptr, *d_status = nullptr;
+    double *d_chain = nullptr, *d_lnp_chain = nullptr;
+    long long keep_cap = 0, kept = 0, steps = 0;
+    bool has_state = false;
+};
+
+MdaEnsemble *as_ensemble(void *p, const char *fn) {
+    MdaEnsemble *e = static_cast<MdaEnsemble *>(p);
+    if (!e || e->magic != kEnsembleMagic || !e->store || e->store->magic != kStoreMagic) {
+        set_error(MDA_ERR_BAD_ARGUMENT, "%s: not a live handle from mdaEnsembleCreate", fn);
+        return nullptr;
+    }
+    return e;
 }
 
 }  // namespace
@@ -691,6 +719,215 @@ int mdaEventElapsedMs(void *start, void *stop, float *ms) {
     return MDA_OK;
 }
 unsigned long long mdaKernelLaunchCount(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- device-resident ensemble sampling --------------------------------------------------------
+void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, double stretchA) {
+    MdaStore *s = as_store(store, "mdaEnsembleCreate");
+    if (!s) return nullptr;
+    if (nWalkers < 2 || (nWalkers & 1)) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: the number of walkers must be even and >= 2 (got %d)", nWalkers); return nullptr; }
+    if (nWalkers < 2 * s->n_l) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: need at least twice as many walkers (%d) as dimensions (%d)", nWalkers, s->n_l); return nullptr; }
+    if (!(stretchA > 1.0)) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: stretch scale must be > 1"); return nullptr; }
+    if (ensure_runtime() != MDA_OK) return nullptr;
+    const EnsembleShape shape = choose_ensemble_shape(nWalkers, s->n_l, s->n_pad, g_rt.smem_optin);
+    if (!shape.fits) {
+        set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: %d walkers x %d dists x %d angles need %zu bytes of shared memory (limit %zu, numL <= %d)",
+                  nWalkers, s->n_l, s->n_pad, shape.smem_bytes, g_rt.smem_optin, kMaxRegL);
+        return nullptr;
+    }
+    MdaEnsemble *e = new MdaEnsemble();
+    e->store = s;
+    e->walkers = nWalkers;
+    e->seed = seed;
+    e->a = stretchA;
+    const size_t n_eval = (size_t)s->bins * (size_t)nWalkers;
+    cudaError_t err = cudaMalloc((void **)&e->d_pos, sizeof(double) * (n_eval * s->n_l ? n_eval * s->n_l : 1));
+    if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_lnp, sizeof(double) * (n_eval ? n_eval : 1));
+    if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_nacc, sizeof(unsigned int) * (n_eval ? n_eval : 1));
+    if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_bin_ids, sizeof(int) * (size_t)(s->bins ? s->bins : 1));
+    if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_status, sizeof(int));
+    if (err == cudaSuccess) err = cudaMemset(e->d_status, 0, sizeof(int));
+    if (err == cudaSuccess) {
+        std::vector<int> ids((size_t)s->bins);
+        for (int b = 0; b < s->bins; ++b) ids[(size_t)b] = b;
+        err = cudaMemcpy(e->d_bin_ids, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice);
+    }
+    if (err != cudaSuccess) { cuda_fail(err, "mdaEnsembleCreate"); mdaEnsembleFree(e); return nullptr; }
+    return e;
+}
+
+void mdaEnsembleFree(void *ens) {
+    MdaEnsemble *e = static_cast<MdaEnsemble *>(ens);
+    if (!e || e->magic != kEnsembleMagic) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleFree: not a handle from mdaEnsembleCreate"); return; }
+    if (g_rt.ready) cudaSetDevice(g_rt.device);
+    if (e->store && e->store->magic == kStoreMagic && e->store->stream) cudaStreamSynchronize(e->store->stream);
+    if (e->d_pos) cudaFree(e->d_pos);
+    if (e->d_lnp) cudaFree(e->d_lnp);
+    if (e->d_nacc) cudaFree(e->d_nacc);
+    if (e->d_bin_ids) cudaFree(e->d_bin_ids);
+    if (e->d_status) cudaFree(e->d_status);
+    if (e->d_chain) cudaFree(e->d_chain);
+    if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
+    e->magic = 0;
+    delete e;
+}
+
+int mdaEnsembleSetBinIds(void *ens, const int *binIds) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleSetBinIds");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (!binIds) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSetBinIds: NULL");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleSetBinIds");
+    MDA_CUDA(cudaMemcpy(e->d_bin_ids, binIds, sizeof(int) * (size_t)e->store->bins, cudaMemcpyHostToDevice), "mdaEnsembleSetBinIds");
+    return MDA_OK;
+}
+
+int mdaEnsembleSetState(void *ens, const double *p0) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleSetState");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (!p0) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSetState: p0 is NULL");
+    MdaStore *s = e->store;
+    const size_t n_eval = (size_t)s->bins * (size_t)e->walkers;
+    for (size_t i = 0; i < n_eval * (size_t)s->n_l; ++i)
+        if (!std::isfinite(p0[i]))
+            return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSetState: at least one parameter value was %s", std::isnan(p0[i]) ? "NaN" : "infinite");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    if ((rc = upload_store(s))) return rc;
+    MDA_CUDA(cudaMemcpyAsync(e->d_pos, p0, sizeof(double) * n_eval * s->n_l, cudaMemcpyHostToDevice, s->stream), "ensemble p0 H2D");
+    MDA_CUDA(cudaMemsetAsync(e->d_nacc, 0, sizeof(unsigned int) * n_eval, s->stream), "ensemble counters");
+    MDA_CUDA(cudaMemsetAsync(e->d_status, 0, sizeof(int), s->stream), "ensemble status");
+    if (n_eval && (rc = enqueue_eval(s, e->walkers, e->d_pos, e->d_lnp, kLnPost))) return rc;
+    MDA_CUDA(cudaStreamSynchronize(s->stream), "mdaEnsembleSetState");
+    e->steps = 0;
+    e->kept = 0;
+    e->has_state = true;
+    return MDA_OK;
+}
+
+int mdaEnsembleReserveChain(void *ens, long long capacity) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleReserveChain");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (capacity < 0) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleReserveChain: negative capacity");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MdaStore *s = e->store;
+    MDA_CUDA(cudaStreamSynchronize(s->stream), "mdaEnsembleReserveChain");
+    if (e->d_chain) cudaFree(e->d_chain);
+    if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
+    e->d_chain = e->d_lnp_chain = nullptr;
+    e->keep_cap = 0;
+    e->kept = 0;
+    if (capacity == 0) return MDA_OK;
+    const size_t per_keep = (size_t)s->bins * (size_t)e->walkers;
+    MDA_CUDA(cudaMalloc((void **)&e->d_chain, sizeof(double) * per_keep * (size_t)s->n_l * (size_t)capacity), "chain allocation");
+    MDA_CUDA(cudaMalloc((void **)&e->d_lnp_chain, sizeof(double) * per_keep * (size_t)capacity), "lnprob chain allocation");
+    e->keep_cap = capacity;
+    return MDA_OK;
+}
+
+int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleAdvance");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (nSteps < 0 || thin < 1) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleAdvance: nSteps >= 0 and thin >= 1 required");
+    if (!e->has_state) return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleAdvance: call mdaEnsembleSetState first");
+    if ((unsigned long long)(e->steps + nSteps) >= (1ull << 31)) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleAdvance: step counter would exceed 2^31");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MdaStore *s = e->store;
+    if (nSteps == 0 || s->bins == 0) return MDA_OK;
+    EnsembleArgs args;
+    memset(&args, 0, sizeof(args));
+    args.consts = s->d_consts;
+    args.n_pts = s->d_npts;
+    args.bin_ids = e->d_bin_ids;
+    args.pos = e->d_pos;
+    args.lnp = e->d_lnp;
+    args.nacc = e->d_nacc;
+    args.chain = e->d_chain;
+    args.lnp_chain = e->d_lnp_chain;
+    args.status = e->d_status;
+    args.bins = s->bins;
+    args.walkers = e->walkers;
+    args.n_l = s->n_l;
+    args.n_pad = s->n_pad;
+    args.n_steps = nSteps;
+    args.thin = thin;
+    args.step0 = e->steps;
+    args.keep0 = e->kept;
+    args.keep_cap = e->keep_cap;
+    args.seed_lo = (unsigned int)(e->seed & 0xFFFFFFFFull);
+    args.seed_hi = (unsigned int)(e->seed >> 32);
+    args.a = e->a;
+    for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
+    const EnsembleShape shape = choose_ensemble_shape(e->walkers, s->n_l, s->n_pad, g_rt.smem_optin);
+    MDA_CUDA(launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const long long new_keeps = (e->steps + nSteps) / thin - e->steps / thin;
+    e->steps += nSteps;
+    if (e->d_chain) e->kept = std::min(e->keep_cap, e->kept + new_keeps);
+    return MDA_OK;
+}
+
+int mdaEnsembleSynchronize(void *ens) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleSynchronize");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    int status = 0;
+    MDA_CUDA(cudaMemcpyAsync(&status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->store->stream), "ensemble status read");
+    MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleSynchronize");
+    if (status & 1) return set_error(MDA_ERR_BAD_STATE, "lnprob returned NaN during ensemble stepping");
+    return MDA_OK;
+}
+
+long long mdaEnsembleSteps(void *ens) { MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleSteps"); return e ? e->steps : -1; }
+long long mdaEnsembleKept(void *ens) { MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleKept"); return e ? e->kept : -1; }
+
+int mdaEnsembleGetState(void *ens, double *pos, double *lnProb, long long *nAccepted) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleGetState");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    int rc = mdaEnsembleSynchronize(ens);
+    if (rc) return rc;
+    MdaStore *s = e->store;
+    const size_t n_eval = (size_t)s->bins * (size_t)e->walkers;
+    if (pos) MDA_CUDA(cudaMemcpy(pos, e->d_pos, sizeof(double) * n_eval * s->n_l, cudaMemcpyDeviceToHost), "ensemble positions D2H");
+    if (lnProb) MDA_CUDA(cudaMemcpy(lnProb, e->d_lnp, sizeof(double) * n_eval, cudaMemcpyDeviceToHost), "ensemble lnprob D2H");
+    if (nAccepted) {
+        std::vector<unsigned int> tmp(n_eval ? n_eval : 1);
+        MDA_CUDA(cudaMemcpy(tmp.data(), e->d_nacc, sizeof(unsigned int) * n_eval, cudaMemcpyDeviceToHost), "ensemble counters D2H");
+        for (size_t i = 0; i < n_eval; ++i) nAccepted[i] = (long long)tmp[i];
+    }
+    return MDA_OK;
+}
+
+int mdaEnsembleGetChain(void *ens, long long first, long long count, double *chain, double *lnProb) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleGetChain");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (first < 0 || count < 0 || first + count > e->kept)
+        return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleGetChain: [%lld, %lld) outside the %lld kept samples", first, first + count, e->kept);
+    int rc = mdaEnsembleSynchronize(ens);
+    if (rc) return rc;
+    if (count == 0) return MDA_OK;
+    MdaStore *s = e->store;
+    const size_t row = (size_t)e->walkers * (size_t)s->n_l * sizeof(double);      // one kept sample of one bin
+    const size_t lrow = (size_t)e->walkers * sizeof(double);
+    if (chain)
+        MDA_CUDA(cudaMemcpy2D(chain, row * (size_t)count, reinterpret_cast<const char *>(e->d_chain) + row * (size_t)first,
+                              row * (size_t)e->keep_cap, row * (size_t)count, (size_t)s->bins, cudaMemcpyDeviceToHost), "chain D2H");
+    if (lnProb)
+        MDA_CUDA(cudaMemcpy2D(lnProb, lrow * (size_t)count, reinterpret_cast<const char *>(e->d_lnp_chain) + lrow * (size_t)first,
+                              lrow * (size_t)e->keep_cap, lrow * (size_t)count, (size_t)s->bins, cudaMemcpyDeviceToHost), "lnprob chain D2H");
+    return MDA_OK;
+}
+
+const double *mdaEnsembleDeviceChain(void *ens) { MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleDeviceChain"); return e ? e->d_chain : nullptr; }
+const double *mdaEnsembleDevicePositions(void *ens) { MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleDevicePositions"); return e ? e->d_pos : nullptr; }
+
+void mdaPhilox4x32(const unsigned int *counter, const unsigned int *key, unsigned int *out) {
+    const Philox4 r = philox4x32_10(Philox4{counter[0], counter[1], counter[2], counter[3]}, key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
 
 // ---- roofline denominators -------------------------------------------------------------------
 int mdaMeasureFp64Peak(int repeats, double *tflops) {

@@ -21,60 +21,11 @@
 //     No cross-lane reduction exists, so results are independent of the tiling.
 //
 // Tensor cores are deliberately not used: the contraction is K = L <= 16 deep in fp64.
-#include "mda_kernels.cuh"
-
-#include <math_constants.h>
+#include "likelihood.cuh"
 
 namespace mda {
 
 namespace {
-
-// ---- PTX helpers (sm_90+: mbarrier transactions, bulk async copies) ---------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MDA_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MDA_DONE;\n"
-        "bra MDA_WAIT;\n"
-        "MDA_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-__device__ __forceinline__ double finish(double chi, bool outside, int mode) {
-    if (mode == kChi) return chi;
-    const double lnl = chi * -0.5;                       // == chi / (-2.0) exactly
-    return (mode == kLnPost && outside) ? -CUDART_INF : lnl;
-}
 
 // Largest chunk of staged constants a single bulk copy may carry (tx-count limit is
 // 2^20-1 bytes per mbarrier phase); chunks are always far below this.
@@ -163,44 +114,7 @@ __global__ void __launch_bounds__(256) lnpost_tile_kernel(const BatchArgs args) 
         mbar_wait(&mbar, parity);
         parity ^= 1u;
 
-        const int valid = min(chunk, n - c0);         // real angles in this chunk
-        const int pairs = valid >> 1;
-        const double2 *p = sC;
-#pragma unroll 2
-        for (int j2 = 0; j2 < pairs; ++j2, p += ROW) {
-            const double2 dv = p[0];
-            double r0[WPT], r1[WPT];
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) { r0[k] = dv.x; r1[k] = dv.y; }
-#pragma unroll
-            for (int l = 0; l < L; ++l) {
-                const double2 D = p[1 + l];
-#pragma unroll
-                for (int k = 0; k < WPT; ++k) {
-                    r0[k] = fma(-a[k][l], D.x, r0[k]);     // C/ChiSquare.c:190,200
-                    r1[k] = fma(-a[k][l], D.y, r1[k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) {
-                chi[k] = fma(r0[k], r0[k], chi[k]);        // C/ChiSquare.c:209, ascending j
-                chi[k] = fma(r1[k], r1[k], chi[k]);
-            }
-        }
-        if (valid & 1) {                               // last, unpaired angle of the bin
-            const double dv = p[0].x;
-            double r0[WPT];
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) r0[k] = dv;
-#pragma unroll
-            for (int l = 0; l < L; ++l) {
-                const double Dx = p[1 + l].x;
-#pragma unroll
-                for (int k = 0; k < WPT; ++k) r0[k] = fma(-a[k][l], Dx, r0[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) chi[k] = fma(r0[k], r0[k], chi[k]);
-        }
+        accumulate_chi<L, WPT>(sC, min(chunk, n - c0), a, chi);
     }
     // a bin with n == 0 never waited on the first chunk's copy: drain it before exit
     if (n <= 0 && first_cols > 0) mbar_wait(&mbar, 0);

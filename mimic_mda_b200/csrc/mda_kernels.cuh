@@ -51,6 +51,37 @@ cudaError_t launch_batch(BatchArgs &args, const TileShape &tile, cudaStream_t st
 // One-time per device: raise the dynamic shared memory limit of every instantiation.
 cudaError_t configure_kernels(size_t smem_optin);
 
+// ---- device-resident ensemble stepping (ensemble_kernel.cu) -----------------------------
+struct EnsembleArgs {
+    const double *consts;      // store layout [bins][n_pad/2][1+L][2]
+    const int *n_pts;          // [bins]
+    const int *bin_ids;        // [bins] global bin index (Philox counter word; partition invariant)
+    double *pos;               // [bins][W][L]   ensemble state, updated in place
+    double *lnp;               // [bins][W]
+    unsigned int *nacc;        // [bins][W]      accepted proposals per walker
+    double *chain;             // [bins][keep_cap][W][L] or null
+    double *lnp_chain;         // [bins][keep_cap][W]    or null
+    int *status;               // bit flags (1 = NaN log-probability seen)
+    int bins, walkers, n_l, n_pad;
+    int n_steps, thin;
+    long long step0;           // index of the first step of this launch (RNG counter)
+    long long keep0, keep_cap; // next free slot / capacity of the chain
+    unsigned int seed_lo, seed_hi;
+    double a;                  // stretch scale (emcee default 2)
+    double lo[kMaxRegL];
+    double hi[kMaxRegL];
+};
+
+struct EnsembleShape {
+    int threads, wpt;
+    size_t smem_bytes;
+    bool fits;                 // constants + ensemble fit in shared memory and numL <= kMaxRegL
+};
+
+EnsembleShape choose_ensemble_shape(int walkers, int n_l, int n_pad, size_t smem_optin);
+cudaError_t configure_ensemble_kernels(size_t smem_optin);
+cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream);
+
 // Legacy scalar path (one bin, one parameter vector), see scalar_kernel.cu.
 //   consts [1+L][n] dense (row 0 data, rows 1..L dists), params[L], result[0] = value,
 //   resid (may be null) [n]

@@ -1,0 +1,156 @@
+"""Device-resident ensemble sampling: the whole emcee loop of mda.py:1128-1131 in one launch.
+
+``DeviceEnsemble`` wraps section 6 of include/mda_chisq.h.  Interface follows the
+emcee 2.x attributes the reference reads (mda.py:1253, 1316, 1393):
+
+    ens = DeviceEnsemble(store, n_walkers, seed=1234)
+    ens.run_mcmc(p0, n_steps)            # p0 [B, W, L]
+    ens.chain                            # [B, W, kept, L]   (emcee: sampler.chain per bin)
+    ens.lnprobability                    # [B, W, kept]
+    ens.acceptance_fraction              # [B, W]
+
+Random numbers are Philox4x32-10 on the device (counter = walker, bin id, half-step,
+draw), so chains are statistically -- not seed-for-seed -- comparable with emcee's
+Mersenne-Twister runs, but identical across launch shapes and GPU counts.
+"""
+import ctypes as ct
+
+import numpy as np
+
+from . import chisq
+
+_DP = ct.POINTER(ct.c_double)
+
+
+def _declare(lib):
+    if getattr(lib, "_mda_ensemble_declared", False):
+        return
+    vp, ll = ct.c_void_p, ct.c_longlong
+    sig = {
+        "mdaEnsembleCreate": (vp, [vp, ct.c_int, ct.c_ulonglong, ct.c_double]),
+        "mdaEnsembleFree": (None, [vp]),
+        "mdaEnsembleSetBinIds": (ct.c_int, [vp, ct.POINTER(ct.c_int)]),
+        "mdaEnsembleSetState": (ct.c_int, [vp, vp]),
+        "mdaEnsembleReserveChain": (ct.c_int, [vp, ll]),
+        "mdaEnsembleAdvance": (ct.c_int, [vp, ct.c_int, ct.c_int]),
+        "mdaEnsembleSynchronize": (ct.c_int, [vp]),
+        "mdaEnsembleSteps": (ll, [vp]),
+        "mdaEnsembleKept": (ll, [vp]),
+        "mdaEnsembleGetState": (ct.c_int, [vp, vp, vp, vp]),
+        "mdaEnsembleGetChain": (ct.c_int, [vp, ll, ll, vp, vp]),
+        "mdaEnsembleDeviceChain": (vp, [vp]),
+        "mdaEnsembleDevicePositions": (vp, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib._mda_ensemble_declared = True
+
+
+class DeviceEnsemble:
+    def __init__(self, store, n_walkers, seed=0, a=2.0, bin_ids=None):
+        self.store, self.lib = store, store.lib
+        _declare(self.lib)
+        self.n_bins, self.k, self.dim = store.n_bins, int(n_walkers), store.n_l
+        self.handle = self.lib.mdaEnsembleCreate(store.handle, self.k, int(seed) & (2 ** 64 - 1), float(a))
+        if not self.handle:
+            msg = self.lib.mdaLastErrorString().decode()
+            if self.lib.mdaLastError() == 3:
+                raise ValueError(msg)
+            raise chisq.MdaError(self.lib.mdaLastError(), msg)
+        if bin_ids is not None:
+            ids = np.ascontiguousarray(bin_ids, dtype=np.int32)
+            if ids.shape != (self.n_bins,):
+                raise ValueError("bin_ids must have one entry per local bin")
+            chisq.check(self.lib, self.lib.mdaEnsembleSetBinIds(self.handle, ids.ctypes.data_as(ct.POINTER(ct.c_int))))
+        self._chain = None
+
+    # -- stepping ---------------------------------------------------------------------
+    def set_state(self, p0):
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        if p0.shape != (self.n_bins, self.k, self.dim):
+            raise ValueError("p0 must be [bins, walkers, dim]")
+        rc = self.lib.mdaEnsembleSetState(self.handle, p0.ctypes.data)
+        if rc == 3:
+            raise ValueError(self.lib.mdaLastErrorString().decode())
+        chisq.check(self.lib, rc, "mdaEnsembleSetState")
+        self._chain = None
+
+    def reserve_chain(self, capacity):
+        chisq.check(self.lib, self.lib.mdaEnsembleReserveChain(self.handle, int(capacity)), "mdaEnsembleReserveChain")
+        self._chain = None
+
+    def advance(self, n_steps, thin=1, wait=True):
+        chisq.check(self.lib, self.lib.mdaEnsembleAdvance(self.handle, int(n_steps), int(thin)), "mdaEnsembleAdvance")
+        self._chain = None
+        if wait:
+            self.synchronize()
+
+    def synchronize(self):
+        rc = self.lib.mdaEnsembleSynchronize(self.handle)
+        if rc == 5:
+            raise ValueError(self.lib.mdaLastErrorString().decode())      # "lnprob returned NaN", as emcee
+        chisq.check(self.lib, rc, "mdaEnsembleSynchronize")
+
+    def run_mcmc(self, p0, n_steps, thin=1, store_chain=True):
+        """emcee-style driver: returns (positions, lnprob) after the last step."""
+        self.set_state(p0)
+        if store_chain:
+            self.reserve_chain(n_steps // thin)
+        self.advance(n_steps, thin)
+        return self.state()[:2]
+
+    # -- results -----------------------------------------------------------------------
+    @property
+    def iterations(self):
+        return int(self.lib.mdaEnsembleSteps(self.handle))
+
+    @property
+    def kept(self):
+        return int(self.lib.mdaEnsembleKept(self.handle))
+
+    def state(self):
+        pos = np.empty((self.n_bins, self.k, self.dim))
+        lnp = np.empty((self.n_bins, self.k))
+        acc = np.empty((self.n_bins, self.k), dtype=np.int64)
+        chisq.check(self.lib, self.lib.mdaEnsembleGetState(self.handle, pos.ctypes.data, lnp.ctypes.data, acc.ctypes.data),
+                    "mdaEnsembleGetState")
+        return pos, lnp, acc
+
+    def _fetch(self):
+        if self._chain is None:
+            kept = self.kept
+            chain = np.empty((self.n_bins, kept, self.k, self.dim))
+            lnp = np.empty((self.n_bins, kept, self.k))
+            chisq.check(self.lib, self.lib.mdaEnsembleGetChain(self.handle, 0, kept, chain.ctypes.data, lnp.ctypes.data),
+                        "mdaEnsembleGetChain")
+            self._chain = (chain, lnp)
+        return self._chain
+
+    @property
+    def chain(self):
+        """[bins, walkers, kept, dim] view (per bin the layout of emcee's sampler.chain)."""
+        return self._fetch()[0].transpose(0, 2, 1, 3)
+
+    @property
+    def lnprobability(self):
+        return self._fetch()[1].transpose(0, 2, 1)
+
+    @property
+    def naccepted(self):
+        return self.state()[2]
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / max(self.iterations, 1)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mdaEnsembleFree(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

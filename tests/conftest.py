@@ -52,6 +52,14 @@ def cs_lib(cuda_lib_path):
     return chisq.prepare_shared_object(cuda_lib_path)
 
 
+@pytest.fixture(autouse=True)
+def _clear_sticky_error(request):
+    """The library's error channel is sticky until cleared: start every GPU test clean."""
+    if "gpu" in request.keywords and "cs_lib" in request.fixturenames:
+        request.getfixturevalue("cs_lib").mdaClearError()
+    yield
+
+
 def rel_err(got, want):
     """max |got - want| / |want| over finite entries (0/0 counts as 0)."""
     got = np.asarray(got, dtype=np.float64)

@@ -1,0 +1,119 @@
+"""Device-resident ensemble stepping against its CPU restatement and
+against the host-driven emcee-2-style sampler."""
+import numpy as np
+import pytest
+
+from mimic_mda_b200 import chisq, synth
+from mimic_mda_b200.ensemble import DeviceEnsemble
+from mimic_mda_b200.sampler import BatchedEnsembleSampler, summarize_chain
+from oracle import device_sampler_oracle as dso
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(n_bins, n_l, n_pts, walkers, ragged=True, seed=17):
+    consts, counts, a_true = synth.make_bins(n_bins, n_l, n_pts, ragged=ragged)
+    lo, hi = synth.default_bounds(n_l)
+    p0 = synth.make_walkers(a_true, walkers, seed=seed, oob_frac=0.0)
+    return consts, counts, lo, hi, p0, a_true
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 30, 64, 150), (5, 9, 60, 96, 60), (3, 5, 31, 512, 25), (2, 8, 41, 34, 80),
+                                   (2, 1, 7, 8, 50), (1, 16, 24, 40, 30)])
+def test_device_chain_equals_cpu_restatement(cs_lib, oracle_lib, shape):
+    n_bins, n_l, n_pts, walkers, steps = shape
+    consts, counts, lo, hi, p0, _ = _problem(n_bins, n_l, n_pts, walkers)
+    want = dso.run(lambda p: oracle_lib.lnpost_bins(consts, counts, lo, hi, p), p0, steps, seed=0xC0FFEE1234)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    ens = DeviceEnsemble(store, walkers, seed=0xC0FFEE1234)
+    pos, lnp = ens.run_mcmc(p0, steps)
+    got = ens.chain.transpose(0, 2, 1, 3)                     # -> [B, kept, W, L]
+    assert got.shape == want["chain"].shape == (n_bins, steps, walkers, n_l)
+    np.testing.assert_allclose(got[:, :5], want["chain"][:, :5], rtol=1e-13, atol=0)   # same trajectory at all
+    same = np.all(got == want["chain"], axis=(2, 3))
+    assert same.mean() > 0.999, same.mean()                   # identical decisions (ties are measure zero)
+    if same.all():
+        np.testing.assert_array_equal(pos, want["pos"])
+        np.testing.assert_array_equal(ens.naccepted, want["nacc"])
+        np.testing.assert_allclose(lnp, want["lnp"], rtol=1e-12)
+        np.testing.assert_allclose(ens.lnprobability.transpose(0, 2, 1), want["lnp_chain"], rtol=1e-12)
+    assert np.all(got >= lo) and np.all(got <= hi)
+    ens.close()
+    store.close()
+
+
+def test_split_runs_thinning_and_partition_invariance(cs_lib):
+    consts, counts, lo, hi, p0, _ = _problem(6, 5, 30, 64)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    one = DeviceEnsemble(store, 64, seed=99)
+    one.run_mcmc(p0, 120)
+    full = one.chain.copy()
+    # 50 + 70 steps == 120 steps
+    two = DeviceEnsemble(store, 64, seed=99)
+    two.set_state(p0)
+    two.reserve_chain(120)
+    two.advance(50)
+    two.advance(70)
+    np.testing.assert_array_equal(two.chain, full)
+    assert two.iterations == 120 and two.kept == 120
+    # thin = 3 keeps steps 3, 6, 9, ...
+    thin = DeviceEnsemble(store, 64, seed=99)
+    thin.run_mcmc(p0, 120, thin=3)
+    np.testing.assert_array_equal(thin.chain, full[:, :, 2::3])
+    # a different seed gives a different chain
+    other = DeviceEnsemble(store, 64, seed=100)
+    other.run_mcmc(p0, 120)
+    assert not np.array_equal(other.chain, full)
+    # bins sharded round-robin over two "ranks" reproduce the same chains via bin ids
+    for r in range(2):
+        idx = np.arange(r, 6, 2)
+        st = chisq.DeviceStore(consts[idx], counts[idx], (lo, hi), cs_lib=cs_lib)
+        part = DeviceEnsemble(st, 64, seed=99, bin_ids=idx)
+        part.run_mcmc(p0[idx], 120)
+        np.testing.assert_array_equal(part.chain, full[idx])
+        part.close()
+        st.close()
+    for e in (one, two, thin, other):
+        e.close()
+    store.close()
+
+
+def test_posterior_agrees_with_host_driven_emcee_style_sampler(cs_lib, oracle_lib):
+    """Different generators (Philox vs Mersenne Twister) => statistical parity:
+    posterior means and quantiles within MCMC noise (mda.py:1429-1431)."""
+    consts, counts, lo, hi, p0, a_true = _problem(4, 4, 40, 128, ragged=False)
+    host = BatchedEnsembleSampler(4, 128, 4, lambda p: oracle_lib.lnpost_bins(consts, counts, lo, hi, p), seeds=5)
+    host.run_mcmc(p0, 600)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    ens = DeviceEnsemble(store, 128, seed=5)
+    ens.run_mcmc(p0, 600)
+    s_h, s_d = summarize_chain(host.chain, 200), summarize_chain(ens.chain, 200)
+    for key in ("mean", "p16", "p50", "p84"):
+        assert np.all(np.abs(s_h[key] - s_d[key]) < 0.25 * s_h["std"] + 1e-5), key
+    np.testing.assert_allclose(s_d["std"], s_h["std"], rtol=0.2)
+    assert abs(ens.acceptance_fraction.mean() - host.acceptance_fraction.mean()) < 0.03
+    ens.close()
+    store.close()
+
+
+def test_ensemble_argument_checks(cs_lib):
+    consts, counts, lo, hi, p0, _ = _problem(2, 3, 10, 16)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    with pytest.raises(ValueError):
+        DeviceEnsemble(store, 15)                  # odd
+    with pytest.raises(ValueError):
+        DeviceEnsemble(store, 4)                   # fewer than 2 * dim
+    ens = DeviceEnsemble(store, 16, seed=1)
+    with pytest.raises(chisq.MdaError):
+        ens.advance(1)                             # no state yet
+    bad = p0.copy()
+    bad[1, 3, 0] = np.nan
+    with pytest.raises(ValueError):
+        ens.set_state(bad)
+    ens.set_state(p0)
+    ens.advance(5)                                 # no chain reserved: state only
+    assert ens.kept == 0 and ens.iterations == 5
+    pos, lnp, acc = ens.state()
+    assert np.all(np.isfinite(lnp)) and acc.max() <= 5
+    ens.close()
+    store.close()

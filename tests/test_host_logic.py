@@ -102,3 +102,37 @@ def test_two_rank_gloo_sharded_run_matches_single_process(tmp_path):
     ref = BatchedEnsembleSampler(5, 12, 3, _oracle_logprob(consts, n_pts, lo, hi), seeds=[40 + b for b in range(5)])
     ref.run_mcmc(p0, 8)
     np.testing.assert_array_equal(merged, ref.chain)
+
+
+def test_philox_known_answers(cs_lib):
+    """Random123's published vectors for Philox4x32-10, on the numpy restatement and on the
+    host build of the very source the kernels compile (csrc/philox.cuh)."""
+    import ctypes as ct
+    from oracle.device_sampler_oracle import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in philox4x32_10(*ctr, *key)) == want
+        c, k, o = (ct.c_uint * 4)(*ctr), (ct.c_uint * 2)(*key), (ct.c_uint * 4)()
+        cs_lib.mdaPhilox4x32(c, k, o)
+        assert tuple(o) == want
+
+
+def test_device_sampler_restatement_samples_the_same_posterior():
+    """The CPU restatement of the device stepper (Philox streams) and the emcee-2-style
+    sampler (Mersenne Twister streams) agree statistically."""
+    from oracle import device_sampler_oracle as dso
+    consts, n_pts, a_true = synth.make_bins(2, 3, 30)
+    lo, hi = synth.default_bounds(3)
+    p0 = synth.make_walkers(a_true, 48, seed=4, oob_frac=0.0)
+    fn = _oracle_logprob(consts, n_pts, lo, hi)
+    dev = dso.run(fn, p0, 500, seed=77)
+    host = BatchedEnsembleSampler(2, 48, 3, fn, seeds=11)
+    host.run_mcmc(p0, 500)
+    s_d = summarize_chain(dev["chain"].transpose(0, 2, 1, 3), 150)
+    s_h = summarize_chain(host.chain, 150)
+    assert np.all(np.abs(s_d["mean"] - s_h["mean"]) < 0.3 * s_h["std"] + 1e-5)
+    assert np.all(dev["chain"] >= lo) and np.all(dev["chain"] <= hi)
+    assert 0.2 < dev["nacc"].mean() / 500 < 0.9

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Times the device-resident ensemble stepper (one persistent launch per run).
+    python tools/ensemble_bench.py [--bins 200 --walkers 512 --n-l 9 --n-pts 60 --steps 500]
+"""
+import argparse
+import ctypes as ct
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mimic_mda_b200 import chisq, synth  # noqa: E402
+from mimic_mda_b200.ensemble import DeviceEnsemble  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bins", type=int, default=200)
+    ap.add_argument("--walkers", type=int, default=512)
+    ap.add_argument("--n-l", type=int, default=9)
+    ap.add_argument("--n-pts", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--chain", type=int, default=1)
+    args = ap.parse_args()
+    lib = chisq.prepare_shared_object()
+    peak = ct.c_double()
+    chisq.check(lib, lib.mdaMeasureFp64Peak(3, ct.byref(peak)))
+    consts, counts, a_true = synth.make_bins(args.bins, args.n_l, args.n_pts)
+    store = chisq.DeviceStore(consts, counts, cs_lib=lib)
+    p0 = synth.make_walkers(a_true, args.walkers, seed=3, oob_frac=0.0)
+    ens = DeviceEnsemble(store, args.walkers, seed=1)
+    ens.set_state(p0)
+    if args.chain:
+        ens.reserve_chain(args.steps)
+    ens.advance(20)                                   # warm-up (also fills 20 chain slots)
+    ev0, ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
+    if args.chain:
+        ens.reserve_chain(args.steps)
+    lib.mdaEventRecord(ev0, store.handle)
+    ens.advance(args.steps, wait=False)
+    lib.mdaEventRecord(ev1, store.handle)
+    lib.mdaEventSynchronize(ev1)
+    ms = ct.c_float()
+    lib.mdaEventElapsedMs(ev0, ev1, ct.byref(ms))
+    ens.synchronize()
+    evals = args.bins * args.walkers * args.steps
+    flops = 2.0 * args.n_pts * (args.n_l + 1) * evals
+    t0 = time.perf_counter()
+    acc = ens.acceptance_fraction.mean()
+    out = {"bins": args.bins, "walkers": args.walkers, "L": args.n_l, "N": args.n_pts, "steps": args.steps,
+           "chain": bool(args.chain), "ms": ms.value, "us_per_step": ms.value * 1e3 / args.steps,
+           "steps_per_s": args.steps / (ms.value * 1e-3), "evals_per_s": evals / (ms.value * 1e-3),
+           "tflops": flops / (ms.value * 1e-3) / 1e12, "frac_fp64": flops / (ms.value * 1e-3) / 1e12 / peak.value,
+           "fp64_peak": peak.value, "acceptance": float(acc)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
