@@ -219,6 +219,10 @@ MDA_API int   mdaEnsembleGetChain(void *ens, long long first, long long count, d
 /* Device pointers of the chain / state, for device-side consumers. */
 MDA_API const double *mdaEnsembleDeviceChain(void *ens);
 MDA_API const double *mdaEnsembleDevicePositions(void *ens);
+/* Debug: per-bin cycle counters of the last Advance, cycles[bin][8] =
+ * {proposal+RNG, likelihood, accept, barrier, chain store, 0, 0, 0} as seen by thread 0
+ * of each CTA.  The first call (cycles may be NULL) switches the counters on. */
+MDA_API int mdaEnsembleProfile(void *ens, long long *cycles);
 /* The generator itself, evaluated on the host from the same source the kernels compile
  * (csrc/philox.cuh): out[4] = Philox4x32-10(counter[4], key[2]).  For known-answer tests. */
 MDA_API void mdaPhilox4x32(const unsigned int *counter, const unsigned int *key, unsigned int *out);

@@ -41,7 +41,8 @@ def prepare_shared_object(path=None):
     Same contract as mda.py:1142-1190 (``path`` plays CONFIG["Shared Lib Path"]);
     the additive symbols of include/mda_chisq.h are declared as well.
     """
-    path = DEFAULT_LIB if path is None else path
+    if path is None:
+        path = os.environ.get("MDA_LIB_PATH", DEFAULT_LIB)      # plays CONFIG["Shared Lib Path"]
     if not os.path.exists(path):
         raise FileNotFoundError(
             "%s not built: run `python -m mimic_mda_b200.build` (needs nvcc); "

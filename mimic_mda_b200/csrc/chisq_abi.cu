@@ -382,6 +382,7 @@ struct MdaEnsemble {
     double *d_chain = nullptr, *d_lnp_chain = nullptr;
     long long keep_cap = 0, kept = 0, steps = 0;
     bool has_state = false;
+    long long *d_prof = nullptr;     // [bins][8] section cycle counters of the last launch (debug)
 };
 
 MdaEnsemble *as_ensemble(void *p, const char *fn) {
@@ -728,7 +729,7 @@ void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, doub
     if (nWalkers < 2 * s->n_l) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: need at least twice as many walkers (%d) as dimensions (%d)", nWalkers, s->n_l); return nullptr; }
     if (!(stretchA > 1.0)) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: stretch scale must be > 1"); return nullptr; }
     if (ensure_runtime() != MDA_OK) return nullptr;
-    const EnsembleShape shape = choose_ensemble_shape(nWalkers, s->n_l, s->n_pad, g_rt.smem_optin);
+    const EnsembleShape shape = choose_ensemble_shape(s->bins, nWalkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
     if (!shape.fits) {
         set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: %d walkers x %d dists x %d angles need %zu bytes of shared memory (limit %zu, numL <= %d)",
                   nWalkers, s->n_l, s->n_pad, shape.smem_bytes, g_rt.smem_optin, kMaxRegL);
@@ -767,6 +768,7 @@ void mdaEnsembleFree(void *ens) {
     if (e->d_status) cudaFree(e->d_status);
     if (e->d_chain) cudaFree(e->d_chain);
     if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
+    if (e->d_prof) cudaFree(e->d_prof);
     e->magic = 0;
     delete e;
 }
@@ -847,6 +849,7 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.chain = e->d_chain;
     args.lnp_chain = e->d_lnp_chain;
     args.status = e->d_status;
+    args.prof = e->d_prof;
     args.bins = s->bins;
     args.walkers = e->walkers;
     args.n_l = s->n_l;
@@ -860,7 +863,7 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.seed_hi = (unsigned int)(e->seed >> 32);
     args.a = e->a;
     for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
-    const EnsembleShape shape = choose_ensemble_shape(e->walkers, s->n_l, s->n_pad, g_rt.smem_optin);
+    const EnsembleShape shape = choose_ensemble_shape(s->bins, e->walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
     MDA_CUDA(launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const long long new_keeps = (e->steps + nSteps) / thin - e->steps / thin;
@@ -918,6 +921,22 @@ int mdaEnsembleGetChain(void *ens, long long first, long long count, double *cha
     if (lnProb)
         MDA_CUDA(cudaMemcpy2D(lnProb, lrow * (size_t)count, reinterpret_cast<const char *>(e->d_lnp_chain) + lrow * (size_t)first,
                               lrow * (size_t)e->keep_cap, lrow * (size_t)count, (size_t)s->bins, cudaMemcpyDeviceToHost), "lnprob chain D2H");
+    return MDA_OK;
+}
+
+int mdaEnsembleProfile(void *ens, long long *cycles) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleProfile");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    const size_t bytes = sizeof(long long) * 8 * (size_t)(e->store->bins ? e->store->bins : 1);
+    if (!e->d_prof) {                                   // first call switches the counters on
+        MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleProfile");
+        MDA_CUDA(cudaMalloc((void **)&e->d_prof, bytes), "profile counters");
+        MDA_CUDA(cudaMemset(e->d_prof, 0, bytes), "profile counters");
+    }
+    MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleProfile");
+    if (cycles) MDA_CUDA(cudaMemcpy(cycles, e->d_prof, bytes, cudaMemcpyDeviceToHost), "profile counters D2H");
     return MDA_OK;
 }
 

@@ -61,12 +61,12 @@ __device__ __forceinline__ double finish(double chi, bool outside, int mode) {
 // registers.  Operation order per walker is the reference's: r_j = d_j - a_0 D_0j, then
 // r_j -= a_l D_lj for ascending l (C/ChiSquare.c:188-202), chi += r_j^2 for ascending j
 // (C/ChiSquare.c:204-210).  chi[] is carried across calls (angle chunks).
-template <int L, int WPT>
+template <int L, int WPT, int UNROLL = 2>
 __device__ __forceinline__ void accumulate_chi(const double2 *p, int valid, const double (&a)[WPT][L],
                                                double (&chi)[WPT]) {
     constexpr int ROW = L + 1;
     const int pairs = valid >> 1;
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int j2 = 0; j2 < pairs; ++j2, p += ROW) {
         const double2 dv = p[0];
         double r0[WPT], r1[WPT];

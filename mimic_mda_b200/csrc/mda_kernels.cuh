@@ -62,8 +62,10 @@ struct EnsembleArgs {
     double *chain;             // [bins][keep_cap][W][L] or null
     double *lnp_chain;         // [bins][keep_cap][W]    or null
     int *status;               // bit flags (1 = NaN log-probability seen)
+    long long *prof;           // optional [bins][8] cycle counters per section, or null
     int bins, walkers, n_l, n_pad;
     int n_steps, thin;
+    int groups;                // angle groups per walker tile (filled in by launch_ensemble)
     long long step0;           // index of the first step of this launch (RNG counter)
     long long keep0, keep_cap; // next free slot / capacity of the chain
     unsigned int seed_lo, seed_hi;
@@ -73,12 +75,13 @@ struct EnsembleArgs {
 };
 
 struct EnsembleShape {
-    int threads, wpt;
+    int threads, wpt, groups;  // blockDim = walker threads x angle groups
     size_t smem_bytes;
     bool fits;                 // constants + ensemble fit in shared memory and numL <= kMaxRegL
 };
 
-EnsembleShape choose_ensemble_shape(int walkers, int n_l, int n_pad, size_t smem_optin);
+EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, int sm_count, size_t smem_optin,
+                                    int force_groups, int force_wpt);
 cudaError_t configure_ensemble_kernels(size_t smem_optin);
 cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream);
 

@@ -38,6 +38,7 @@ def _declare(lib):
         "mdaEnsembleKept": (ll, [vp]),
         "mdaEnsembleGetState": (ct.c_int, [vp, vp, vp, vp]),
         "mdaEnsembleGetChain": (ct.c_int, [vp, ll, ll, vp, vp]),
+        "mdaEnsembleProfile": (ct.c_int, [vp, vp]),
         "mdaEnsembleDeviceChain": (vp, [vp]),
         "mdaEnsembleDevicePositions": (vp, [vp]),
     }
@@ -143,6 +144,12 @@ class DeviceEnsemble:
     @property
     def acceptance_fraction(self):
         return self.naccepted / max(self.iterations, 1)
+
+    def profile(self):
+        """Per-bin section cycle counters of the last advance (first call enables them)."""
+        out = np.zeros((self.n_bins, 8), dtype=np.int64)
+        chisq.check(self.lib, self.lib.mdaEnsembleProfile(self.handle, out.ctypes.data), "mdaEnsembleProfile")
+        return out
 
     def close(self):
         if getattr(self, "handle", None):

@@ -29,6 +29,12 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+def uniform43(w, x, y):
+    """Acceptance uniform from the bits uniform53 leaves unused (word w + 5 + 6 low bits of x, y)."""
+    low = ((x & np.uint64(31)) << np.uint64(6)) | (y & np.uint64(63))
+    return (w.astype(np.float64) * 2048.0 + low.astype(np.float64)) / 8796093022208.0
+
+
 def uniform53(a, b):
     return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
 
@@ -61,10 +67,9 @@ def run(lnpost_fn, p0, n_steps, seed, bin_ids=None, a=2.0, thin=1, step0=0, lnpr
             s = p[:, s_sl]
             q = c - z[:, :, None] * (c - s)
             newlnp = np.asarray(lnpost_fn(q), dtype=np.float64)
-            r2 = philox4x32_10(gw, bin_ids[:, None], t, np.uint64(1), k0, k1)
             with np.errstate(divide="ignore", invalid="ignore"):
                 lnpdiff = (n_l - 1.0) * np.log(z) + newlnp - lnp[:, s_sl]
-                accept = lnpdiff > np.log(uniform53(r2[0], r2[1]))
+                accept = lnpdiff > np.log(uniform43(r[3], r[0], r[1]))
             p[:, s_sl][accept] = q[accept]
             lnp[:, s_sl][accept] = newlnp[accept]
             nacc[:, s_sl][accept] += 1

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--n-pts", type=int, default=60)
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--chain", type=int, default=1)
+    ap.add_argument("--profile", type=int, default=0)
     args = ap.parse_args()
     lib = chisq.prepare_shared_object()
     peak = ct.c_double()
@@ -34,6 +35,8 @@ def main():
     ens.set_state(p0)
     if args.chain:
         ens.reserve_chain(args.steps)
+    if args.profile:
+        ens.profile()
     ens.advance(20)                                   # warm-up (also fills 20 chain slots)
     ev0, ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
     if args.chain:
@@ -54,6 +57,10 @@ def main():
            "steps_per_s": args.steps / (ms.value * 1e-3), "evals_per_s": evals / (ms.value * 1e-3),
            "tflops": flops / (ms.value * 1e-3) / 1e12, "frac_fp64": flops / (ms.value * 1e-3) / 1e12 / peak.value,
            "fp64_peak": peak.value, "acceptance": float(acc)}
+    if args.profile:
+        cyc = ens.profile().astype(float)
+        per_half = cyc.mean(axis=0) / (2 * args.steps)
+        out["cycles_per_half_step"] = dict(zip(["propose+bar", "bar_after_A", "accept+bar", "chi_loop", "draw"], [round(x, 1) for x in per_half[:5]]))
     print(json.dumps(out))
 
 
