@@ -15,12 +15,16 @@ Workload (BASELINE.json configs[3], the one the metric is quoted on): per GPU
 half-ensemble launches of [bins][256][9] parameter vectors (the two halves of the
 stretch move, mda.py:1128-1131), i.e. bins x 512 likelihood evaluations.
 
-  value  evals/s with parameter blocks already resident in HBM (CUDA events on the
-         launching stream; a ring of distinct blocks larger than 2x L2 so that every
-         launch reads its parameters from HBM).
-  e2e    evals/s through the C-ABI staged call with HOST buffers: every half-step
-         copies its [bins][256][9] block from pinned host memory, runs the kernel
-         and copies [bins][256] results back (one captured CUDA graph per call).
+  value  evals/s of the device-resident ensemble sampler (mdaEnsembleAdvance): K steps of
+         every bin's 512 walkers in ONE persistent launch -- proposals, box prior,
+         likelihood, accept/reject and the chain all stay in HBM/shared memory; CUDA events
+         on the launching stream.
+  e2e    the same sampler through the C-ABI call with HOST buffers (mdaEnsembleSetState +
+         mdaEnsembleRunToHost): start positions come from pinned host memory and the whole
+         chain + log-probabilities are delivered to pinned host memory, chunk c+1 computed
+         while chunk c crosses PCIe.  This is what emcee's run_mcmc leaves on the host.
+  batched_half_step  the host-driven alternative (one launch per half-ensemble, parameters
+         from the host each time): resident ring > 2x L2, and staged-graph e2e.
   roofline       the likelihood kernel against the fp64 FMA pipe (measured live by a
                  DFMA microbenchmark) and against HBM (MEASURED_PEAKS.json).
   cpu_baseline   the unmodified reference library (oracle/_ref) through the Python
@@ -258,7 +262,8 @@ def workload_config(cfg, world, note):
         "bins_per_gpu": cfg["bins"], "bins_total": cfg["bins"] * world, "walkers": cfg["walkers"],
         "dists": cfg["n_l"], "angles": cfg["n_pts"], "walkers_per_launch": cfg["walkers"] // 2,
         "launches_per_step": 2, "partition": "bins round-robin over ranks, no collective",
-        "l2_policy": "inputs larger than L2: ring of distinct parameter blocks > 2x126 MB",
+        "l2_policy": "sampler: state lives in shared memory, chain streams out (nothing to re-read); "
+                     "batched_half_step: ring of distinct parameter blocks > 2x126 MB",
         "note": note,
     }
 
@@ -346,6 +351,55 @@ class GpuWorkload:
         self.ev0, self.ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
         self.stage_p, self.stage_o = self.store.staging(self.half)
         self.halves = halves
+        # device-resident sampler: global bin ids make the chains independent of the partition
+        from mimic_mda_b200.ensemble import DeviceEnsemble
+        self.bin_ids = first_bin + bin_step * np.arange(self.bins)
+        self.ens = DeviceEnsemble(self.store, self.walkers, seed=20261019, bin_ids=self.bin_ids)
+        self.p0 = synth.make_walkers(self.a_true, self.walkers, seed=7 + rank, oob_frac=0.0)
+        self.pinned = []
+
+    def pinned_array(self, shape):
+        n = int(np.prod(shape))
+        ptr = self.lib.mdaHostAlloc(max(n, 1) * 8)
+        if not ptr:
+            raise self.chisq.MdaError(self.lib.mdaLastError(), self.lib.mdaLastErrorString().decode())
+        self.pinned.append(ptr)
+        buf = (ct.c_double * max(n, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+
+    def sampler_resident(self, steps, warmup):
+        """K ensemble steps in one persistent launch, chain kept in HBM; elapsed ms (events)."""
+        lib = self.lib
+        self.ens.set_state(self.p0)
+        thin = max(1, -(-steps // 2048))                   # keep at most 2048 samples per walker in HBM
+        self.ens.reserve_chain(max(warmup, 1) // thin + steps // thin + 2)
+        if warmup > 0:
+            self.ens.advance(warmup, thin)
+        self.chisq.check(lib, lib.mdaEventRecord(self.ev0, self.store.handle))
+        self.ens.advance(steps, thin, wait=False)
+        self.chisq.check(lib, lib.mdaEventRecord(self.ev1, self.store.handle))
+        self.chisq.check(lib, lib.mdaEventSynchronize(self.ev1))
+        self.ens.synchronize()
+        ms = ct.c_float()
+        self.chisq.check(lib, lib.mdaEventElapsedMs(self.ev0, self.ev1, ct.byref(ms)))
+        return float(ms.value), thin
+
+    def sampler_e2e(self, steps, host_p0, host_chain, host_lnp):
+        """Host buffers in, host buffers out; wall seconds."""
+        self.store.synchronize()
+        t0 = time.perf_counter()
+        self.ens.set_state(host_p0)
+        self.ens.run_to_host(steps, 1, 0, host_chain, host_lnp)
+        return time.perf_counter() - t0
+
+    def sampler_parity(self, oracle, steps=3):
+        """The sampler's own log-probabilities against the oracle on the positions it visited."""
+        self.ens.run_mcmc(self.p0, steps)
+        chain = np.ascontiguousarray(self.ens.chain[:, :, -1, :])          # [B, W, L] after the last step
+        got = self.ens.lnprobability[:, :, -1]
+        want = oracle.lnpost_bins(self.consts, self.n_pts, self.lo, self.hi, chain)
+        fin = np.isfinite(want)
+        return float(np.max(np.abs(got[fin] - want[fin]) / np.abs(want[fin])))
 
     def evals_per_step(self):
         return self.bins * self.walkers
@@ -387,11 +441,35 @@ class GpuWorkload:
         return worst
 
     def close(self):
+        self.ens.close()
+        for p in self.pinned:
+            self.lib.mdaHostFree(p)
         for p in self.d_params + self.d_out:
             self.lib.mdaDeviceFree(p)
         self.lib.mdaEventDestroy(self.ev0)
         self.lib.mdaEventDestroy(self.ev1)
         self.store.close()
+
+
+def measure_sampler(work, dist, steps, warmup, e2e_cap=192):
+    """Device-resident sampler: resident (events) and host-buffer e2e (wall), max over ranks."""
+    work.store.synchronize()
+    dist.barrier()
+    ms, thin = work.sampler_resident(steps, max(warmup, 3))
+    work.store.synchronize()
+    dist.barrier()
+    ms = dist.max(ms)
+    e2e_steps = max(1, min(steps, e2e_cap))
+    host_p0 = work.pinned_array(work.p0.shape)
+    host_p0[...] = work.p0
+    host_chain = work.pinned_array((e2e_steps, work.bins, work.walkers, work.n_l))
+    host_lnp = work.pinned_array((e2e_steps, work.bins, work.walkers))
+    work.sampler_e2e(min(e2e_steps, 8), host_p0, host_chain[:min(e2e_steps, 8)], host_lnp[:min(e2e_steps, 8)])
+    dist.barrier()
+    secs = work.sampler_e2e(e2e_steps, host_p0, host_chain, host_lnp)
+    dist.barrier()
+    secs = dist.max(secs)
+    return ms, thin, secs, e2e_steps
 
 
 def measure(work, dist, steps, warmup):
@@ -451,12 +529,15 @@ def main():
 
     launches0 = lib.mdaKernelLaunchCount()
     sampler = ClockSampler(lib.mdaGetDevice())
+    # headline: the device-resident sampler (K steps = one persistent launch)
+    s_ms, s_thin, s_secs, s_e2e_steps = measure_sampler(work, dist, args.steps, args.warmup)
+    # the host-driven alternative: one launch per half-ensemble
     ms, e2e_secs, e2e_steps = measure(work, dist, args.steps, args.warmup)
     timed_launches = 2 * args.steps
-    # keep the same load running while nvidia-smi samples (the timed region is milliseconds long)
+    # keep the same load running while nvidia-smi samples (the timed regions are milliseconds long)
     t_end = time.perf_counter() + 1.0
     while time.perf_counter() < t_end:
-        work.resident(500)
+        work.ens.advance(200, 10 ** 6)            # thin beyond the run: nothing is kept
     clocks = sampler.stop()
     total_launches = lib.mdaKernelLaunchCount() - launches0
 
@@ -464,39 +545,57 @@ def main():
     from oracle import reflib
     if not os.path.exists(reflib.ORACLE_LIB):
         reflib.build()
-    worst = work.check_against(reflib.OracleLib())
+    orc = reflib.OracleLib()
+    worst = max(work.check_against(orc), work.sampler_parity(orc))
     if worst > 1e-12:
         raise SystemExit("bench.py: parity gate failed, max rel err %.3e" % worst)
 
-    evals_step = work.evals_per_step() * world
-    value = evals_step * args.steps / (ms * 1e-3)
-    e2e_value = evals_step * e2e_steps / e2e_secs
     n_l, n_ang, bins, half = cfg["n_l"], cfg["n_pts"], cfg["bins"], work.half
-    dur_s = ms * 1e-3 / timed_launches                              # average launch duration
-    flops_launch = 2.0 * n_ang * (n_l + 1) * bins * half            # 2 N (L+1) per eval
-    bytes_launch = 8.0 * (n_l + 1) * bins * (half + n_ang)          # params in, lnL out, constants once
-    tf = flops_launch / dur_s / 1e12
-    gbs = bytes_launch / dur_s / 1e9
-    frac_fp64, frac_hbm = tf / peak_tf.value, gbs / hbm_peak
-    traffic = None
+    evals_step = work.evals_per_step() * world
+    value = evals_step * args.steps / (s_ms * 1e-3)
+    e2e_value = evals_step * s_e2e_steps / s_secs
+    traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            traffic = json.load(open(tpath))
         except Exception:
-            traffic = None
-    roofline = {
-        "bound": "fp64" if frac_fp64 >= frac_hbm else "hbm",
-        "achieved": tf if frac_fp64 >= frac_hbm else gbs,
-        "peak": peak_tf.value if frac_fp64 >= frac_hbm else hbm_peak,
-        "unit": "TFLOP/s" if frac_fp64 >= frac_hbm else "GB/s",
-        "frac": max(frac_fp64, frac_hbm), "traffic": traffic,
-        "kernel": "lnpost_tile_kernel<L=%d,WPT=%d> %d threads x %d CTAs" % (n_l, tile[1], tile[0], tile[2]),
-        "launch_us": dur_s * 1e6, "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
-        "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf.value, "frac": frac_fp64,
-                 "peak_source": "DFMA microbenchmark measured in this run (mdaMeasureFp64Peak); MEASURED_PEAKS.json has no fp64 figure"},
-        "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": frac_hbm, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"},
-        "tensor_cores": "not used: skinny fp64 contraction (K = L = %d)" % n_l,
+            traffic = {}
+
+    def roofline_of(kernel, seconds_per_launch, flops_launch, bytes_launch, traffic_key):
+        tf = flops_launch / seconds_per_launch / 1e12
+        gbs = bytes_launch / seconds_per_launch / 1e9
+        f64, fhbm = tf / peak_tf.value, gbs / hbm_peak
+        return {
+            "bound": "fp64" if f64 >= fhbm else "hbm",
+            "achieved": tf if f64 >= fhbm else gbs,
+            "peak": peak_tf.value if f64 >= fhbm else hbm_peak,
+            "unit": "TFLOP/s" if f64 >= fhbm else "GB/s",
+            "frac": max(f64, fhbm), "traffic": traffic.get(traffic_key),
+            "kernel": kernel, "launch_us": seconds_per_launch * 1e6,
+            "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
+            "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf.value, "frac": f64,
+                     "peak_source": "DFMA microbenchmark measured in this run (mdaMeasureFp64Peak); MEASURED_PEAKS.json has no fp64 figure"},
+            "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": fhbm, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"},
+            "tensor_cores": "not used: skinny fp64 contraction (K = L = %d)" % n_l,
+        }
+
+    # sampler launch: 2 N (L+1) flop per evaluation; HBM: kept chain + lnprob out,
+    # constants + state in/out once
+    s_flops = 2.0 * n_ang * (n_l + 1) * bins * cfg["walkers"] * args.steps
+    s_bytes = 8.0 * (n_l + 1) * bins * (cfg["walkers"] * (args.steps // s_thin + 2) + n_ang)
+    roofline = roofline_of("ensemble_kernel<L=%d> persistent, 1 CTA per bin, %d steps per launch" % (n_l, args.steps),
+                           s_ms * 1e-3, s_flops, s_bytes, args.workload + "_sampler")
+    dur_s = ms * 1e-3 / timed_launches
+    b_roofline = roofline_of("lnpost_tile_kernel<L=%d,WPT=%d> %d threads x %d CTAs" % (n_l, tile[1], tile[0], tile[2]), dur_s,
+                             2.0 * n_ang * (n_l + 1) * bins * half, 8.0 * (n_l + 1) * bins * (half + n_ang), args.workload)
+    batched = {
+        "value": evals_step * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
+        "gpu_launches": timed_launches, "roofline": b_roofline,
+        "e2e": {"value": evals_step * e2e_steps / e2e_secs, "unit": UNIT, "steps": e2e_steps,
+                "h2d_bytes_per_step": bins * cfg["walkers"] * n_l * 8, "d2h_bytes_per_step": bins * cfg["walkers"] * 8,
+                "path": "mdaBatchLnPostStaged: pinned host block -> H2D -> kernel -> D2H -> sync, one CUDA graph per call"},
+        "l2_policy": "inputs larger than L2: ring of distinct parameter blocks > 2x126 MB",
     }
 
     strong = None
@@ -504,10 +603,10 @@ def main():
         # companion: BASELINE configs[3] literally -- 200 bins in total, sharded round-robin
         mine = shard.bins_for_rank(cfg["bins"], rank, world)
         sw = GpuWorkload(lib, cfg, rank, world, len(mine), rank, world, args.tile)
-        s_ms, s_secs, s_steps = measure(sw, dist, args.steps, args.warmup)
+        q_ms, _, q_secs, q_steps = measure_sampler(sw, dist, args.steps, args.warmup)
         tot = cfg["bins"] * cfg["walkers"]
-        strong = {"bins_total": cfg["bins"], "value": tot * args.steps / (s_ms * 1e-3), "unit": UNIT,
-                  "e2e": tot * s_steps / s_secs, "ms_per_step": s_ms / args.steps}
+        strong = {"bins_total": cfg["bins"], "bins_per_gpu": len(mine), "value": tot * args.steps / (q_ms * 1e-3),
+                  "unit": UNIT, "e2e": tot * q_steps / q_secs, "ms_per_step": q_ms / args.steps}
         sw.close()
 
     cpu = None
@@ -517,17 +616,20 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": s_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(cfg, world, "fp64 chi-square log-posterior, box prior in-kernel"),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bins * cfg["walkers"] * n_l * 8,
-                    "d2h_bytes_per_step": bins * cfg["walkers"] * 8, "steps": e2e_steps,
-                    "ensemble_steps_per_s": e2e_steps / e2e_secs,
-                    "path": "mdaBatchLnPostStaged: pinned host block -> H2D -> kernel -> D2H -> sync, one CUDA graph per call"},
-            "gpu_launches": timed_launches,
+            "config": workload_config(cfg, world, "device-resident stretch-move sampler: proposal, box prior, fp64 chi-square "
+                                      "log-likelihood and accept/reject in one persistent kernel; chain kept in HBM (thin %d)" % s_thin),
+            "e2e": {"value": e2e_value, "unit": UNIT, "steps": s_e2e_steps,
+                    "h2d_bytes_per_step": bins * cfg["walkers"] * n_l * 8 // s_e2e_steps,
+                    "d2h_bytes_per_step": bins * cfg["walkers"] * (n_l + 1) * 8,
+                    "ensemble_steps_per_s": s_e2e_steps / s_secs,
+                    "path": "mdaEnsembleSetState(pinned host p0) + mdaEnsembleRunToHost: full chain + lnprob delivered to pinned "
+                            "host memory, chunked D2H overlapped with stepping (PCIe bound: 80 B per evaluation)"},
+            "gpu_launches": 1,
             "gpu_launches_total_in_run": int(total_launches),
-            "ensemble_steps_per_s": args.steps / (ms * 1e-3),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "ensemble_steps_per_s": args.steps / (s_ms * 1e-3),
+            "roofline": roofline, "batched_half_step": batched, "cpu_baseline": cpu, "clocks": clocks,
             "parity_max_rel_err": worst,
             "device": {"name": name.value.decode(), "sms": sms.value, "cc": cc.value},
         }

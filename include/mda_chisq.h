@@ -203,8 +203,9 @@ MDA_API int   mdaEnsembleSetBinIds(void *ens, const int *binIds);
 /* p0[bin][walker][l] (host).  Evaluates the starting log-posteriors, zeroes
  * the acceptance counters and the step counter.  Rejects NaN/inf positions. */
 MDA_API int   mdaEnsembleSetState(void *ens, const double *p0);
-/* Room for `capacity` kept samples per bin: chain[bin][kept][walker][l] and
- * lnprob[bin][kept][walker] in HBM.  Resets the kept count. */
+/* Room for `capacity` kept samples: chain[kept][bin][walker][l] and
+ * lnprob[kept][bin][walker] in HBM (step-major, so a run streams out as
+ * contiguous slabs).  Resets the kept count. */
 MDA_API int   mdaEnsembleReserveChain(void *ens, long long capacity);
 /* Asynchronous: advance nSteps steps, keeping every thin-th (if a chain is reserved). */
 MDA_API int   mdaEnsembleAdvance(void *ens, int nSteps, int thin);
@@ -214,8 +215,14 @@ MDA_API long long mdaEnsembleSteps(void *ens);
 MDA_API long long mdaEnsembleKept(void *ens);
 /* Host copies; any pointer may be NULL.  nAccepted[bin][walker]. */
 MDA_API int   mdaEnsembleGetState(void *ens, double *pos, double *lnProb, long long *nAccepted);
-/* chain[bin][count][walker][l], lnProb[bin][count][walker] for kept samples first..first+count-1. */
+/* chain[count][bin][walker][l], lnProb[count][bin][walker] for kept samples first..first+count-1. */
 MDA_API int   mdaEnsembleGetChain(void *ens, long long first, long long count, double *chain, double *lnProb);
+/* The emcee call with host buffers: advance nSteps steps, keeping every thin-th, and deliver
+ * the kept samples to hostChain[nSteps/thin][bin][walker][l] / hostLnProb[nSteps/thin][bin][walker]
+ * (either may be NULL; pinned memory from mdaHostAlloc gives full PCIe rate).  The run is cut
+ * into chunks of chunkSteps steps (0 = library default); chunk c+1 is computed while chunk c
+ * crosses PCIe from a double-buffered device chain.  Synchronous. */
+MDA_API int   mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double *hostChain, double *hostLnProb);
 /* Device pointers of the chain / state, for device-side consumers. */
 MDA_API const double *mdaEnsembleDeviceChain(void *ens);
 MDA_API const double *mdaEnsembleDevicePositions(void *ens);

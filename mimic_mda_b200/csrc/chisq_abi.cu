@@ -383,6 +383,8 @@ struct MdaEnsemble {
     long long keep_cap = 0, kept = 0, steps = 0;
     bool has_state = false;
     long long *d_prof = nullptr;     // [bins][8] section cycle counters of the last launch (debug)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
 };
 
 MdaEnsemble *as_ensemble(void *p, const char *fn) {
@@ -769,6 +771,11 @@ void mdaEnsembleFree(void *ens) {
     if (e->d_chain) cudaFree(e->d_chain);
     if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
     if (e->d_prof) cudaFree(e->d_prof);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (e->chunk_done[i]) cudaEventDestroy(e->chunk_done[i]);
+        if (e->copy_done[i]) cudaEventDestroy(e->copy_done[i]);
+    }
     e->magic = 0;
     delete e;
 }
@@ -913,14 +920,14 @@ int mdaEnsembleGetChain(void *ens, long long first, long long count, double *cha
     if (rc) return rc;
     if (count == 0) return MDA_OK;
     MdaStore *s = e->store;
-    const size_t row = (size_t)e->walkers * (size_t)s->n_l * sizeof(double);      // one kept sample of one bin
-    const size_t lrow = (size_t)e->walkers * sizeof(double);
+    const size_t slab = (size_t)s->bins * (size_t)e->walkers * (size_t)s->n_l * sizeof(double);   // one kept sample, all bins
+    const size_t lslab = (size_t)s->bins * (size_t)e->walkers * sizeof(double);
     if (chain)
-        MDA_CUDA(cudaMemcpy2D(chain, row * (size_t)count, reinterpret_cast<const char *>(e->d_chain) + row * (size_t)first,
-                              row * (size_t)e->keep_cap, row * (size_t)count, (size_t)s->bins, cudaMemcpyDeviceToHost), "chain D2H");
+        MDA_CUDA(cudaMemcpy(chain, reinterpret_cast<const char *>(e->d_chain) + slab * (size_t)first, slab * (size_t)count,
+                            cudaMemcpyDeviceToHost), "chain D2H");
     if (lnProb)
-        MDA_CUDA(cudaMemcpy2D(lnProb, lrow * (size_t)count, reinterpret_cast<const char *>(e->d_lnp_chain) + lrow * (size_t)first,
-                              lrow * (size_t)e->keep_cap, lrow * (size_t)count, (size_t)s->bins, cudaMemcpyDeviceToHost), "lnprob chain D2H");
+        MDA_CUDA(cudaMemcpy(lnProb, reinterpret_cast<const char *>(e->d_lnp_chain) + lslab * (size_t)first, lslab * (size_t)count,
+                            cudaMemcpyDeviceToHost), "lnprob chain D2H");
     return MDA_OK;
 }
 
@@ -938,6 +945,64 @@ int mdaEnsembleProfile(void *ens, long long *cycles) {
     MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleProfile");
     if (cycles) MDA_CUDA(cudaMemcpy(cycles, e->d_prof, bytes, cudaMemcpyDeviceToHost), "profile counters D2H");
     return MDA_OK;
+}
+
+int mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double *hostChain, double *hostLnProb) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleRunToHost");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (nSteps < 0 || thin < 1) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleRunToHost: nSteps >= 0 and thin >= 1 required");
+    if (!e->has_state) return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleRunToHost: call mdaEnsembleSetState first");
+    if (e->steps % thin != 0) return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleRunToHost: %lld steps already taken is not a multiple of thin = %d", e->steps, thin);
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MdaStore *s = e->store;
+    if (nSteps == 0 || s->bins == 0) return MDA_OK;
+    const size_t slab = (size_t)s->bins * (size_t)e->walkers * (size_t)s->n_l * sizeof(double);   // one kept sample, all bins
+    const size_t lslab = (size_t)s->bins * (size_t)e->walkers * sizeof(double);
+    if (chunkSteps <= 0) {                      // default: ~64 MB of chain per chunk, at least one kept sample
+        const size_t per_keep = slab + lslab;
+        long long keeps = (long long)((64u << 20) / (per_keep ? per_keep : 1));
+        if (keeps < 1) keeps = 1;
+        chunkSteps = (int)std::min<long long>(keeps * thin, 1 << 20);
+    }
+    chunkSteps = std::max(thin, chunkSteps / thin * thin);
+    const long long chunk_keep = chunkSteps / thin, total_keep = nSteps / thin;
+    if ((rc = mdaEnsembleReserveChain(ens, 2 * chunk_keep))) return rc;
+    if (!e->copy_stream) {
+        MDA_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking), "copy stream");
+        for (int i = 0; i < 2; ++i) {
+            MDA_CUDA(cudaEventCreateWithFlags(&e->chunk_done[i], cudaEventDisableTiming), "chunk event");
+            MDA_CUDA(cudaEventCreateWithFlags(&e->copy_done[i], cudaEventDisableTiming), "copy event");
+        }
+    }
+    long long done_keep = 0;
+    int remaining = nSteps;
+    for (int c = 0; remaining > 0; ++c) {
+        const int buf = c & 1;
+        const int steps = std::min(remaining, chunkSteps);
+        const long long keeps = (e->steps + steps) / thin - e->steps / thin;
+        if (c >= 2) MDA_CUDA(cudaStreamWaitEvent(s->stream, e->copy_done[buf], 0), "wait for the chunk buffer to drain");
+        e->kept = buf * chunk_keep;                                  // the kernel appends from this slot
+        if ((rc = mdaEnsembleAdvance(ens, steps, thin))) return rc;
+        MDA_CUDA(cudaEventRecord(e->chunk_done[buf], s->stream), "chunk event record");
+        MDA_CUDA(cudaStreamWaitEvent(e->copy_stream, e->chunk_done[buf], 0), "copy waits for the chunk");
+        if (keeps > 0 && done_keep + keeps <= total_keep) {
+            if (hostChain)
+                MDA_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(hostChain) + slab * (size_t)done_keep,
+                                         reinterpret_cast<const char *>(e->d_chain) + slab * (size_t)(buf * chunk_keep),
+                                         slab * (size_t)keeps, cudaMemcpyDeviceToHost, e->copy_stream), "chain chunk D2H");
+            if (hostLnProb)
+                MDA_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(hostLnProb) + lslab * (size_t)done_keep,
+                                         reinterpret_cast<const char *>(e->d_lnp_chain) + lslab * (size_t)(buf * chunk_keep),
+                                         lslab * (size_t)keeps, cudaMemcpyDeviceToHost, e->copy_stream), "lnprob chunk D2H");
+        }
+        MDA_CUDA(cudaEventRecord(e->copy_done[buf], e->copy_stream), "copy event record");
+        done_keep += keeps;
+        remaining -= steps;
+    }
+    MDA_CUDA(cudaStreamSynchronize(e->copy_stream), "mdaEnsembleRunToHost (copies)");
+    e->kept = 0;                                                     // the device chain was only a staging ring
+    return mdaEnsembleSynchronize(ens);
 }
 
 const double *mdaEnsembleDeviceChain(void *ens) { MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleDeviceChain"); return e ? e->d_chain : nullptr; }

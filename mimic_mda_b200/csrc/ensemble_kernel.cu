@@ -13,7 +13,7 @@
 //      register-tiled inner loop as the batched kernel (likelihood.cuh, reference order
 //      C/ChiSquare.c:188-212),
 //   4. accepts iff (L-1) ln z + lnp(q) - lnp(x) > ln u and updates its walker in place.
-// Nothing crosses PCIe per step; kept samples go to an HBM chain [bin][kept][W][L].
+// Nothing crosses PCIe per step; kept samples go to an HBM chain [kept][bin][W][L].
 #include "likelihood.cuh"
 #include "philox.cuh"
 
@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
     long long slot = args.keep0;
     auto store_step = [&]() {                      // thread 0, after a barrier that followed phase B
         if (!keeping || slot >= args.keep_cap) return;
-        bulk_s2g(args.chain + (((size_t)bin * args.keep_cap + (size_t)slot) * W) * L, sPos, (uint32_t)W * L * 8u);
-        bulk_s2g(args.lnp_chain + ((size_t)bin * args.keep_cap + (size_t)slot) * W, sLnp, (uint32_t)W * 8u);
+        bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
+        bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
         bulk_commit();
     };
 

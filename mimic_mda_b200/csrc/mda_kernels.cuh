@@ -59,8 +59,8 @@ struct EnsembleArgs {
     double *pos;               // [bins][W][L]   ensemble state, updated in place
     double *lnp;               // [bins][W]
     unsigned int *nacc;        // [bins][W]      accepted proposals per walker
-    double *chain;             // [bins][keep_cap][W][L] or null
-    double *lnp_chain;         // [bins][keep_cap][W]    or null
+    double *chain;             // [keep_cap][bins][W][L] or null  (step-major: a run streams out contiguously)
+    double *lnp_chain;         // [keep_cap][bins][W]    or null
     int *status;               // bit flags (1 = NaN log-probability seen)
     long long *prof;           // optional [bins][8] cycle counters per section, or null
     int bins, walkers, n_l, n_pad;

@@ -39,6 +39,7 @@ def _declare(lib):
         "mdaEnsembleGetState": (ct.c_int, [vp, vp, vp, vp]),
         "mdaEnsembleGetChain": (ct.c_int, [vp, ll, ll, vp, vp]),
         "mdaEnsembleProfile": (ct.c_int, [vp, vp]),
+        "mdaEnsembleRunToHost": (ct.c_int, [vp, ct.c_int, ct.c_int, ct.c_int, vp, vp]),
         "mdaEnsembleDeviceChain": (vp, [vp]),
         "mdaEnsembleDevicePositions": (vp, [vp]),
     }
@@ -101,6 +102,27 @@ class DeviceEnsemble:
         self.advance(n_steps, thin)
         return self.state()[:2]
 
+    def run_to_host(self, n_steps, thin=1, chunk_steps=0, chain=None, lnprob=None):
+        """Advance ``n_steps`` and stream the kept samples into host arrays while the next
+        chunk is being computed.  ``chain [n_steps//thin, B, W, L]`` / ``lnprob [kept, B, W]``
+        (step-major, the order the run produces them) may be given, e.g. as views of pinned
+        memory; they are allocated otherwise.  ``chain.transpose(1, 2, 0, 3)`` is emcee's
+        per-bin ``sampler.chain`` layout [B, W, kept, L]."""
+        kept = n_steps // thin
+        if chain is None:
+            chain = np.empty((kept, self.n_bins, self.k, self.dim))
+        if lnprob is None:
+            lnprob = np.empty((kept, self.n_bins, self.k))
+        assert chain.shape == (kept, self.n_bins, self.k, self.dim) and chain.flags.c_contiguous
+        assert lnprob.shape == (kept, self.n_bins, self.k) and lnprob.flags.c_contiguous
+        rc = self.lib.mdaEnsembleRunToHost(self.handle, int(n_steps), int(thin), int(chunk_steps),
+                                           chain.ctypes.data, lnprob.ctypes.data)
+        if rc == 5 and b"NaN" in self.lib.mdaLastErrorString():
+            raise ValueError(self.lib.mdaLastErrorString().decode())
+        chisq.check(self.lib, rc, "mdaEnsembleRunToHost")
+        self._chain = None
+        return chain, lnprob
+
     # -- results -----------------------------------------------------------------------
     @property
     def iterations(self):
@@ -121,8 +143,8 @@ class DeviceEnsemble:
     def _fetch(self):
         if self._chain is None:
             kept = self.kept
-            chain = np.empty((self.n_bins, kept, self.k, self.dim))
-            lnp = np.empty((self.n_bins, kept, self.k))
+            chain = np.empty((kept, self.n_bins, self.k, self.dim))
+            lnp = np.empty((kept, self.n_bins, self.k))
             chisq.check(self.lib, self.lib.mdaEnsembleGetChain(self.handle, 0, kept, chain.ctypes.data, lnp.ctypes.data),
                         "mdaEnsembleGetChain")
             self._chain = (chain, lnp)
@@ -131,11 +153,11 @@ class DeviceEnsemble:
     @property
     def chain(self):
         """[bins, walkers, kept, dim] view (per bin the layout of emcee's sampler.chain)."""
-        return self._fetch()[0].transpose(0, 2, 1, 3)
+        return self._fetch()[0].transpose(1, 2, 0, 3)
 
     @property
     def lnprobability(self):
-        return self._fetch()[1].transpose(0, 2, 1)
+        return self._fetch()[1].transpose(1, 2, 0)
 
     @property
     def naccepted(self):

@@ -117,3 +117,22 @@ def test_ensemble_argument_checks(cs_lib):
     assert np.all(np.isfinite(lnp)) and acc.max() <= 5
     ens.close()
     store.close()
+
+
+def test_run_to_host_streams_the_same_chain(cs_lib):
+    """Chunked, double-buffered delivery to host memory == one resident run."""
+    consts, counts, lo, hi, p0, _ = _problem(5, 5, 30, 64)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    ref = DeviceEnsemble(store, 64, seed=3)
+    ref.run_mcmc(p0, 90, thin=3)
+    want_chain, want_lnp = ref.chain.transpose(2, 0, 1, 3), ref.lnprobability.transpose(2, 0, 1)   # step-major
+    for chunk in (0, 3, 12, 33, 90, 500):
+        ens = DeviceEnsemble(store, 64, seed=3)
+        ens.set_state(p0)
+        chain, lnp = ens.run_to_host(90, thin=3, chunk_steps=chunk)
+        np.testing.assert_array_equal(chain, want_chain)
+        np.testing.assert_array_equal(lnp, want_lnp)
+        np.testing.assert_array_equal(ens.state()[0], ref.state()[0])
+        ens.close()
+    ref.close()
+    store.close()
