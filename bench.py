@@ -282,6 +282,8 @@ class Dist:
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
             try:
                 torch.cuda.set_device(local_rank)
                 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -264,14 +264,20 @@ TileShape choose_tile(int bins, int walkers, int n_l, int n_pad, int sm_count, s
         // Heuristic: the largest register tile that still leaves every SM a few CTAs
         // to overlap staging with arithmetic; small launches fall back to small tiles
         // so the work spreads over all 148 SMs.
-        static const int cand[][2] = {{128, 2}, {64, 2}, {64, 1}, {32, 1}};
+        // Measured on B200 (profiles/r01_sweep_*): every register tile with WPT >= 2 performs alike
+        // once there are >= 2 CTAs per SM; WPT 4 wins ~4 % on launches of many waves (one shared
+        // load feeds 8 DFMAs) as long as its 4 L parameter registers do not cut occupancy.
+        static const int cand[][2] = {{64, 4}, {128, 2}, {64, 2}, {64, 1}, {32, 1}};
+        const int n_cand = 5;
         const int walkers32 = (walkers + 31) / 32 * 32;
-        int pick = 3;
-        for (int c = 0; c < 4; ++c) {
+        int pick = n_cand - 1;
+        for (int c = 0; c < n_cand; ++c) {
             const int tw = cand[c][0] * (generic ? 1 : cand[c][1]);
-            if (tw > walkers32 && c < 3) continue;
+            if (tw > walkers32 && c < n_cand - 1) continue;
             const long tiles = (long)bins * ((walkers + tw - 1) / tw);
-            if (tiles >= 2L * sm_count || c == 3) { pick = c; break; }
+            const long need = (cand[c][1] == 4) ? 8L * sm_count : 2L * sm_count;
+            if (cand[c][1] == 4 && (n_l > 10 || generic)) continue;
+            if (tiles >= need || c == n_cand - 1) { pick = c; break; }
         }
         if (threads <= 0) threads = cand[pick][0];
         if (wpt <= 0) wpt = generic ? 1 : cand[pick][1];
