@@ -235,7 +235,22 @@ MDA_API int mdaEnsembleProfile(void *ens, long long *cycles);
 MDA_API void mdaPhilox4x32(const unsigned int *counter, const unsigned int *key, unsigned int *out);
 
 /* ------------------------------------------------------------------------
- * 7. Roofline denominators measured on the device this process uses
+ * 7. Batched initial fits (replaces the multi-start L-BFGS-B loop on
+ *    calculateChi, mda.py:1114,1664-1709,1912-1957)
+ *
+ * For every bin and every start point: the minimiser of chi^2(a) over the box
+ * lo <= a <= hi (the bounds do_init_fit passes, mda.py:1697) and its chi^2.
+ * chi^2 is a convex quadratic, so the result is the exact constrained
+ * least-squares solution that L-BFGS-B approaches from that start.
+ * starts: [startsPerBin][numL] if sharedStarts (the reference's one grid for
+ * all bins, mda.py:179-183), else [bin][startsPerBin][numL]; params
+ * [bin][startsPerBin][numL]; chi [bin][startsPerBin] (either may be NULL).
+ * numL <= 16.  Host pointers; synchronous.
+ * --------------------------------------------------------------------- */
+MDA_API int mdaBatchFit(void *store, int startsPerBin, int sharedStarts, const double *starts, double *params, double *chi);
+
+/* ------------------------------------------------------------------------
+ * 8. Roofline denominators measured on the device this process uses
  * --------------------------------------------------------------------- */
 /* Dependent-free DFMA stream on every SM; best of `repeats`. TFLOP/s (2/FMA). */
 MDA_API int mdaMeasureFp64Peak(int repeats, double *tflops);

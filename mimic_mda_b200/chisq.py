@@ -107,6 +107,7 @@ def prepare_shared_object(path=None):
         "mdaEventSynchronize": (ct.c_int, [_VP]),
         "mdaEventElapsedMs": (ct.c_int, [_VP, _VP, ct.POINTER(ct.c_float)]),
         "mdaKernelLaunchCount": (ct.c_ulonglong, []),
+        "mdaBatchFit": (ct.c_int, [_VP, ct.c_int, ct.c_int, _VP, _VP, _VP]),
         "mdaPhilox4x32": (None, [ct.POINTER(ct.c_uint), ct.POINTER(ct.c_uint), ct.POINTER(ct.c_uint)]),
         "mdaMeasureFp64Peak": (ct.c_int, [ct.c_int, _DP]),
         "mdaMeasureHbmCopy": (ct.c_int, [ct.c_size_t, ct.c_int, _DP]),
@@ -260,6 +261,22 @@ class DeviceStore:
         check(self.lib, self.lib.mdaBatchChi(self.handle, params.shape[1], params.ctypes.data, out.ctypes.data),
               "mdaBatchChi")
         return out
+
+    def fit(self, starts):
+        """Batched initial fits (the multi-start L-BFGS-B loop of mda.py:1664-1709 in one call):
+        ``starts`` is ``[S, L]`` (one grid shared by every bin, mda.py:179-183) or ``[B, S, L]``.
+        Returns ``(params [B, S, L], chi2 [B, S])`` -- per bin and start the box-constrained
+        minimiser of chi^2 and its value."""
+        starts = np.ascontiguousarray(starts, dtype=np.float64)
+        shared = starts.ndim == 2
+        if starts.shape[-1] != self.n_l or (not shared and starts.shape[0] != self.n_bins):
+            raise ValueError("starts must be [S, L] or [bins, S, L]")
+        n_s = starts.shape[-2]
+        params = np.empty((self.n_bins, n_s, self.n_l))
+        chi = np.empty((self.n_bins, n_s))
+        check(self.lib, self.lib.mdaBatchFit(self.handle, n_s, 1 if shared else 0, starts.ctypes.data, params.ctypes.data,
+                                             chi.ctypes.data), "mdaBatchFit")
+        return params, chi
 
     # -- pinned staging + CUDA graph ---------------------------------------------------
     def staging(self, walkers):

@@ -723,6 +723,39 @@ int mdaEventElapsedMs(void *start, void *stop, float *ms) {
 }
 unsigned long long mdaKernelLaunchCount(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// ---- batched initial fits -----------------------------------------------------------------------
+int mdaBatchFit(void *store, int startsPerBin, int sharedStarts, const double *starts, double *params, double *chi) {
+    MdaStore *s = as_store(store, "mdaBatchFit");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    if (startsPerBin < 0 || (startsPerBin > 0 && !starts)) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaBatchFit: bad start list");
+    if (s->n_l > kMaxRegL) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaBatchFit: numL %d > %d", s->n_l, kMaxRegL);
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    if (startsPerBin == 0 || s->bins == 0) return MDA_OK;
+    if ((rc = upload_store(s))) return rc;
+    const size_t L = (size_t)s->n_l, B = (size_t)s->bins, S = (size_t)startsPerBin;
+    const size_t n_start = (sharedStarts ? 1 : B) * S * L;
+    double *d_gram = nullptr, *d_rhs = nullptr, *d_starts = nullptr, *d_fit = nullptr, *d_chi = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_gram, sizeof(double) * B * L * L);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_rhs, sizeof(double) * B * L);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_starts, sizeof(double) * n_start);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_fit, sizeof(double) * B * S * L);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_chi, sizeof(double) * B * S);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_starts, starts, sizeof(double) * n_start, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = launch_gram(s->d_consts, s->d_npts, s->bins, s->n_l, s->n_pad, d_gram, d_rhs, s->stream);
+    if (e == cudaSuccess) e = launch_bvls(d_gram, d_rhs, s->d_lo, s->d_hi, d_starts, s->bins, s->n_l, startsPerBin, sharedStarts != 0, d_fit, nullptr, s->stream);
+    if (e == cudaSuccess) g_launches.fetch_add(2, std::memory_order_relaxed);
+    if (e == cudaSuccess) rc = enqueue_eval(s, startsPerBin, d_fit, d_chi, kChi);
+    if (e == cudaSuccess && rc == MDA_OK && params) e = cudaMemcpyAsync(params, d_fit, sizeof(double) * B * S * L, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && rc == MDA_OK && chi) e = cudaMemcpyAsync(chi, d_chi, sizeof(double) * B * S, cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e2 = cudaStreamSynchronize(s->stream);
+    cudaFree(d_gram); cudaFree(d_rhs); cudaFree(d_starts); cudaFree(d_fit); cudaFree(d_chi);
+    if (e != cudaSuccess) return cuda_fail(e, "mdaBatchFit");
+    if (rc != MDA_OK) return rc;
+    if (e2 != cudaSuccess) return cuda_fail(e2, "mdaBatchFit");
+    return MDA_OK;
+}
+
 // ---- device-resident ensemble sampling --------------------------------------------------------
 void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, double stretchA) {
     MdaStore *s = as_store(store, "mdaEnsembleCreate");

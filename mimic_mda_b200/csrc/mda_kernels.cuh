@@ -85,6 +85,16 @@ EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, i
 cudaError_t configure_ensemble_kernels(size_t smem_optin);
 cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream);
 
+// ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
+// gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.
+cudaError_t launch_gram(const double *consts, const int *n_pts, int bins, int n_l, int n_pad, double *gram, double *rhs,
+                        cudaStream_t stream);
+// One thread per (bin, start): box-constrained least-squares minimiser, warm-started at the start.
+// starts is [starts_per_bin][L] when shared, else [bins][starts_per_bin][L]; out [bins][starts_per_bin][L].
+cudaError_t launch_bvls(const double *gram, const double *rhs, const double *lo, const double *hi, const double *starts,
+                        int bins, int n_l, int starts_per_bin, bool shared_starts, double *out, int *iters,
+                        cudaStream_t stream);
+
 // Legacy scalar path (one bin, one parameter vector), see scalar_kernel.cu.
 //   consts [1+L][n] dense (row 0 data, rows 1..L dists), params[L], result[0] = value,
 //   resid (may be null) [n]
