@@ -223,6 +223,18 @@ MDA_API int   mdaEnsembleGetChain(void *ens, long long first, long long count, d
  * into chunks of chunkSteps steps (0 = library default); chunk c+1 is computed while chunk c
  * crosses PCIe from a double-buffered device chain.  Synchronous. */
 MDA_API int   mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double *hostChain, double *hostLnProb);
+/* Posterior summaries computed on the device-resident chain (replaces pulling the chain to
+ * the host for calc_param_values / find_most_likely_values, mda.py:1253-1259,1399-1491).
+ * Samples = kept samples firstKept.. of every walker, per bin and parameter:
+ *   points[bin][l] = (v50, vhi - v50, v50 - vlo) from numpy.percentile at
+ *                    100*(0.5 -+ confidenceInterval/2) and 50 (linear interpolation);
+ *   peaks[bin][l]  = the same triple around the percentile of the fullest of numBins
+ *                    equal-width histogram bins (mda.py:1436-1491), or (v, 0, 0) if the
+ *                    samples span less than 1e-7;
+ *   acceptFrac[bin] = mean acceptance fraction of the bin's walkers (mda.py:1316).
+ * Order statistics are exact; interpolation follows numpy.  Any output may be NULL. */
+MDA_API int   mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterval, int numBins,
+                                   double *points, double *peaks, double *acceptFrac);
 /* Device pointers of the chain / state, for device-side consumers. */
 MDA_API const double *mdaEnsembleDeviceChain(void *ens);
 MDA_API const double *mdaEnsembleDevicePositions(void *ens);

@@ -1038,6 +1038,204 @@ int mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double
     return mdaEnsembleSynchronize(ens);
 }
 
+namespace {
+
+double key_to_double(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    double x;
+    memcpy(&x, &u, sizeof(x));
+    return x;
+}
+
+// numpy.percentile(..., method="linear") pieces (numpy/lib/_function_base_impl.py, numpy 2.x):
+// virtual index (n - 1) * q with q = percent / 100, neighbours floor / floor + 1, _lerp.
+struct RankPair { long long lower, upper; double gamma; };
+RankPair percentile_ranks(long long n, double percent) {
+    const double q = percent / 100.0;
+    const double vi = (double)(n - 1) * q;
+    RankPair r;
+    if (vi >= (double)(n - 1)) { r.lower = r.upper = n - 1; r.gamma = 0.0; return r; }
+    if (vi < 0.0) { r.lower = r.upper = 0; r.gamma = 0.0; return r; }
+    const double fl = std::floor(vi);
+    r.lower = (long long)fl;
+    r.upper = r.lower + 1;
+    r.gamma = vi - fl;
+    return r;
+}
+double numpy_lerp(double a, double b, double t) {
+    const double diff = b - a;
+    double out = a + diff * t;
+    if (t >= 0.5) out = b - diff * (1.0 - t);
+    return out;
+}
+
+// Exact order statistics for `n_ranks` ranks per column (ranks[cols][n_ranks]) -> values.
+int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<unsigned long long> &mm,
+                 const std::vector<long long> &ranks, int n_ranks, std::vector<double> &values) {
+    MdaStore *s = e->store;
+    const size_t cols = (size_t)s->bins * (size_t)s->n_l, n_state = cols * (size_t)n_ranks;
+    std::vector<int> top(cols);
+    std::vector<unsigned long long> prefix(2 * n_state, 0ull);
+    std::vector<long long> remaining(2 * n_state, 0);
+    int max_top = 0;
+    for (size_t c = 0; c < cols; ++c) {
+        const unsigned long long x = mm[2 * c] ^ mm[2 * c + 1];
+        int t = 0;
+        while (t < 64 && (x >> t) != 0ull) ++t;               // bits [0, t) may differ inside the column
+        top[c] = t;
+        max_top = std::max(max_top, t);
+        const unsigned long long common = t >= 64 ? 0ull : (mm[2 * c] >> t) << t;
+        for (int r = 0; r < n_ranks; ++r) {
+            prefix[c * n_ranks + r] = common;
+            remaining[c * n_ranks + r] = ranks[c * n_ranks + r];
+        }
+    }
+    unsigned long long *d_prefix = nullptr;
+    long long *d_remaining = nullptr;
+    int *d_top = nullptr;
+    unsigned int *d_hist = nullptr;
+    cudaError_t err = cudaMalloc((void **)&d_prefix, sizeof(unsigned long long) * 2 * n_state);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&d_remaining, sizeof(long long) * 2 * n_state);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&d_top, sizeof(int) * cols);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&d_hist, sizeof(unsigned int) * n_state * 4096);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(unsigned long long) * 2 * n_state, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_remaining, remaining.data(), sizeof(long long) * 2 * n_state, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_top, top.data(), sizeof(int) * cols, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess)
+        err = launch_chain_select(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_prefix, d_remaining, d_top, d_hist,
+                                  n_ranks, max_top, g_rt.sm_count, s->stream);
+    if (err == cudaSuccess) g_launches.fetch_add(3ull * (unsigned long long)((max_top + 11) / 12), std::memory_order_relaxed);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(prefix.data(), d_prefix, sizeof(unsigned long long) * n_state, cudaMemcpyDeviceToHost, s->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
+    cudaFree(d_prefix); cudaFree(d_remaining); cudaFree(d_top); cudaFree(d_hist);
+    if (err != cudaSuccess) return cuda_fail(err, "order-statistic selection");
+    values.resize(n_state);
+    for (size_t i = 0; i < n_state; ++i) values[i] = key_to_double(prefix[i]);
+    return MDA_OK;
+}
+
+}  // namespace
+
+int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterval, int numBins,
+                         double *points, double *peaks, double *acceptFrac) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleSummarize");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (firstKept < 0 || firstKept >= e->kept)
+        return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSummarize: firstKept %lld outside the %lld kept samples", firstKept, e->kept);
+    if (!(confidenceInterval > 0.0 && confidenceInterval <= 1.0) || numBins < 1)
+        return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSummarize: confidenceInterval in (0, 1] and numBins >= 1 required");
+    int rc = mdaEnsembleSynchronize(ens);
+    if (rc) return rc;
+    MdaStore *s = e->store;
+    const size_t B = (size_t)s->bins, L = (size_t)s->n_l, cols = B * L;
+    if (cols == 0) return MDA_OK;
+    if (s->n_l > 32) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSummarize: numL %d > 32", s->n_l);
+    const long long k0 = firstKept, k1 = e->kept;
+    const long long n = (k1 - k0) * (long long)e->walkers;            // samples per column
+
+    // 1. smallest / largest sample per column
+    std::vector<unsigned long long> mm(2 * cols);
+    for (size_t c = 0; c < cols; ++c) { mm[2 * c] = ~0ull; mm[2 * c + 1] = 0ull; }
+    unsigned long long *d_mm = nullptr;
+    MDA_CUDA(cudaMalloc((void **)&d_mm, sizeof(unsigned long long) * 2 * cols), "summary min/max");
+    cudaError_t err = cudaMemcpyAsync(d_mm, mm.data(), sizeof(unsigned long long) * 2 * cols, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) err = launch_chain_minmax(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_mm, g_rt.sm_count, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(mm.data(), d_mm, sizeof(unsigned long long) * 2 * cols, cudaMemcpyDeviceToHost, s->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
+    cudaFree(d_mm);
+    if (err != cudaSuccess) return cuda_fail(err, "summary min/max");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+
+    // 2. percentile error bars (calc_param_values, mda.py:1426-1431)
+    const double pct[3] = {100.0 * (0.5 - confidenceInterval / 2.0), 100.0 * 0.5, 100.0 * (0.5 + confidenceInterval / 2.0)};
+    std::vector<long long> ranks(cols * 6);
+    std::vector<double> vals;
+    if (points) {
+        RankPair rp[3];
+        for (int i = 0; i < 3; ++i) rp[i] = percentile_ranks(n, pct[i]);
+        for (size_t c = 0; c < cols; ++c)
+            for (int i = 0; i < 3; ++i) { ranks[c * 6 + 2 * i] = rp[i].lower; ranks[c * 6 + 2 * i + 1] = rp[i].upper; }
+        if ((rc = select_ranks(e, k0, k1, mm, ranks, 6, vals))) return rc;
+        for (size_t c = 0; c < cols; ++c) {
+            double v[3];
+            for (int i = 0; i < 3; ++i) v[i] = numpy_lerp(vals[c * 6 + 2 * i], vals[c * 6 + 2 * i + 1], rp[i].gamma);
+            points[c * 3 + 0] = v[1];
+            points[c * 3 + 1] = v[2] - v[1];
+            points[c * 3 + 2] = v[1] - v[0];
+        }
+    }
+
+    // 3. histogram peak and its error bars (find_most_likely_values, mda.py:1436-1491)
+    if (peaks) {
+        const size_t nb = (size_t)numBins;
+        std::vector<double> edges(cols * (nb + 1));
+        for (size_t c = 0; c < cols; ++c) {                       // numpy.linspace(first, last, nb + 1)
+            const double first = key_to_double(mm[2 * c]), last = key_to_double(mm[2 * c + 1]);
+            const double step = (last - first) / (double)nb;
+            double *ed = edges.data() + c * (nb + 1);
+            for (size_t i = 0; i <= nb; ++i) { const double y = (double)i * step; ed[i] = y + first; }
+            ed[nb] = last;
+        }
+        double *d_edges = nullptr;
+        unsigned int *d_hist = nullptr;
+        std::vector<unsigned int> hist(cols * nb);
+        err = cudaMalloc((void **)&d_edges, sizeof(double) * edges.size());
+        if (err == cudaSuccess) err = cudaMalloc((void **)&d_hist, sizeof(unsigned int) * hist.size());
+        if (err == cudaSuccess) err = cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * hist.size(), s->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_edges, edges.data(), sizeof(double) * edges.size(), cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess) err = launch_chain_hist(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_edges, numBins, d_hist, g_rt.sm_count, s->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned int) * hist.size(), cudaMemcpyDeviceToHost, s->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
+        cudaFree(d_edges); cudaFree(d_hist);
+        if (err != cudaSuccess) return cuda_fail(err, "summary histogram");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        std::vector<RankPair> rp(cols * 3);
+        std::vector<char> flat(cols, 0);
+        for (size_t c = 0; c < cols; ++c) {
+            const double first = key_to_double(mm[2 * c]), last = key_to_double(mm[2 * c + 1]);
+            if (1.0e-7 > std::fabs(last - first)) { flat[c] = 1; for (int i = 0; i < 6; ++i) ranks[c * 6 + i] = 0; continue; }
+            const unsigned int *h = hist.data() + c * nb;
+            size_t ind = 0;
+            for (size_t i = 1; i < nb; ++i) if (h[i] > h[ind]) ind = i;             // numpy.argmax: first maximum
+            double quantile = 0.0;
+            for (size_t j = 0; j <= ind; ++j) quantile += (double)h[j];
+            quantile /= (double)n;
+            const double peak_percentile = 100.0 * quantile;
+            double lo_p = peak_percentile - 100.0 * (confidenceInterval / 2.0);
+            if (lo_p < 0.0) lo_p = 0.0;
+            double hi_p = peak_percentile + 100.0 * (confidenceInterval / 2.0);
+            if (hi_p > 100.0) hi_p = 100.0;
+            const double p3[3] = {lo_p, peak_percentile, hi_p};
+            for (int i = 0; i < 3; ++i) {
+                rp[c * 3 + i] = percentile_ranks(n, p3[i]);
+                ranks[c * 6 + 2 * i] = rp[c * 3 + i].lower;
+                ranks[c * 6 + 2 * i + 1] = rp[c * 3 + i].upper;
+            }
+        }
+        if ((rc = select_ranks(e, k0, k1, mm, ranks, 6, vals))) return rc;
+        for (size_t c = 0; c < cols; ++c) {
+            if (flat[c]) { peaks[c * 3] = key_to_double(mm[2 * c]); peaks[c * 3 + 1] = 0.0; peaks[c * 3 + 2] = 0.0; continue; }
+            double v[3];
+            for (int i = 0; i < 3; ++i) v[i] = numpy_lerp(vals[c * 6 + 2 * i], vals[c * 6 + 2 * i + 1], rp[c * 3 + i].gamma);
+            peaks[c * 3 + 0] = v[1];
+            peaks[c * 3 + 1] = v[2] - v[1];
+            peaks[c * 3 + 2] = v[1] - v[0];
+        }
+    }
+
+    // 4. acceptance fraction (mda.py:1316: np.mean(sampler.acceptance_fraction))
+    if (acceptFrac) {
+        std::vector<unsigned int> acc(B * (size_t)e->walkers);
+        MDA_CUDA(cudaMemcpy(acc.data(), e->d_nacc, sizeof(unsigned int) * acc.size(), cudaMemcpyDeviceToHost), "acceptance counters D2H");
+        for (size_t b = 0; b < B; ++b) {
+            double sum = 0.0;
+            for (int w = 0; w < e->walkers; ++w) sum += (double)acc[b * e->walkers + w] / (double)(e->steps > 0 ? e->steps : 1);
+            acceptFrac[b] = sum / (double)e->walkers;
+        }
+    }
+    return MDA_OK;
+}
+
 const double *mdaEnsembleDeviceChain(void *ens) { MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleDeviceChain"); return e ? e->d_chain : nullptr; }
 const double *mdaEnsembleDevicePositions(void *ens) { MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleDevicePositions"); return e ? e->d_pos : nullptr; }
 

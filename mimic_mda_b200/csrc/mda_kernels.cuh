@@ -95,6 +95,20 @@ cudaError_t launch_bvls(const double *gram, const double *rhs, const double *lo,
                         int bins, int n_l, int starts_per_bin, bool shared_starts, double *out, int *iters,
                         cudaStream_t stream);
 
+// ---- posterior reductions on the device chain (summary_kernel.cu) ---------------------------------
+constexpr int kMaxRanks = 8;           // order statistics selected together per (bin, dim) column
+// minmax[cols][2]: order-preserving keys of the smallest / largest sample (init ~0 / 0)
+cudaError_t launch_chain_minmax(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
+                                unsigned long long *minmax, int sm_count, cudaStream_t stream);
+// hist[cols][n_bins] += numpy.histogram counts over edges[cols][n_bins + 1]
+cudaError_t launch_chain_hist(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
+                              const double *edges, int n_bins, unsigned int *hist, int sm_count, cudaStream_t stream);
+// radix selection; prefix / remaining are [2][cols][n_ranks] (second half is scratch),
+// hist is [cols][n_ranks][4096], top[cols] = undecided low key bits per column
+cudaError_t launch_chain_select(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
+                                unsigned long long *prefix, long long *remaining, const int *top, unsigned int *hist,
+                                int n_ranks, int max_top, int sm_count, cudaStream_t stream);
+
 // Legacy scalar path (one bin, one parameter vector), see scalar_kernel.cu.
 //   consts [1+L][n] dense (row 0 data, rows 1..L dists), params[L], result[0] = value,
 //   resid (may be null) [n]

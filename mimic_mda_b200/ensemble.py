@@ -39,6 +39,7 @@ def _declare(lib):
         "mdaEnsembleGetState": (ct.c_int, [vp, vp, vp, vp]),
         "mdaEnsembleGetChain": (ct.c_int, [vp, ll, ll, vp, vp]),
         "mdaEnsembleProfile": (ct.c_int, [vp, vp]),
+        "mdaEnsembleSummarize": (ct.c_int, [vp, ll, ct.c_double, ct.c_int, vp, vp, vp]),
         "mdaEnsembleRunToHost": (ct.c_int, [vp, ct.c_int, ct.c_int, ct.c_int, vp, vp]),
         "mdaEnsembleDeviceChain": (vp, [vp]),
         "mdaEnsembleDevicePositions": (vp, [vp]),
@@ -166,6 +167,19 @@ class DeviceEnsemble:
     @property
     def acceptance_fraction(self):
         return self.naccepted / max(self.iterations, 1)
+
+    def summarize(self, burn_in=0, confidence_interval=0.682689492, num_bins=1000):
+        """Posterior summaries computed on the device chain (mda.py:1253-1259, 1399-1491):
+        ``points [B, L, 3]`` and ``peaks [B, L, 3]`` as (value, +error, -error) -- the
+        reference's percentile and histogram-peak estimates -- and the mean acceptance
+        fraction per bin.  ``burn_in`` counts kept samples."""
+        points = np.empty((self.n_bins, self.dim, 3))
+        peaks = np.empty((self.n_bins, self.dim, 3))
+        acc = np.empty(self.n_bins)
+        chisq.check(self.lib, self.lib.mdaEnsembleSummarize(self.handle, int(burn_in), float(confidence_interval), int(num_bins),
+                                                            points.ctypes.data, peaks.ctypes.data, acc.ctypes.data),
+                    "mdaEnsembleSummarize")
+        return {"points": points, "peaks": peaks, "acceptance_fraction": acc}
 
     def profile(self):
         """Per-bin section cycle counters of the last advance (first call enables them)."""
