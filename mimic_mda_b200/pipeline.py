@@ -1,0 +1,61 @@
+"""The per-bin worker of the reference, for every Ex bin of a rank at once.
+
+``fit_and_mcmc`` (mda.py:1072-1139) does, per bin inside a pool worker: load the library,
+fill the struct, multi-start fits, pick generators, randomise walker starts, run emcee,
+summarise the samples, free the struct.  ``fit_and_mcmc_all`` runs the same stages for all
+bins of a ``DeviceStore`` in a handful of launches:
+
+    initial fits        mdaBatchFit              (mda.py:1114-1120)
+    walker starts       fits.gen_walker_starts   (mda.py:1122, host numpy, once per bin)
+    MCMC                mdaEnsembleAdvance       (mda.py:1128-1131; chain stays in HBM)
+    summaries           mdaEnsembleSummarize     (mda.py:1253-1259, 1399-1491, 1316)
+    chi^2 of estimates  mdaBatchChi              (calculate_fit_chis, mda.py:1321-1354)
+
+and returns, per bin, the tuple the reference's worker returns:
+``((points, peaks), (acor_time, (perc_chi, peak_chi), accept_frac))``.  Only the walker
+starts go to the device and only the summaries come back.
+"""
+import numpy as np
+
+from . import fits
+from .ensemble import DeviceEnsemble
+
+# the CONFIG keys this path reads, with the values of mda_config0.py
+DEFAULTS = {
+    "Number of Walkers": 2500, "Sample Points": 16385, "Burn-in Points": 512,
+    "Number Walker Generators": 50, "Sample Spread": 2.0, "Sample Offset Centroid": 0.04,
+    "Sample Offset Width": 0.02, "Confidence Interval": 0.682689492, "Num Bins": 1000,
+}
+
+
+def fit_and_mcmc_all(store, start_params, config, ewsr=None, seed=0, bin_ids=None, rng=None, thin=1):
+    """Returns ``(results, ensemble)``; ``results[b]`` has the shape of the reference worker's
+    return value for bin b (mda.py:1318).  ``config`` holds the reference's CONFIG keys (missing
+    ones take mda_config0.py's values); ``ewsr`` defaults to 1 for every multipole."""
+    cfg = dict(DEFAULTS)
+    cfg.update(config)
+    n_l = store.n_l
+    ewsr = np.ones(n_l) if ewsr is None else np.asarray(ewsr, dtype=np.float64)
+    rng = np.random.RandomState(seed) if rng is None else rng
+    # initial fits from every start, best "Number Walker Generators" per bin
+    gens, _ = fits.initial_fits(store, start_params, cfg["Number Walker Generators"])
+    # walker start positions (mda.py:1122)
+    walkers = cfg["Number of Walkers"]
+    starts = np.stack([fits.gen_walker_starts(gens[b], walkers, cfg["Sample Spread"], cfg["Sample Offset Centroid"],
+                                              cfg["Sample Offset Width"], ewsr, rng) for b in range(store.n_bins)])
+    # the ensemble (mda.py:1128-1131): bounds (0, 1/EWSR) are the store's
+    ens = DeviceEnsemble(store, walkers, seed=seed, bin_ids=bin_ids)
+    ens.set_state(starts)
+    steps = cfg["Sample Points"]
+    ens.reserve_chain(steps // thin)
+    ens.advance(steps, thin)
+    # summaries on the device chain (perform_sample_manips, mda.py:1193-1318)
+    summ = ens.summarize(cfg["Burn-in Points"] // thin, cfg["Confidence Interval"], cfg["Num Bins"])
+    points, peaks = summ["points"], summ["peaks"]
+    # chi^2 of the percentile and peak parameter sets (calculate_fit_chis, mda.py:1350-1353)
+    chis = store.chi(np.stack([points[:, :, 0], peaks[:, :, 0]], axis=1))             # [B, 2]
+    results = []
+    for b in range(store.n_bins):
+        values = ([tuple(points[b, l]) for l in range(n_l)], [tuple(peaks[b, l]) for l in range(n_l)])
+        results.append((values, ([], (float(chis[b, 0]), float(chis[b, 1])), float(summ["acceptance_fraction"][b]))))
+    return results, ens
