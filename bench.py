@@ -394,6 +394,18 @@ class GpuWorkload:
         self.ens.run_to_host(steps, 1, 0, host_chain, host_lnp)
         return time.perf_counter() - t0
 
+    def sampler_summary_e2e(self, steps, host_p0, burn_frac=0.25):
+        """Host start positions in, posterior summaries out (percentile and histogram-peak
+        estimates per bin and parameter, acceptance fractions); the chain never leaves HBM."""
+        self.store.synchronize()
+        t0 = time.perf_counter()
+        self.ens.set_state(host_p0)
+        self.ens.reserve_chain(steps)
+        self.ens.advance(steps, 1)
+        summ = self.ens.summarize(int(steps * burn_frac), 0.682689492, 1000)
+        secs = time.perf_counter() - t0
+        return secs, summ
+
     def sampler_parity(self, oracle, steps=3):
         """The sampler's own log-probabilities against the oracle on the positions it visited."""
         self.ens.run_mcmc(self.p0, steps)
@@ -471,6 +483,12 @@ def measure_sampler(work, dist, steps, warmup, e2e_cap=192):
     secs = work.sampler_e2e(e2e_steps, host_p0, host_chain, host_lnp)
     dist.barrier()
     secs = dist.max(secs)
+    work.sampler_summary_e2e(min(e2e_steps, 16), host_p0)                     # warm-up
+    dist.barrier()
+    sum_steps = max(4, min(steps, 1024))
+    sum_secs, _ = work.sampler_summary_e2e(sum_steps, host_p0)
+    dist.barrier()
+    work.summary_e2e = (dist.max(sum_secs), sum_steps)
     return ms, thin, secs, e2e_steps
 
 
@@ -628,6 +646,12 @@ def main():
                     "ensemble_steps_per_s": s_e2e_steps / s_secs,
                     "path": "mdaEnsembleSetState(pinned host p0) + mdaEnsembleRunToHost: full chain + lnprob delivered to pinned "
                             "host memory, chunked D2H overlapped with stepping (PCIe bound: 80 B per evaluation)"},
+            "e2e_summaries": {"value": evals_step * work.summary_e2e[1] / work.summary_e2e[0], "unit": UNIT,
+                              "steps": work.summary_e2e[1], "seconds": work.summary_e2e[0],
+                              "h2d_bytes": bins * cfg["walkers"] * n_l * 8, "d2h_bytes": bins * (n_l * 6 + 1) * 8,
+                              "path": "mdaEnsembleSetState(host p0) + mdaEnsembleAdvance + mdaEnsembleSummarize: the chain stays in "
+                                      "HBM; percentile / histogram-peak estimates (mda.py:1399-1491) and acceptance fractions "
+                                      "come back -- what the reference's worker returns (mda.py:1318)"},
             "gpu_launches": 1,
             "gpu_launches_total_in_run": int(total_launches),
             "ensemble_steps_per_s": args.steps / (s_ms * 1e-3),

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -383,6 +384,8 @@ struct MdaEnsemble {
     long long keep_cap = 0, kept = 0, steps = 0;
     bool has_state = false;
     long long *d_prof = nullptr;     // [bins][8] section cycle counters of the last launch (debug)
+    void *scratch = nullptr;         // device scratch of the posterior reductions, grown on demand
+    size_t scratch_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
 };
@@ -804,6 +807,7 @@ void mdaEnsembleFree(void *ens) {
     if (e->d_chain) cudaFree(e->d_chain);
     if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
     if (e->d_prof) cudaFree(e->d_prof);
+    if (e->scratch) cudaFree(e->scratch);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (e->chunk_done[i]) cudaEventDestroy(e->chunk_done[i]);
@@ -1040,6 +1044,18 @@ int mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double
 
 namespace {
 
+// Device scratch owned by the ensemble: one allocation reused by every summary call.
+int ensure_scratch(MdaEnsemble *e, size_t bytes) {
+    if (bytes <= e->scratch_bytes) return MDA_OK;
+    MDA_CUDA(cudaStreamSynchronize(e->store->stream), "summary scratch");
+    if (e->scratch) cudaFree(e->scratch);
+    e->scratch = nullptr;
+    e->scratch_bytes = 0;
+    MDA_CUDA(cudaMalloc(&e->scratch, bytes), "summary scratch");
+    e->scratch_bytes = bytes;
+    return MDA_OK;
+}
+
 double key_to_double(unsigned long long k) {
     const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
     double x;
@@ -1090,14 +1106,17 @@ int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<u
             remaining[c * n_ranks + r] = ranks[c * n_ranks + r];
         }
     }
-    unsigned long long *d_prefix = nullptr;
-    long long *d_remaining = nullptr;
-    int *d_top = nullptr;
-    unsigned int *d_hist = nullptr;
-    cudaError_t err = cudaMalloc((void **)&d_prefix, sizeof(unsigned long long) * 2 * n_state);
-    if (err == cudaSuccess) err = cudaMalloc((void **)&d_remaining, sizeof(long long) * 2 * n_state);
-    if (err == cudaSuccess) err = cudaMalloc((void **)&d_top, sizeof(int) * cols);
-    if (err == cudaSuccess) err = cudaMalloc((void **)&d_hist, sizeof(unsigned int) * n_state * 4096);
+    auto round_up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_prefix = round_up(sizeof(unsigned long long) * 2 * n_state), b_rem = round_up(sizeof(long long) * 2 * n_state),
+                 b_top = round_up(sizeof(int) * cols), b_hist = round_up(sizeof(unsigned int) * n_state * 4096);
+    int rc0 = ensure_scratch(e, b_prefix + b_rem + b_top + b_hist);
+    if (rc0) return rc0;
+    char *base = static_cast<char *>(e->scratch);
+    unsigned long long *d_prefix = reinterpret_cast<unsigned long long *>(base);
+    long long *d_remaining = reinterpret_cast<long long *>(base + b_prefix);
+    int *d_top = reinterpret_cast<int *>(base + b_prefix + b_rem);
+    unsigned int *d_hist = reinterpret_cast<unsigned int *>(base + b_prefix + b_rem + b_top);
+    cudaError_t err = cudaSuccess;
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(unsigned long long) * 2 * n_state, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_remaining, remaining.data(), sizeof(long long) * 2 * n_state, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_top, top.data(), sizeof(int) * cols, cudaMemcpyHostToDevice, s->stream);
@@ -1107,7 +1126,6 @@ int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<u
     if (err == cudaSuccess) g_launches.fetch_add(3ull * (unsigned long long)((max_top + 11) / 12), std::memory_order_relaxed);
     if (err == cudaSuccess) err = cudaMemcpyAsync(prefix.data(), d_prefix, sizeof(unsigned long long) * n_state, cudaMemcpyDeviceToHost, s->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
-    cudaFree(d_prefix); cudaFree(d_remaining); cudaFree(d_top); cudaFree(d_hist);
     if (err != cudaSuccess) return cuda_fail(err, "order-statistic selection");
     values.resize(n_state);
     for (size_t i = 0; i < n_state; ++i) values[i] = key_to_double(prefix[i]);
@@ -1116,8 +1134,22 @@ int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<u
 
 }  // namespace
 
+namespace {
+struct StageTimer {
+    bool on = getenv("MDA_SUMMARY_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mda summary] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
 int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterval, int numBins,
                          double *points, double *peaks, double *acceptFrac) {
+    StageTimer timer;
     MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleSummarize");
     if (!e) return MDA_ERR_BAD_ARGUMENT;
     if (firstKept < 0 || firstKept >= e->kept)
@@ -1136,38 +1168,20 @@ int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterv
     // 1. smallest / largest sample per column
     std::vector<unsigned long long> mm(2 * cols);
     for (size_t c = 0; c < cols; ++c) { mm[2 * c] = ~0ull; mm[2 * c + 1] = 0ull; }
-    unsigned long long *d_mm = nullptr;
-    MDA_CUDA(cudaMalloc((void **)&d_mm, sizeof(unsigned long long) * 2 * cols), "summary min/max");
+    if ((rc = ensure_scratch(e, sizeof(unsigned long long) * 2 * cols))) return rc;
+    unsigned long long *d_mm = static_cast<unsigned long long *>(e->scratch);
     cudaError_t err = cudaMemcpyAsync(d_mm, mm.data(), sizeof(unsigned long long) * 2 * cols, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) err = launch_chain_minmax(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_mm, g_rt.sm_count, s->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(mm.data(), d_mm, sizeof(unsigned long long) * 2 * cols, cudaMemcpyDeviceToHost, s->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
-    cudaFree(d_mm);
     if (err != cudaSuccess) return cuda_fail(err, "summary min/max");
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    timer.lap("sync + min/max");
 
-    // 2. percentile error bars (calc_param_values, mda.py:1426-1431)
-    const double pct[3] = {100.0 * (0.5 - confidenceInterval / 2.0), 100.0 * 0.5, 100.0 * (0.5 + confidenceInterval / 2.0)};
-    std::vector<long long> ranks(cols * 6);
-    std::vector<double> vals;
-    if (points) {
-        RankPair rp[3];
-        for (int i = 0; i < 3; ++i) rp[i] = percentile_ranks(n, pct[i]);
-        for (size_t c = 0; c < cols; ++c)
-            for (int i = 0; i < 3; ++i) { ranks[c * 6 + 2 * i] = rp[i].lower; ranks[c * 6 + 2 * i + 1] = rp[i].upper; }
-        if ((rc = select_ranks(e, k0, k1, mm, ranks, 6, vals))) return rc;
-        for (size_t c = 0; c < cols; ++c) {
-            double v[3];
-            for (int i = 0; i < 3; ++i) v[i] = numpy_lerp(vals[c * 6 + 2 * i], vals[c * 6 + 2 * i + 1], rp[i].gamma);
-            points[c * 3 + 0] = v[1];
-            points[c * 3 + 1] = v[2] - v[1];
-            points[c * 3 + 2] = v[1] - v[0];
-        }
-    }
-
-    // 3. histogram peak and its error bars (find_most_likely_values, mda.py:1436-1491)
+    // 2. the histogram of find_most_likely_values (mda.py:1466-1467) needs only min and max
+    const size_t nb = (size_t)numBins;
+    std::vector<unsigned int> hist;
     if (peaks) {
-        const size_t nb = (size_t)numBins;
         std::vector<double> edges(cols * (nb + 1));
         for (size_t c = 0; c < cols; ++c) {                       // numpy.linspace(first, last, nb + 1)
             const double first = key_to_double(mm[2 * c]), last = key_to_double(mm[2 * c + 1]);
@@ -1176,52 +1190,78 @@ int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterv
             for (size_t i = 0; i <= nb; ++i) { const double y = (double)i * step; ed[i] = y + first; }
             ed[nb] = last;
         }
-        double *d_edges = nullptr;
-        unsigned int *d_hist = nullptr;
-        std::vector<unsigned int> hist(cols * nb);
-        err = cudaMalloc((void **)&d_edges, sizeof(double) * edges.size());
-        if (err == cudaSuccess) err = cudaMalloc((void **)&d_hist, sizeof(unsigned int) * hist.size());
+        hist.resize(cols * nb);
+        const size_t b_edges = (sizeof(double) * edges.size() + 255) & ~(size_t)255;
+        if ((rc = ensure_scratch(e, b_edges + sizeof(unsigned int) * hist.size()))) return rc;
+        double *d_edges = static_cast<double *>(e->scratch);
+        unsigned int *d_hist = reinterpret_cast<unsigned int *>(static_cast<char *>(e->scratch) + b_edges);
+        err = cudaSuccess;
         if (err == cudaSuccess) err = cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * hist.size(), s->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(d_edges, edges.data(), sizeof(double) * edges.size(), cudaMemcpyHostToDevice, s->stream);
         if (err == cudaSuccess) err = launch_chain_hist(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_edges, numBins, d_hist, g_rt.sm_count, s->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned int) * hist.size(), cudaMemcpyDeviceToHost, s->stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
-        cudaFree(d_edges); cudaFree(d_hist);
         if (err != cudaSuccess) return cuda_fail(err, "summary histogram");
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        std::vector<RankPair> rp(cols * 3);
-        std::vector<char> flat(cols, 0);
-        for (size_t c = 0; c < cols; ++c) {
+    }
+    timer.lap("edges + histogram");
+
+    // 3. all percentiles of both estimators in ONE selection: six ranks for calc_param_values
+    //    (mda.py:1426-1431), six around the histogram peak (mda.py:1468-1489)
+    const double pct[3] = {100.0 * (0.5 - confidenceInterval / 2.0), 100.0 * 0.5, 100.0 * (0.5 + confidenceInterval / 2.0)};
+    const int n_ranks = peaks ? 12 : 6;
+    std::vector<long long> ranks(cols * (size_t)n_ranks, 0);
+    std::vector<RankPair> rp(cols * 6);
+    std::vector<char> flat(cols, 0);
+    for (size_t c = 0; c < cols; ++c) {
+        for (int i = 0; i < 3; ++i) rp[c * 6 + i] = percentile_ranks(n, pct[i]);
+        if (peaks) {
             const double first = key_to_double(mm[2 * c]), last = key_to_double(mm[2 * c + 1]);
-            if (1.0e-7 > std::fabs(last - first)) { flat[c] = 1; for (int i = 0; i < 6; ++i) ranks[c * 6 + i] = 0; continue; }
-            const unsigned int *h = hist.data() + c * nb;
-            size_t ind = 0;
-            for (size_t i = 1; i < nb; ++i) if (h[i] > h[ind]) ind = i;             // numpy.argmax: first maximum
-            double quantile = 0.0;
-            for (size_t j = 0; j <= ind; ++j) quantile += (double)h[j];
-            quantile /= (double)n;
-            const double peak_percentile = 100.0 * quantile;
-            double lo_p = peak_percentile - 100.0 * (confidenceInterval / 2.0);
-            if (lo_p < 0.0) lo_p = 0.0;
-            double hi_p = peak_percentile + 100.0 * (confidenceInterval / 2.0);
-            if (hi_p > 100.0) hi_p = 100.0;
-            const double p3[3] = {lo_p, peak_percentile, hi_p};
-            for (int i = 0; i < 3; ++i) {
-                rp[c * 3 + i] = percentile_ranks(n, p3[i]);
-                ranks[c * 6 + 2 * i] = rp[c * 3 + i].lower;
-                ranks[c * 6 + 2 * i + 1] = rp[c * 3 + i].upper;
+            if (1.0e-7 > std::fabs(last - first)) {
+                flat[c] = 1;
+                for (int i = 3; i < 6; ++i) rp[c * 6 + i] = RankPair{0, 0, 0.0};
+            } else {
+                const unsigned int *h = hist.data() + c * nb;
+                size_t ind = 0;
+                for (size_t i = 1; i < nb; ++i) if (h[i] > h[ind]) ind = i;             // numpy.argmax: first maximum
+                double quantile = 0.0;
+                for (size_t j = 0; j <= ind; ++j) quantile += (double)h[j];
+                quantile /= (double)n;
+                const double peak_percentile = 100.0 * quantile;
+                double lo_p = peak_percentile - 100.0 * (confidenceInterval / 2.0);
+                if (lo_p < 0.0) lo_p = 0.0;
+                double hi_p = peak_percentile + 100.0 * (confidenceInterval / 2.0);
+                if (hi_p > 100.0) hi_p = 100.0;
+                const double p3[3] = {lo_p, peak_percentile, hi_p};
+                for (int i = 0; i < 3; ++i) rp[c * 6 + 3 + i] = percentile_ranks(n, p3[i]);
             }
         }
-        if ((rc = select_ranks(e, k0, k1, mm, ranks, 6, vals))) return rc;
-        for (size_t c = 0; c < cols; ++c) {
-            if (flat[c]) { peaks[c * 3] = key_to_double(mm[2 * c]); peaks[c * 3 + 1] = 0.0; peaks[c * 3 + 2] = 0.0; continue; }
-            double v[3];
-            for (int i = 0; i < 3; ++i) v[i] = numpy_lerp(vals[c * 6 + 2 * i], vals[c * 6 + 2 * i + 1], rp[c * 3 + i].gamma);
-            peaks[c * 3 + 0] = v[1];
-            peaks[c * 3 + 1] = v[2] - v[1];
-            peaks[c * 3 + 2] = v[1] - v[0];
+        for (int i = 0; i < n_ranks / 2; ++i) {
+            ranks[c * n_ranks + 2 * i] = rp[c * 6 + i].lower;
+            ranks[c * n_ranks + 2 * i + 1] = rp[c * 6 + i].upper;
         }
     }
+    std::vector<double> vals;
+    if ((rc = select_ranks(e, k0, k1, mm, ranks, n_ranks, vals))) return rc;
+    for (size_t c = 0; c < cols; ++c) {
+        double v[6];
+        for (int i = 0; i < n_ranks / 2; ++i)
+            v[i] = numpy_lerp(vals[c * n_ranks + 2 * i], vals[c * n_ranks + 2 * i + 1], rp[c * 6 + i].gamma);
+        if (points) {
+            points[c * 3 + 0] = v[1];
+            points[c * 3 + 1] = v[2] - v[1];
+            points[c * 3 + 2] = v[1] - v[0];
+        }
+        if (peaks) {
+            if (flat[c]) { peaks[c * 3] = key_to_double(mm[2 * c]); peaks[c * 3 + 1] = 0.0; peaks[c * 3 + 2] = 0.0; }
+            else {
+                peaks[c * 3 + 0] = v[4];
+                peaks[c * 3 + 1] = v[5] - v[4];
+                peaks[c * 3 + 2] = v[4] - v[3];
+            }
+        }
+    }
+    timer.lap("order statistics + lerp");
 
     // 4. acceptance fraction (mda.py:1316: np.mean(sampler.acceptance_fraction))
     if (acceptFrac) {

@@ -96,7 +96,7 @@ cudaError_t launch_bvls(const double *gram, const double *rhs, const double *lo,
                         cudaStream_t stream);
 
 // ---- posterior reductions on the device chain (summary_kernel.cu) ---------------------------------
-constexpr int kMaxRanks = 8;           // order statistics selected together per (bin, dim) column
+constexpr int kMaxRanks = 12;          // order statistics selected together per (bin, dim) column
 // minmax[cols][2]: order-preserving keys of the smallest / largest sample (init ~0 / 0)
 cudaError_t launch_chain_minmax(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
                                 unsigned long long *minmax, int sm_count, cudaStream_t stream);

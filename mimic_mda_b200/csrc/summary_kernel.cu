@@ -33,17 +33,33 @@ struct ChainView {
     int bins, walkers, n_l;
 };
 
+// Visit every sample of column (bin, l) owned by this thread: four independent loads are in
+// flight per thread, enough bytes in flight per SM to run at HBM rate with ~1000 threads.
+template <typename F>
+__device__ __forceinline__ void for_each_sample(const ChainView &v, int bin, int l, F visit) {
+    const int stride = blockDim.y;
+    for (long long k = v.k0 + blockIdx.y; k < v.k1; k += gridDim.y) {
+        const double *slab = v.chain + ((size_t)k * v.bins + bin) * v.walkers * v.n_l + l;
+        int w = threadIdx.y;
+        for (; w + 3 * stride < v.walkers; w += 4 * stride) {
+            const double x0 = slab[(size_t)w * v.n_l];
+            const double x1 = slab[(size_t)(w + stride) * v.n_l];
+            const double x2 = slab[(size_t)(w + 2 * stride) * v.n_l];
+            const double x3 = slab[(size_t)(w + 3 * stride) * v.n_l];
+            visit(x0); visit(x1); visit(x2); visit(x3);
+        }
+        for (; w < v.walkers; w += stride) visit(slab[(size_t)w * v.n_l]);
+    }
+}
+
 __global__ void __launch_bounds__(256) minmax_kernel(ChainView v, unsigned long long *__restrict__ mm) {
     const int l = threadIdx.x, bin = blockIdx.x;
     unsigned long long lo = ~0ull, hi = 0ull;
-    for (long long k = v.k0 + blockIdx.y; k < v.k1; k += gridDim.y) {
-        const double *slab = v.chain + ((size_t)k * v.bins + bin) * v.walkers * v.n_l;
-        for (int w = threadIdx.y; w < v.walkers; w += blockDim.y) {
-            const unsigned long long key = to_key(slab[(size_t)w * v.n_l + l]);
-            lo = key < lo ? key : lo;
-            hi = key > hi ? key : hi;
-        }
-    }
+    for_each_sample(v, bin, l, [&](double x) {
+        const unsigned long long key = to_key(x);
+        lo = key < lo ? key : lo;
+        hi = key > hi ? key : hi;
+    });
     __shared__ unsigned long long s_lo[32], s_hi[32];
     if (threadIdx.y == 0) { s_lo[l] = ~0ull; s_hi[l] = 0ull; }
     __syncthreads();
@@ -68,19 +84,15 @@ __global__ void __launch_bounds__(256) hist_kernel(ChainView v, const double *__
     const double norm = (double)n_bins / (last - first);
     unsigned int *h = hist + col * (size_t)n_bins;
     if (!(last > first)) return;
-    for (long long k = v.k0 + blockIdx.y; k < v.k1; k += gridDim.y) {
-        const double *slab = v.chain + ((size_t)k * v.bins + bin) * v.walkers * v.n_l;
-        for (int w = threadIdx.y; w < v.walkers; w += blockDim.y) {
-            const double x = slab[(size_t)w * v.n_l + l];
-            // numpy: f_indices = ((x - first_edge) * norm_numerator) / norm_denom
-            int idx = (int)(__dmul_rn(__dsub_rn(x, first), (double)n_bins) / __dsub_rn(last, first));
-            (void)norm;
-            if (idx == n_bins) idx -= 1;
-            if (x < e[idx]) idx -= 1;
-            else if (idx != n_bins - 1 && x >= e[idx + 1]) idx += 1;
-            atomicAdd(&h[idx], 1u);
-        }
-    }
+    for_each_sample(v, bin, l, [&](double x) {
+        // any estimate within one bin of the truth will do: numpy corrects its own estimate
+        // against the edges in exactly this way
+        int idx = (int)((x - first) * norm);
+        idx = idx < 0 ? 0 : (idx >= n_bins ? n_bins - 1 : idx);
+        if (x < e[idx]) idx -= 1;
+        else if (idx != n_bins - 1 && x >= e[idx + 1]) idx += 1;
+        atomicAdd(&h[idx], 1u);
+    });
 }
 
 constexpr int kDigitBits = 12;
@@ -98,6 +110,7 @@ struct SelectState {
     int n_ranks;
 };
 
+template <int NR>
 __global__ void __launch_bounds__(256) select_hist_kernel(ChainView v, SelectState st, int pass) {
     const int l = threadIdx.x, bin = blockIdx.x;
     const size_t col = (size_t)bin * v.n_l + l;
@@ -106,23 +119,33 @@ __global__ void __launch_bounds__(256) select_hist_kernel(ChainView v, SelectSta
     const int lo_bit = hi_bit > kDigitBits ? hi_bit - kDigitBits : 0;
     const unsigned long long digit_mask = (hi_bit - lo_bit >= 64) ? ~0ull : ((1ull << (hi_bit - lo_bit)) - 1ull);
     const unsigned long long above = hi_bit >= 64 ? 0ull : (~0ull << hi_bit);
-    unsigned long long pre[kMaxRanks];
-    bool lead[kMaxRanks];
-    for (int r = 0; r < st.n_ranks; ++r) {
-        pre[r] = st.prefix[col * st.n_ranks + r];
-        lead[r] = true;
-        for (int q = 0; q < r; ++q) lead[r] = lead[r] && (pre[q] != pre[r]);      // equal prefixes share a histogram
-    }
-    for (long long k = v.k0 + blockIdx.y; k < v.k1; k += gridDim.y) {
-        const double *slab = v.chain + ((size_t)k * v.bins + bin) * v.walkers * v.n_l;
-        for (int w = threadIdx.y; w < v.walkers; w += blockDim.y) {
-            const unsigned long long key = to_key(slab[(size_t)w * v.n_l + l]);
-            const unsigned int digit = (unsigned int)((key >> lo_bit) & digit_mask);
-            for (int r = 0; r < st.n_ranks; ++r)
-                if (lead[r] && (key & above) == (pre[r] & above))
-                    atomicAdd(&st.hist[(col * st.n_ranks + r) * kDigits + digit], 1u);
+    // the ranks' prefixes live in registers (NR is a compile-time bound, loops fully unrolled);
+    // a rank whose prefix equals an earlier rank's shares that rank's histogram
+    unsigned long long pre[NR];
+    unsigned int lead = 0;
+    unsigned long long pre_min = ~0ull, pre_max = 0ull;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        pre[r] = r < st.n_ranks ? (st.prefix[col * st.n_ranks + r] & above) : ~0ull;
+        bool is_lead = r < st.n_ranks;
+#pragma unroll
+        for (int q = 0; q < r; ++q) is_lead = is_lead && (pre[q] != pre[r]);
+        if (is_lead) {
+            lead |= 1u << r;
+            pre_min = pre[r] < pre_min ? pre[r] : pre_min;
+            pre_max = pre[r] > pre_max ? pre[r] : pre_max;
         }
     }
+    unsigned int *h = st.hist + col * st.n_ranks * kDigits;
+    for_each_sample(v, bin, l, [&](double x) {
+        const unsigned long long key = to_key(x);
+        const unsigned long long kp = key & above;
+        if (kp < pre_min || kp > pre_max) return;                // outside every bucket still in play
+        const unsigned int digit = (unsigned int)((key >> lo_bit) & digit_mask);
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if ((lead >> r & 1u) && kp == pre[r]) atomicAdd(&h[(size_t)r * kDigits + digit], 1u);
+    });
 }
 
 // One CTA per (column, rank): locate the digit whose cumulative count passes the remaining
@@ -224,7 +247,8 @@ cudaError_t launch_chain_select(const double *chain, long long k0, long long k1,
     for (int p = 0; p < passes; ++p) {
         cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(unsigned int) * n_state * kDigits, stream);
         if (e != cudaSuccess) return e;
-        select_hist_kernel<<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, st, p);
+        if (n_ranks <= 6) select_hist_kernel<6><<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, st, p);
+        else select_hist_kernel<kMaxRanks><<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, st, p);
         select_scan_kernel<<<dim3((unsigned)cols, (unsigned)n_ranks), 256, 0, stream>>>(st, p, n_l);
         select_commit_kernel<<<(unsigned)((n_state + 255) / 256), 256, 0, stream>>>(st, n_state, p, (int)cols);
     }
