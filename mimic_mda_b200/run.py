@@ -1,0 +1,72 @@
+"""Run a reference configuration file end to end on the GPU(s).
+
+    python -m mimic_mda_b200.run config.py [--seed N] [--out results.json]
+    torchrun --nproc-per-node G -m mimic_mda_b200.run config.py      # bins round-robin over G GPUs
+
+``config.py`` is the reference's configuration format: a Python file that fills a ``CONFIG``
+dictionary (mda.py:50-53, config_example.py).  The keys on the likelihood path are honoured
+(input files, energy window, Max Theta, Maximum L, EWSR Fractions, IVGDR subtraction, start
+grid, walkers, sample points, burn-in, confidence interval, Num Bins); plotting, directory
+and CSV-format keys are ignored -- this driver prints / saves the per-bin estimates that
+``fit_and_mcmc`` returns (mda.py:1318) instead of the reference's plot and CSV tree.
+"""
+import argparse
+import json
+import sys
+
+import numpy as np
+
+from . import builder, fits, pipeline, shard
+
+
+def load_config(path):
+    scope = {}
+    with open(path) as fh:
+        exec(compile(fh.read(), path, "exec"), scope)          # mda.py:50-53
+    return scope["CONFIG"]
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("config")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--thin", type=int, default=1)
+    args = ap.parse_args(argv)
+    config = load_config(args.config)
+    rank, _, world = shard.rank_and_world()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")                        # host-side gather only; no data-path collective
+    inputs = builder.build_inputs(config)
+    n_bins = len(inputs["energies"])
+    mine = shard.bins_for_rank(n_bins, rank, world)
+    n_l = config["Maximum L"] + 1
+    starts = fits.calc_start_params([config["Start Pts a%d" % i] for i in range(n_l)])
+    from . import chisq
+    store = chisq.DeviceStore(inputs["consts"][mine], inputs["n_pts"][mine], inputs["bounds"])
+    results, ens = pipeline.fit_and_mcmc_all(store, starts, config, ewsr=config["EWSR Fractions"][:n_l], seed=args.seed,
+                                             bin_ids=mine, rng=np.random.RandomState(args.seed + 7919 * rank), thin=args.thin)
+    ens.close()
+    store.close()
+    merged = shard.gather_results(results, n_bins)
+    if rank == 0:
+        table = []
+        for b, (values, (_, chis, acc)) in enumerate(merged):
+            row = {"Ex": inputs["energies"][b], "n_points": int(inputs["n_pts"][b]), "acceptance_fraction": acc,
+                   "chi2_percentile": chis[0], "chi2_peak": chis[1]}
+            for l in range(n_l):
+                row["a%d" % l] = {"percentile": list(values[0][l]), "peak": list(values[1][l])}
+            table.append(row)
+            print("Ex %6.2f MeV  N=%3d  acc=%.3f  chi2=%.3f  " % (row["Ex"], row["n_points"], acc, chis[0]) +
+                  "  ".join("a%d=%.4f+%.4f-%.4f" % ((l,) + tuple(values[0][l])) for l in range(n_l)))
+        if args.out:
+            with open(args.out, "w") as fh:
+                json.dump(table, fh, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

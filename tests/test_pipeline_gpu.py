@@ -65,3 +65,22 @@ def test_whole_path_and_sharding(tmp_path, cs_lib):
     assert len(merged) == n_bins and all(len(m[0][0]) == 4 for m in merged)
     # rank 0's first bin is global bin 0 with the same walker-start draws => identical result
     np.testing.assert_array_equal(np.array(merged[0][0][0]), np.array(results[0][0][0]))
+
+
+def test_cli_runs_a_reference_style_config(tmp_path, cs_lib):
+    """A configuration file in the reference's format (a Python file filling CONFIG) drives the
+    whole path; keys unrelated to the likelihood path are ignored."""
+    import json
+    from mimic_mda_b200 import run
+    cfg = _config(tmp_path)
+    cfg.update({"Start Pts a0": [0.05, 0.25], "Start Pts a1": [0.05, 0.25], "Start Pts a2": [0.1], "Start Pts a3": [0.05, 0.2],
+                "Shared Lib Path": "./C/libChiSq.so", "Generate Fit Plots": True, "Plot DPI": 300, "Number of Threads": 4})
+    path = tmp_path / "mda_config_test.py"
+    path.write_text("CONFIG = {}\n" + "".join("CONFIG[%r] = %r\n" % kv for kv in cfg.items()))
+    out = tmp_path / "res.json"
+    assert run.main([str(path), "--seed", "3", "--out", str(out)]) == 0
+    table = json.loads(out.read_text())
+    assert len(table) == 6 and abs(table[0]["Ex"] - 10.1) < 1e-12
+    for row in table:
+        assert 0.05 < row["acceptance_fraction"] < 0.95 and row["chi2_percentile"] > 0
+        assert all(0.0 <= row["a%d" % l]["percentile"][0] <= 1.25 for l in range(4))
