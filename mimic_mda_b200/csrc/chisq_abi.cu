@@ -386,6 +386,8 @@ struct MdaEnsemble {
     long long *d_prof = nullptr;     // [bins][8] section cycle counters of the last launch (debug)
     void *scratch = nullptr;         // device scratch of the posterior reductions, grown on demand
     size_t scratch_bytes = 0;
+    void *buckets = nullptr;         // keys gathered for the order-statistic selection
+    size_t bucket_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
 };
@@ -808,6 +810,7 @@ void mdaEnsembleFree(void *ens) {
     if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
     if (e->d_prof) cudaFree(e->d_prof);
     if (e->scratch) cudaFree(e->scratch);
+    if (e->buckets) cudaFree(e->buckets);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (e->chunk_done[i]) cudaEventDestroy(e->chunk_done[i]);
@@ -1049,6 +1052,7 @@ int ensure_scratch(MdaEnsemble *e, size_t bytes) {
     if (bytes <= e->scratch_bytes) return MDA_OK;
     MDA_CUDA(cudaStreamSynchronize(e->store->stream), "summary scratch");
     if (e->scratch) cudaFree(e->scratch);
+    if (e->buckets) cudaFree(e->buckets);
     e->scratch = nullptr;
     e->scratch_bytes = 0;
     MDA_CUDA(cudaMalloc(&e->scratch, bytes), "summary scratch");
@@ -1091,42 +1095,87 @@ int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<u
     MdaStore *s = e->store;
     const size_t cols = (size_t)s->bins * (size_t)s->n_l, n_state = cols * (size_t)n_ranks;
     std::vector<int> top(cols);
-    std::vector<unsigned long long> prefix(2 * n_state, 0ull);
-    std::vector<long long> remaining(2 * n_state, 0);
-    int max_top = 0;
+    std::vector<unsigned long long> prefix(n_state, 0ull);
+    std::vector<long long> remaining(n_state, 0);
+    std::vector<unsigned int> count(n_state, 0u);
     for (size_t c = 0; c < cols; ++c) {
         const unsigned long long x = mm[2 * c] ^ mm[2 * c + 1];
         int t = 0;
         while (t < 64 && (x >> t) != 0ull) ++t;               // bits [0, t) may differ inside the column
         top[c] = t;
-        max_top = std::max(max_top, t);
         const unsigned long long common = t >= 64 ? 0ull : (mm[2 * c] >> t) << t;
         for (int r = 0; r < n_ranks; ++r) {
             prefix[c * n_ranks + r] = common;
             remaining[c * n_ranks + r] = ranks[c * n_ranks + r];
         }
     }
-    auto round_up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t b_prefix = round_up(sizeof(unsigned long long) * 2 * n_state), b_rem = round_up(sizeof(long long) * 2 * n_state),
-                 b_top = round_up(sizeof(int) * cols), b_hist = round_up(sizeof(unsigned int) * n_state * 4096);
-    int rc0 = ensure_scratch(e, b_prefix + b_rem + b_top + b_hist);
-    if (rc0) return rc0;
-    char *base = static_cast<char *>(e->scratch);
-    unsigned long long *d_prefix = reinterpret_cast<unsigned long long *>(base);
-    long long *d_remaining = reinterpret_cast<long long *>(base + b_prefix);
-    int *d_top = reinterpret_cast<int *>(base + b_prefix + b_rem);
-    unsigned int *d_hist = reinterpret_cast<unsigned int *>(base + b_prefix + b_rem + b_top);
-    cudaError_t err = cudaSuccess;
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(unsigned long long) * 2 * n_state, cudaMemcpyHostToDevice, s->stream);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d_remaining, remaining.data(), sizeof(long long) * 2 * n_state, cudaMemcpyHostToDevice, s->stream);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d_top, top.data(), sizeof(int) * cols, cudaMemcpyHostToDevice, s->stream);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_prefix = up(8 * n_state), b_rem = up(8 * n_state), b_count = up(4 * n_state), b_top = up(4 * cols),
+                 b_hist = up(4 * cols * 4096), b_lead = up(n_state), b_off = up(8 * n_state), b_cur = up(4 * n_state);
+    const size_t fixed = b_prefix + b_rem + b_count + b_top + b_hist + b_lead + b_off + b_cur;
+    int rc = ensure_scratch(e, fixed);
+    if (rc) return rc;
+    auto carve = [&](char *base) {
+        struct { unsigned long long *prefix; long long *rem; unsigned int *count; int *top; unsigned int *hist;
+                 unsigned char *lead; long long *off; unsigned int *cur; char *end; } p;
+        p.prefix = reinterpret_cast<unsigned long long *>(base); base += b_prefix;
+        p.rem = reinterpret_cast<long long *>(base); base += b_rem;
+        p.count = reinterpret_cast<unsigned int *>(base); base += b_count;
+        p.top = reinterpret_cast<int *>(base); base += b_top;
+        p.hist = reinterpret_cast<unsigned int *>(base); base += b_hist;
+        p.lead = reinterpret_cast<unsigned char *>(base); base += b_lead;
+        p.off = reinterpret_cast<long long *>(base); base += b_off;
+        p.cur = reinterpret_cast<unsigned int *>(base); base += b_cur;
+        p.end = base;
+        return p;
+    };
+    auto d = carve(static_cast<char *>(e->scratch));
+    cudaError_t err = cudaMemcpyAsync(d.prefix, prefix.data(), 8 * n_state, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d.rem, remaining.data(), 8 * n_state, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d.top, top.data(), 4 * cols, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess)
-        err = launch_chain_select(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_prefix, d_remaining, d_top, d_hist,
-                                  n_ranks, max_top, g_rt.sm_count, s->stream);
-    if (err == cudaSuccess) g_launches.fetch_add(3ull * (unsigned long long)((max_top + 11) / 12), std::memory_order_relaxed);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(prefix.data(), d_prefix, sizeof(unsigned long long) * n_state, cudaMemcpyDeviceToHost, s->stream);
+        err = launch_select_first(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d.prefix, d.rem, d.count, d.top, d.hist,
+                                  n_ranks, g_rt.sm_count, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(prefix.data(), d.prefix, 8 * n_state, cudaMemcpyDeviceToHost, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(count.data(), d.count, 4 * n_state, cudaMemcpyDeviceToHost, s->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
-    if (err != cudaSuccess) return cuda_fail(err, "order-statistic selection");
+    if (err != cudaSuccess) return cuda_fail(err, "order-statistic selection (first pass)");
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    // buckets in play: ranks of a column that fell into the same bucket share one buffer
+    std::vector<unsigned char> lead(n_state, 0);
+    std::vector<long long> offset(n_state, 0);
+    long long total = 0;
+    for (size_t c = 0; c < cols; ++c) {
+        if (top[c] <= 12) continue;                            // decided by the first digit already
+        for (int r = 0; r < n_ranks; ++r) {
+            const size_t i = c * n_ranks + r;
+            int owner = r;
+            for (int q = 0; q < r; ++q)
+                if (prefix[c * n_ranks + q] == prefix[i]) { owner = q; break; }
+            if (owner == r) { lead[i] = 1; offset[i] = total; total += (long long)count[i]; }
+            else offset[i] = offset[c * n_ranks + owner];
+        }
+    }
+    // the bucket buffers have their own allocation, so growing them never moves the state above
+    const size_t b_buf = up(8 * (size_t)(total > 0 ? total : 1));
+    if (b_buf > e->bucket_bytes) {
+        MDA_CUDA(cudaStreamSynchronize(s->stream), "bucket buffers");
+        if (e->buckets) cudaFree(e->buckets);
+        e->buckets = nullptr;
+        e->bucket_bytes = 0;
+        MDA_CUDA(cudaMalloc(&e->buckets, b_buf), "bucket buffers");
+        e->bucket_bytes = b_buf;
+    }
+    unsigned long long *d_buf = static_cast<unsigned long long *>(e->buckets);
+    err = cudaMemcpyAsync(d.lead, lead.data(), n_state, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d.off, offset.data(), 8 * n_state, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess)
+        err = launch_select_finish(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d.prefix, d.rem, d.count, d.top, d.lead,
+                                   d.off, d.cur, d_buf, n_ranks, g_rt.sm_count, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(prefix.data(), d.prefix, 8 * n_state, cudaMemcpyDeviceToHost, s->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
+    if (err != cudaSuccess) return cuda_fail(err, "order-statistic selection (gather / finish)");
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     values.resize(n_state);
     for (size_t i = 0; i < n_state; ++i) values[i] = key_to_double(prefix[i]);
     return MDA_OK;
@@ -1178,31 +1227,30 @@ int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterv
     g_launches.fetch_add(1, std::memory_order_relaxed);
     timer.lap("sync + min/max");
 
-    // 2. the histogram of find_most_likely_values (mda.py:1466-1467) needs only min and max
+    // 2. the histogram of find_most_likely_values (mda.py:1466-1473) needs only min and max; edges,
+    //    counts, argmax and the cumulative count up to the peak bin all stay on the device
     const size_t nb = (size_t)numBins;
-    std::vector<unsigned int> hist;
+    std::vector<int> peak_bin(cols, 0);
+    std::vector<long long> peak_cum(cols, 0);
     if (peaks) {
-        std::vector<double> edges(cols * (nb + 1));
-        for (size_t c = 0; c < cols; ++c) {                       // numpy.linspace(first, last, nb + 1)
-            const double first = key_to_double(mm[2 * c]), last = key_to_double(mm[2 * c + 1]);
-            const double step = (last - first) / (double)nb;
-            double *ed = edges.data() + c * (nb + 1);
-            for (size_t i = 0; i <= nb; ++i) { const double y = (double)i * step; ed[i] = y + first; }
-            ed[nb] = last;
-        }
-        hist.resize(cols * nb);
-        const size_t b_edges = (sizeof(double) * edges.size() + 255) & ~(size_t)255;
-        if ((rc = ensure_scratch(e, b_edges + sizeof(unsigned int) * hist.size()))) return rc;
-        double *d_edges = static_cast<double *>(e->scratch);
-        unsigned int *d_hist = reinterpret_cast<unsigned int *>(static_cast<char *>(e->scratch) + b_edges);
-        err = cudaSuccess;
-        if (err == cudaSuccess) err = cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * hist.size(), s->stream);
-        if (err == cudaSuccess) err = cudaMemcpyAsync(d_edges, edges.data(), sizeof(double) * edges.size(), cudaMemcpyHostToDevice, s->stream);
-        if (err == cudaSuccess) err = launch_chain_hist(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_edges, numBins, d_hist, g_rt.sm_count, s->stream);
-        if (err == cudaSuccess) err = cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned int) * hist.size(), cudaMemcpyDeviceToHost, s->stream);
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t b_mm = up(16 * cols), b_edges = up(8 * cols * (nb + 1)), b_hist = up(4 * cols * nb), b_bin = up(4 * cols), b_cum = up(8 * cols);
+        if ((rc = ensure_scratch(e, b_mm + b_edges + b_hist + b_bin + b_cum))) return rc;
+        char *base = static_cast<char *>(e->scratch);
+        unsigned long long *d_mm2 = reinterpret_cast<unsigned long long *>(base);
+        double *d_edges = reinterpret_cast<double *>(base + b_mm);
+        unsigned int *d_hist = reinterpret_cast<unsigned int *>(base + b_mm + b_edges);
+        int *d_bin = reinterpret_cast<int *>(base + b_mm + b_edges + b_hist);
+        long long *d_cum = reinterpret_cast<long long *>(base + b_mm + b_edges + b_hist + b_bin);
+        err = cudaMemcpyAsync(d_mm2, mm.data(), 16 * cols, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess)
+            err = launch_chain_hist(e->d_chain, k0, k1, s->bins, e->walkers, s->n_l, d_mm2, d_edges, numBins, d_hist, d_bin, d_cum,
+                                    g_rt.sm_count, s->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(peak_bin.data(), d_bin, 4 * cols, cudaMemcpyDeviceToHost, s->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(peak_cum.data(), d_cum, 8 * cols, cudaMemcpyDeviceToHost, s->stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
         if (err != cudaSuccess) return cuda_fail(err, "summary histogram");
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        g_launches.fetch_add(3, std::memory_order_relaxed);
     }
     timer.lap("edges + histogram");
 
@@ -1221,11 +1269,8 @@ int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterv
                 flat[c] = 1;
                 for (int i = 3; i < 6; ++i) rp[c * 6 + i] = RankPair{0, 0, 0.0};
             } else {
-                const unsigned int *h = hist.data() + c * nb;
-                size_t ind = 0;
-                for (size_t i = 1; i < nb; ++i) if (h[i] > h[ind]) ind = i;             // numpy.argmax: first maximum
-                double quantile = 0.0;
-                for (size_t j = 0; j <= ind; ++j) quantile += (double)h[j];
+                // quantile = sum(hist[0..argmax]) / len(values): integer counts sum exactly in double
+                double quantile = (double)peak_cum[c];
                 quantile /= (double)n;
                 const double peak_percentile = 100.0 * quantile;
                 double lo_p = peak_percentile - 100.0 * (confidenceInterval / 2.0);

@@ -100,14 +100,24 @@ constexpr int kMaxRanks = 12;          // order statistics selected together per
 // minmax[cols][2]: order-preserving keys of the smallest / largest sample (init ~0 / 0)
 cudaError_t launch_chain_minmax(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
                                 unsigned long long *minmax, int sm_count, cudaStream_t stream);
-// hist[cols][n_bins] += numpy.histogram counts over edges[cols][n_bins + 1]
+// numpy.histogram(values, bins=n_bins) of every column over [min, max] (edges[cols][n_bins + 1] and
+// hist[cols][n_bins] are scratch), then per column the first fullest bin and the number of
+// samples up to and including it (mda.py:1466-1473).
 cudaError_t launch_chain_hist(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
-                              const double *edges, int n_bins, unsigned int *hist, int sm_count, cudaStream_t stream);
-// radix selection; prefix / remaining are [2][cols][n_ranks] (second half is scratch),
-// hist is [cols][n_ranks][4096], top[cols] = undecided low key bits per column
-cudaError_t launch_chain_select(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
-                                unsigned long long *prefix, long long *remaining, const int *top, unsigned int *hist,
-                                int n_ranks, int max_top, int sm_count, cudaStream_t stream);
+                              const unsigned long long *minmax, double *edges, int n_bins, unsigned int *hist,
+                              int *peak_bin, long long *peak_cum, int sm_count, cudaStream_t stream);
+// radix selection, step 1: one histogram pass over the chain; on return prefix / remaining /
+// count [cols][n_ranks] describe the bucket (12 leading undecided bits fixed) of every rank.
+// hist is [cols][4096] scratch, top[cols] = undecided low key bits per column.
+cudaError_t launch_select_first(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
+                                unsigned long long *prefix, long long *remaining, unsigned int *count, const int *top,
+                                unsigned int *hist, int n_ranks, int sm_count, cudaStream_t stream);
+// step 2: gather the keys of the buckets in play (lead / offset [cols][n_ranks] from the host,
+// cursor scratch) into buf and finish every rank on its bucket; prefix then holds the exact keys.
+cudaError_t launch_select_finish(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
+                                 unsigned long long *prefix, long long *remaining, unsigned int *count, const int *top,
+                                 const unsigned char *lead, const long long *offset, unsigned int *cursor,
+                                 unsigned long long *buf, int n_ranks, int sm_count, cudaStream_t stream);
 
 // Legacy scalar path (one bin, one parameter vector), see scalar_kernel.cu.
 //   consts [1+L][n] dense (row 0 data, rows 1..L dists), params[L], result[0] = value,
