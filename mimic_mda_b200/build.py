@@ -45,19 +45,36 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into libChiSq.so (no-op when up to date)."""
+    """Compile every CUDA source (one nvcc per file, in parallel) and link libChiSq.so;
+    a no-op when the library is newer than its sources."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = nvcc_path()
+    obj_dir = os.path.join(HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    for drop in ("-cudart", "static"):
+        compile_flags.remove(drop)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+            "-Xcompiler", "-fPIC"] + [obj for obj, _ in results] + ["-o", LIB_PATH + ".tmp"]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     if verbose:
-        print(res.stdout + res.stderr)
+        print("".join(log for _, log in results))
     return LIB_PATH
 
 
