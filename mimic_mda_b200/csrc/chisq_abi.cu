@@ -112,6 +112,7 @@ int ensure_runtime() {
     snprintf(g_rt.name, sizeof(g_rt.name), "%s", prop.name);
     MDA_CUDA(configure_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem)");
     MDA_CUDA(configure_ensemble_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, ensemble)");
+    MDA_CUDA(configure_ensemble_mma_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, DMMA ensemble)");
     g_rt.ready = true;
     return MDA_OK;
 }
@@ -187,9 +188,12 @@ struct MdaStore {
     uint32_t magic = kStoreMagic;
     int bins = 0, n_l = 0, max_pts = 0, n_pad = 0;
     std::vector<double> host;        // [bins][n_pad/2][1+L][2]  (the HBM layout)
+    std::vector<double> host_mma;    // [bins][n_tiles][8 (1+L)]  fragment-major copy for the DMMA stepper
+    int n_tiles = 0;                 // angle tiles of 8
     std::vector<int> n_pts;          // [bins]
     std::vector<double> lo, hi;      // [L]
     double *d_consts = nullptr;
+    double *d_consts_mma = nullptr;
     int *d_npts = nullptr;
     double *d_lo = nullptr, *d_hi = nullptr;
     bool dirty = true;
@@ -227,6 +231,20 @@ void write_bin(MdaStore *s, int bin, int n, const double *data, const double *di
         cell[0] = data[j];
         for (int l = 0; l < s->n_l; ++l) cell[(size_t)(1 + l) * 2] = dists[(size_t)l * dist_stride + j];
     }
+    // fragment-major copy (mda_kernels.cuh): per angle tile the rows the DFMA prologue reads, then
+    // the B fragments of mma.m8n8k4 (lane (g, tig) <- dist R + 4 ks + tig at angle 8 t + g)
+    const int n_l = s->n_l, r_lead = n_l % 4, k_steps = n_l / 4, ts = 8 * (n_l + 1);
+    double *mblk = s->host_mma.data() + (size_t)bin * (size_t)s->n_tiles * ts;
+    std::fill(mblk, mblk + (size_t)s->n_tiles * ts, 0.0);
+    for (int j = 0; j < n; ++j) {
+        double *tile = mblk + (size_t)(j >> 3) * ts;
+        const int c = j & 7;
+        tile[c] = data[j];
+        for (int l = 0; l < r_lead; ++l) tile[8 * (1 + l) + c] = dists[(size_t)l * dist_stride + j];
+        for (int ks = 0; ks < k_steps; ++ks)
+            for (int tig = 0; tig < 4; ++tig)
+                tile[8 * (1 + r_lead) + 32 * ks + 4 * c + tig] = dists[(size_t)(r_lead + 4 * ks + tig) * dist_stride + j];
+    }
     s->n_pts[bin] = n;
     s->dirty = true;
 }
@@ -235,6 +253,8 @@ int upload_store(MdaStore *s) {
     if (!s->dirty) return MDA_OK;
     MDA_CUDA(cudaMemcpyAsync(s->d_consts, s->host.data(), sizeof(double) * s->host.size(), cudaMemcpyHostToDevice,
                              s->stream), "store upload (constants)");
+    MDA_CUDA(cudaMemcpyAsync(s->d_consts_mma, s->host_mma.data(), sizeof(double) * s->host_mma.size(), cudaMemcpyHostToDevice,
+                             s->stream), "store upload (fragment-major constants)");
     MDA_CUDA(cudaMemcpyAsync(s->d_npts, s->n_pts.data(), sizeof(int) * s->n_pts.size(), cudaMemcpyHostToDevice,
                              s->stream), "store upload (angle counts)");
     MDA_CUDA(cudaMemcpyAsync(s->d_lo, s->lo.data(), sizeof(double) * s->lo.size(), cudaMemcpyHostToDevice, s->stream),
@@ -392,6 +412,17 @@ struct MdaEnsemble {
     cudaEvent_t chunk_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
 };
 
+// The DMMA stepper wherever it can run; MDA_ENS_IMPL=dfma forces the register-tiled DFMA stepper
+// (which also carries numL < 4 and ensembles too large for the double-buffered layout).
+EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
+    const char *impl = getenv("MDA_ENS_IMPL");
+    EnsembleShape shape{};
+    if (!(impl && strcmp(impl, "dfma") == 0) &&
+        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), &shape))
+        return shape;
+    return choose_ensemble_shape(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
+}
+
 MdaEnsemble *as_ensemble(void *p, const char *fn) {
     MdaEnsemble *e = static_cast<MdaEnsemble *>(p);
     if (!e || e->magic != kEnsembleMagic || !e->store || e->store->magic != kStoreMagic) {
@@ -545,11 +576,14 @@ void *mdaStoreCreate(int numBins, int numL, int maxPts) {
     s->n_pad = maxPts + (maxPts & 1);
     if (s->n_pad == 0) s->n_pad = 2;
     s->host.assign((size_t)numBins * bin_stride(s), 0.0);
+    s->n_tiles = (s->n_pad + 7) / 8;
+    s->host_mma.assign((size_t)numBins * (size_t)s->n_tiles * 8 * (size_t)(numL + 1), 0.0);
     s->n_pts.assign((size_t)numBins, 0);
     s->lo.assign((size_t)numL, 0.0);
     s->hi.assign((size_t)numL, 1.0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_consts, sizeof(double) * (s->host.size() ? s->host.size() : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_consts_mma, sizeof(double) * (s->host_mma.size() ? s->host_mma.size() : 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_npts, sizeof(int) * (size_t)(numBins ? numBins : 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_lo, sizeof(double) * (size_t)numL);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_hi, sizeof(double) * (size_t)numL);
@@ -568,6 +602,7 @@ void mdaStoreFree(void *store) {
     if (s->d_params) cudaFree(s->d_params);
     if (s->d_out) cudaFree(s->d_out);
     if (s->d_consts) cudaFree(s->d_consts);
+    if (s->d_consts_mma) cudaFree(s->d_consts_mma);
     if (s->d_npts) cudaFree(s->d_npts);
     if (s->d_lo) cudaFree(s->d_lo);
     if (s->d_hi) cudaFree(s->d_hi);
@@ -769,7 +804,7 @@ void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, doub
     if (nWalkers < 2 * s->n_l) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: need at least twice as many walkers (%d) as dimensions (%d)", nWalkers, s->n_l); return nullptr; }
     if (!(stretchA > 1.0)) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: stretch scale must be > 1"); return nullptr; }
     if (ensure_runtime() != MDA_OK) return nullptr;
-    const EnsembleShape shape = choose_ensemble_shape(s->bins, nWalkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
+    const EnsembleShape shape = ensemble_shape_for(s, nWalkers);
     if (!shape.fits) {
         set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleCreate: %d walkers x %d dists x %d angles need %zu bytes of shared memory (limit %zu, numL <= %d)",
                   nWalkers, s->n_l, s->n_pad, shape.smem_bytes, g_rt.smem_optin, kMaxRegL);
@@ -910,8 +945,10 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.seed_hi = (unsigned int)(e->seed >> 32);
     args.a = e->a;
     for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
-    const EnsembleShape shape = choose_ensemble_shape(s->bins, e->walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
-    MDA_CUDA(launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
+    args.consts_mma = s->d_consts_mma;
+    args.n_tiles = s->n_tiles;
+    const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
+    MDA_CUDA(shape.mma ? launch_ensemble_mma(args, shape, s->stream) : launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const long long new_keeps = (e->steps + nSteps) / thin - e->steps / thin;
     e->steps += nSteps;

@@ -30,12 +30,14 @@ constexpr int kStatusNaN = 1;          // a log-probability came out NaN (emcee 
 // Shared-memory carve-up, identical on host (size) and device (pointers).
 struct EnsembleSmem {
     size_t consts, pos, lnp, q, part, z, uacc, fast, partner, outside, acc, total;
-    __host__ __device__ EnsembleSmem(int walkers, int n_l, int n_pad, int groups) {
+    // state_in_smem = false: positions, log-probabilities and acceptance counters stay in HBM/L2
+    // (ensembles too large for shared memory, e.g. the reference's 2500 walkers x 8 parameters)
+    __host__ __device__ EnsembleSmem(int walkers, int n_l, int n_pad, int groups, bool state_in_smem) {
         const size_t lp = (size_t)(n_l | 1), h = (size_t)walkers / 2;
         size_t off = 0;
         consts = off;  off += (size_t)n_pad * (size_t)(n_l + 1) * 8;     // [n_pad/2][1+L] double2
-        pos = off;     off += (size_t)walkers * (size_t)n_l * 8;         // [W][L] dense: bulk-stored as is
-        lnp = off;     off += (size_t)walkers * 8;                       // [W]
+        pos = off;     off += state_in_smem ? (size_t)walkers * (size_t)n_l * 8 : 0;   // [W][L] dense: bulk-stored as is
+        lnp = off;     off += state_in_smem ? (size_t)walkers * 8 : 0;                 // [W]
         off = (off + 15) & ~(size_t)15;
         q = off;       off += h * lp * 8;                                // [H][LP]  proposals of the half-step
         part = off;    off += (size_t)groups * h * 8;                    // [G][H]   partial chi^2 per angle group
@@ -44,7 +46,7 @@ struct EnsembleSmem {
         fast = off;    off += 2 * h * 4;                                 // [2][H]   float (L-1) ln z - ln u
         partner = off; off += h * 4;                                     // [H] int
         outside = off; off += h * 4;                                     // [H] int
-        acc = off;     off += (size_t)walkers * 4;                       // [W] unsigned
+        acc = off;     off += state_in_smem ? (size_t)walkers * 4 : 0;   // [W] unsigned
         total = (off + 15) & ~(size_t)15;
     }
 };
@@ -74,7 +76,7 @@ __host__ __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uin
 //                          free); thread 0 also launches the bulk store of a finished step
 //   phase B  H threads   : sum partials in ascending group order, accept / update in place
 //   phase C  H threads   : stage the proposals q = c - z (c - x) of half-step t+1
-template <int L, int WPT>
+template <int L, int WPT, bool GS>          // GS: ensemble state in global memory instead of shared
 __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) {
     constexpr int LP = L | 1;
     constexpr int ROW = L + 1;
@@ -93,10 +95,13 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
     const int H = W >> 1;                         // walkers updated per half-step
     const int n_pad = args.n_pad;
 
-    const EnsembleSmem lay(W, L, n_pad, G);
+    const EnsembleSmem lay(W, L, n_pad, G, !GS);
     double2 *sC = reinterpret_cast<double2 *>(smem_raw + lay.consts);
-    double *sPos = reinterpret_cast<double *>(smem_raw + lay.pos);
-    double *sLnp = reinterpret_cast<double *>(smem_raw + lay.lnp);
+    double *gPos = args.pos + (size_t)bin * W * L;
+    double *gLnp = args.lnp + (size_t)bin * W;
+    unsigned int *gAcc = args.nacc + (size_t)bin * W;
+    double *sPos = GS ? gPos : reinterpret_cast<double *>(smem_raw + lay.pos);
+    double *sLnp = GS ? gLnp : reinterpret_cast<double *>(smem_raw + lay.lnp);
     double *sQ = reinterpret_cast<double *>(smem_raw + lay.q);
     double *sPart = reinterpret_cast<double *>(smem_raw + lay.part);
     double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
@@ -104,24 +109,24 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
     float *sFast = reinterpret_cast<float *>(smem_raw + lay.fast);
     int *sPartner = reinterpret_cast<int *>(smem_raw + lay.partner);
     int *sOutside = reinterpret_cast<int *>(smem_raw + lay.outside);
-    unsigned int *sAcc = reinterpret_cast<unsigned int *>(smem_raw + lay.acc);
+    unsigned int *sAcc = GS ? gAcc : reinterpret_cast<unsigned int *>(smem_raw + lay.acc);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    double *gPos = args.pos + (size_t)bin * W * L;
-    double *gLnp = args.lnp + (size_t)bin * W;
-    unsigned int *gAcc = args.nacc + (size_t)bin * W;
-    if (tid == 0) {                                // constants, positions, log-probabilities: three bulk copies
-        const uint32_t cb = (uint32_t)n_pad * ROW * 8u, pb = (uint32_t)W * L * 8u, lb = (uint32_t)W * 8u;
+    if (tid == 0) {                                // constants, positions, log-probabilities: bulk copies
+        const uint32_t cb = (uint32_t)n_pad * ROW * 8u, pb = GS ? 0u : (uint32_t)W * L * 8u, lb = GS ? 0u : (uint32_t)W * 8u;
         mbar_arrive_expect_tx(&mbar, cb + pb + lb);
         bulk_g2s(sC, reinterpret_cast<const double2 *>(args.consts) + (size_t)bin * (n_pad / 2) * ROW, cb, &mbar);
-        bulk_g2s(sPos, gPos, pb, &mbar);
-        bulk_g2s(sLnp, gLnp, lb, &mbar);
+        if (!GS) {
+            bulk_g2s(sPos, gPos, pb, &mbar);
+            bulk_g2s(sLnp, gLnp, lb, &mbar);
+        }
     }
-    for (int w = tid; w < W; w += T) sAcc[w] = gAcc[w];
+    if (!GS)
+        for (int w = tid; w < W; w += T) sAcc[w] = gAcc[w];
     const int n = args.n_pts[bin];
     const uint32_t bin_id = (uint32_t)args.bin_ids[bin];
     const uint32_t k0 = args.seed_lo, k1 = args.seed_hi;
@@ -189,6 +194,13 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
         bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
         bulk_commit();
     };
+    auto copy_step = [&]() {                       // global-state variant: all threads, HBM -> HBM
+        if (!keeping || slot >= args.keep_cap) return;
+        double *gc = args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L;
+        for (int i = tid; i < W * L; i += T) gc[i] = sPos[i];
+        double *gl = args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W;
+        for (int w = tid; w < W; w += T) gl[w] = sLnp[w];
+    };
 
     const bool prof = args.prof != nullptr && tid == 0;
     long long t_like = 0, t_acc = 0, t_prop = 0, t_chi = 0, t_draw = 0, t_mark = 0;
@@ -214,7 +226,8 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
     for (uint32_t t = t_begin; t < t_end; ++t) {
         const int s_base = (t & 1u) ? H : 0;
         // ---- phase A: likelihood partials (+ bulk store of the finished step, + the draw for t+1)
-        if (tid == 0 && store_pending) store_step();
+        if (GS) { if (store_pending) copy_step(); }
+        else if (tid == 0 && store_pending) store_step();
         for (int wb = 0; wb < H; wb += Tw * WPT) {
             double a[WPT][L], chi[WPT];
 #pragma unroll
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
         MDA_SECTION(t_chi)
         if (t + 1 < t_end) draw(t + 1);
         MDA_SECTION(t_draw)
-        if (tid == 0 && store_pending) bulk_wait_read_all();   // the store has read sPos/sLnp: they may change again
+        if (!GS && tid == 0 && store_pending) bulk_wait_read_all();   // the store has read sPos/sLnp: they may change again
         if (store_pending) { store_pending = false; ++slot; }
         __syncthreads();
         MDA_SECTION(t_like)
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
                     sAcc[gw] += 1u;
                 }
             }
-            if (keeping && (t & 1u)) fence_proxy_async_smem();     // order these writes before a bulk store
+            if (!GS && keeping && (t & 1u)) fence_proxy_async_smem();     // order these writes before a bulk store
         }
         __syncthreads();
         MDA_SECTION(t_acc)
@@ -283,7 +296,9 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
         }
         MDA_SECTION(t_prop)
     }
-    if (tid == 0) {
+    if (GS) {
+        if (store_pending) copy_step();
+    } else if (tid == 0) {
         if (store_pending) store_step();
         bulk_wait_all();
     }
@@ -293,10 +308,12 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
     }
 #undef MDA_SECTION
 
-    for (int i = tid; i < W * L; i += T) gPos[i] = sPos[i];
-    for (int w = tid; w < W; w += T) {
-        gLnp[w] = sLnp[w];
-        gAcc[w] = sAcc[w];
+    if (!GS) {
+        for (int i = tid; i < W * L; i += T) gPos[i] = sPos[i];
+        for (int w = tid; w < W; w += T) {
+            gLnp[w] = sLnp[w];
+            gAcc[w] = sAcc[w];
+        }
     }
     if (saw_nan) atomicOr(args.status, kStatusNaN);
 }
@@ -304,33 +321,33 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
 using EnsKernel = void (*)(const EnsembleArgs);
 
 template <int L>
-EnsKernel pick_ens_wpt(int wpt) {
+EnsKernel pick_ens_wpt(int wpt, bool global_state) {
+    if (global_state) return wpt == 2 ? ensemble_kernel<L, 2, true> : (wpt == 1 ? ensemble_kernel<L, 1, true> : nullptr);
     switch (wpt) {
-        case 1: return ensemble_kernel<L, 1>;
-        case 2: return ensemble_kernel<L, 2>;
-        case 4: return ensemble_kernel<L, 4>;
+        case 1: return ensemble_kernel<L, 1, false>;
+        case 2: return ensemble_kernel<L, 2, false>;
         default: return nullptr;
     }
 }
 
-EnsKernel pick_ens_kernel(int n_l, int wpt) {
+EnsKernel pick_ens_kernel(int n_l, int wpt, bool global_state) {
     switch (n_l) {
-        case 1: return pick_ens_wpt<1>(wpt);
-        case 2: return pick_ens_wpt<2>(wpt);
-        case 3: return pick_ens_wpt<3>(wpt);
-        case 4: return pick_ens_wpt<4>(wpt);
-        case 5: return pick_ens_wpt<5>(wpt);
-        case 6: return pick_ens_wpt<6>(wpt);
-        case 7: return pick_ens_wpt<7>(wpt);
-        case 8: return pick_ens_wpt<8>(wpt);
-        case 9: return pick_ens_wpt<9>(wpt);
-        case 10: return pick_ens_wpt<10>(wpt);
-        case 11: return pick_ens_wpt<11>(wpt);
-        case 12: return pick_ens_wpt<12>(wpt);
-        case 13: return pick_ens_wpt<13>(wpt);
-        case 14: return pick_ens_wpt<14>(wpt);
-        case 15: return pick_ens_wpt<15>(wpt);
-        case 16: return pick_ens_wpt<16>(wpt);
+        case 1: return pick_ens_wpt<1>(wpt, global_state);
+        case 2: return pick_ens_wpt<2>(wpt, global_state);
+        case 3: return pick_ens_wpt<3>(wpt, global_state);
+        case 4: return pick_ens_wpt<4>(wpt, global_state);
+        case 5: return pick_ens_wpt<5>(wpt, global_state);
+        case 6: return pick_ens_wpt<6>(wpt, global_state);
+        case 7: return pick_ens_wpt<7>(wpt, global_state);
+        case 8: return pick_ens_wpt<8>(wpt, global_state);
+        case 9: return pick_ens_wpt<9>(wpt, global_state);
+        case 10: return pick_ens_wpt<10>(wpt, global_state);
+        case 11: return pick_ens_wpt<11>(wpt, global_state);
+        case 12: return pick_ens_wpt<12>(wpt, global_state);
+        case 13: return pick_ens_wpt<13>(wpt, global_state);
+        case 14: return pick_ens_wpt<14>(wpt, global_state);
+        case 15: return pick_ens_wpt<15>(wpt, global_state);
+        case 16: return pick_ens_wpt<16>(wpt, global_state);
         default: return nullptr;
     }
 }
@@ -342,7 +359,7 @@ EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, i
     EnsembleShape s{};
     const int half = walkers / 2;
     s.wpt = half >= 64 ? 2 : 1;
-    if (force_wpt == 1 || force_wpt == 2 || force_wpt == 4) s.wpt = force_wpt;
+    if (force_wpt == 1 || force_wpt == 2) s.wpt = force_wpt;
     int tw = (half + s.wpt - 1) / s.wpt;
     tw = (tw + 31) / 32 * 32;
     if (tw > 256) tw = 256;
@@ -357,7 +374,15 @@ EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, i
     while (groups > 1 && tw * groups > 512) --groups;
     s.groups = groups;
     s.threads = tw * groups;
-    s.smem_bytes = EnsembleSmem(walkers, n_l, n_pad, groups).total;
+    s.smem_bytes = EnsembleSmem(walkers, n_l, n_pad, groups, true).total;
+    s.global_state = false;
+    s.mma = false;
+    if (s.smem_bytes > smem_optin) {               // the ensemble state moves to HBM/L2; shrink the partials if need be
+        s.global_state = true;
+        while (s.groups > 1 && EnsembleSmem(walkers, n_l, n_pad, s.groups, false).total > smem_optin) --s.groups;
+        s.threads = tw * s.groups;
+        s.smem_bytes = EnsembleSmem(walkers, n_l, n_pad, s.groups, false).total;
+    }
     s.fits = n_l >= 1 && n_l <= kMaxRegL && s.smem_bytes <= smem_optin &&
              (size_t)n_pad * (size_t)(n_l + 1) * 8 < (1u << 20);
     return s;
@@ -365,17 +390,18 @@ EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, i
 
 cudaError_t configure_ensemble_kernels(size_t smem_optin) {
     for (int l = 1; l <= kMaxRegL; ++l)
-        for (int wpt = 1; wpt <= 4; wpt *= 2) {
-            cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(pick_ens_kernel(l, wpt)),
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
-            if (e != cudaSuccess) return e;
-        }
+        for (int wpt = 1; wpt <= 2; ++wpt)
+            for (int gs = 0; gs < 2; ++gs) {
+                cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(pick_ens_kernel(l, wpt, gs != 0)),
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+                if (e != cudaSuccess) return e;
+            }
     return cudaSuccess;
 }
 
 cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream) {
     if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
-    EnsKernel k = pick_ens_kernel(args.n_l, shape.wpt);
+    EnsKernel k = pick_ens_kernel(args.n_l, shape.wpt, shape.global_state);
     if (!k || !shape.fits) return cudaErrorInvalidValue;
     EnsembleArgs a = args;
     a.groups = shape.groups;

@@ -7,6 +7,7 @@
 namespace mda {
 
 constexpr int kMaxRegL = 16;        // largest numL the register-tiled kernel is instantiated for
+constexpr int kMinMmaL = 4;         // smallest numL with at least one DMMA k-step (ensemble_mma_kernel.cu)
 
 enum EvalMode : int {
     kLnPost = 0,   // box prior (-inf outside) then chi^2 / -2   (mda.py:1574-1578)
@@ -54,6 +55,7 @@ cudaError_t configure_kernels(size_t smem_optin);
 // ---- device-resident ensemble stepping (ensemble_kernel.cu) -----------------------------
 struct EnsembleArgs {
     const double *consts;      // store layout [bins][n_pad/2][1+L][2]
+    const double *consts_mma;  // fragment-major copy [bins][n_tiles][8 (1+L)] (see mma_tile_doubles), or null
     const int *n_pts;          // [bins]
     const int *bin_ids;        // [bins] global bin index (Philox counter word; partition invariant)
     double *pos;               // [bins][W][L]   ensemble state, updated in place
@@ -64,6 +66,7 @@ struct EnsembleArgs {
     int *status;               // bit flags (1 = NaN log-probability seen)
     long long *prof;           // optional [bins][8] cycle counters per section, or null
     int bins, walkers, n_l, n_pad;
+    int n_tiles;               // angle tiles of 8 in consts_mma
     int n_steps, thin;
     int groups;                // angle groups per walker tile (filled in by launch_ensemble)
     long long step0;           // index of the first step of this launch (RNG counter)
@@ -77,13 +80,25 @@ struct EnsembleArgs {
 struct EnsembleShape {
     int threads, wpt, groups;  // blockDim = walker threads x angle groups
     size_t smem_bytes;
-    bool fits;                 // constants + ensemble fit in shared memory and numL <= kMaxRegL
+    bool fits;                 // the launch is possible (shared memory, numL <= kMaxRegL)
+    bool global_state;         // positions / log-probabilities stay in HBM (ensemble too large for shared memory)
+    bool mma;                  // ensemble_mma_kernel (wpt = walker tiles of 8 in flight per warp)
 };
 
 EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, int sm_count, size_t smem_optin,
                                     int force_groups, int force_wpt);
 cudaError_t configure_ensemble_kernels(size_t smem_optin);
 cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream);
+
+// DMMA variant (ensemble_mma_kernel.cu).  Constants per bin and angle tile t (8 angles, zero padded):
+//   rows 0..R  (R = L % 4): [8] data, then D_l for l < R            -> 8 (1 + R) doubles
+//   k-step ks < L / 4     : [32] B fragment, lane (g, tig) holds D_{R + 4 ks + tig}[8 t + g]
+// i.e. 8 (1 + L) doubles per tile.  Returns false when the shape cannot run (numL < kMinMmaL,
+// numL > kMaxRegL or the double-buffered ensemble does not fit shared memory).
+bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
+                               EnsembleShape *out);
+cudaError_t configure_ensemble_mma_kernels(size_t smem_optin);
+cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream);
 
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
 // gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.

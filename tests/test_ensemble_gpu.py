@@ -19,7 +19,10 @@ def _problem(n_bins, n_l, n_pts, walkers, ragged=True, seed=17):
 
 
 @pytest.mark.parametrize("shape", [(1, 4, 30, 64, 150), (5, 9, 60, 96, 60), (3, 5, 31, 512, 25), (2, 8, 41, 34, 80),
-                                   (2, 1, 7, 8, 50), (1, 16, 24, 40, 30)])
+                                   (2, 1, 7, 8, 50), (1, 16, 24, 40, 30),
+                                   # ensembles larger than shared memory (state in HBM/L2): the reference's own
+                                   # 2500 walkers x 8 parameters (mda_config0.py:93,105), and a wider one
+                                   (1, 8, 41, 2500, 12), (2, 9, 60, 3000, 6)])
 def test_device_chain_equals_cpu_restatement(cs_lib, oracle_lib, shape):
     n_bins, n_l, n_pts, walkers, steps = shape
     consts, counts, lo, hi, p0, _ = _problem(n_bins, n_l, n_pts, walkers)

@@ -60,7 +60,9 @@ def main():
     if args.profile:
         cyc = ens.profile().astype(float)
         per_half = cyc.mean(axis=0) / (2 * args.steps)
-        out["cycles_per_half_step"] = dict(zip(["propose+bar", "bar_after_A", "accept+bar", "chi_loop", "draw"], [round(x, 1) for x in per_half[:5]]))
+        names = (["propose", "chi+barrier", "accept", "chi_loop", "draw", "barrier", "store"] if os.environ.get("MDA_ENS_IMPL") != "dfma" and args.n_l >= 4
+                 else ["propose+bar", "bar_after_A", "accept+bar", "chi_loop", "draw", "-"])
+        out["cycles_per_half_step"] = dict(zip(names, [round(x, 1) for x in per_half[:7]]))
     print(json.dumps(out))
 
 
