@@ -232,7 +232,8 @@ void write_bin(MdaStore *s, int bin, int n, const double *data, const double *di
         for (int l = 0; l < s->n_l; ++l) cell[(size_t)(1 + l) * 2] = dists[(size_t)l * dist_stride + j];
     }
     // fragment-major copy (mda_kernels.cuh): per angle tile the rows the DFMA prologue reads, then
-    // the B fragments of mma.m8n8k4 (lane (g, tig) <- dist R + 4 ks + tig at angle 8 t + g)
+    // the B fragments of mma.m8n8k4 (lane (g, tig) <- dist R + 4 ks + tig at angle 8 t + g); the
+    // distributions are negated here so the device only multiply-accumulates
     const int n_l = s->n_l, r_lead = n_l % 4, k_steps = n_l / 4, ts = 8 * (n_l + 1);
     double *mblk = s->host_mma.data() + (size_t)bin * (size_t)s->n_tiles * ts;
     std::fill(mblk, mblk + (size_t)s->n_tiles * ts, 0.0);
@@ -240,10 +241,10 @@ void write_bin(MdaStore *s, int bin, int n, const double *data, const double *di
         double *tile = mblk + (size_t)(j >> 3) * ts;
         const int c = j & 7;
         tile[c] = data[j];
-        for (int l = 0; l < r_lead; ++l) tile[8 * (1 + l) + c] = dists[(size_t)l * dist_stride + j];
+        for (int l = 0; l < r_lead; ++l) tile[8 * (1 + l) + c] = -dists[(size_t)l * dist_stride + j];
         for (int ks = 0; ks < k_steps; ++ks)
             for (int tig = 0; tig < 4; ++tig)
-                tile[8 * (1 + r_lead) + 32 * ks + 4 * c + tig] = dists[(size_t)(r_lead + 4 * ks + tig) * dist_stride + j];
+                tile[8 * (1 + r_lead) + 32 * ks + 4 * c + tig] = -dists[(size_t)(r_lead + 4 * ks + tig) * dist_stride + j];
     }
     s->n_pts[bin] = n;
     s->dirty = true;
@@ -400,6 +401,8 @@ struct MdaEnsemble {
     double *d_pos = nullptr, *d_lnp = nullptr;
     unsigned int *d_nacc = nullptr;
     int *d_bin_ids = nullptr, *d_status = nullptr;
+    unsigned long long *d_progress = nullptr;   // [bins] hand-over words of the DMMA stepper's (chunk, bin) units
+    unsigned long long launches = 0;            // stepping launches so far (the words' high half)
     double *d_chain = nullptr, *d_lnp_chain = nullptr;
     long long keep_cap = 0, kept = 0, steps = 0;
     bool has_state = false;
@@ -822,6 +825,8 @@ void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, doub
     if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_bin_ids, sizeof(int) * (size_t)(s->bins ? s->bins : 1));
     if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_status, sizeof(int));
     if (err == cudaSuccess) err = cudaMemset(e->d_status, 0, sizeof(int));
+    if (err == cudaSuccess) err = cudaMalloc((void **)&e->d_progress, sizeof(unsigned long long) * (size_t)(s->bins ? s->bins : 1));
+    if (err == cudaSuccess) err = cudaMemset(e->d_progress, 0, sizeof(unsigned long long) * (size_t)(s->bins ? s->bins : 1));
     if (err == cudaSuccess) {
         std::vector<int> ids((size_t)s->bins);
         for (int b = 0; b < s->bins; ++b) ids[(size_t)b] = b;
@@ -841,6 +846,7 @@ void mdaEnsembleFree(void *ens) {
     if (e->d_nacc) cudaFree(e->d_nacc);
     if (e->d_bin_ids) cudaFree(e->d_bin_ids);
     if (e->d_status) cudaFree(e->d_status);
+    if (e->d_progress) cudaFree(e->d_progress);
     if (e->d_chain) cudaFree(e->d_chain);
     if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
     if (e->d_prof) cudaFree(e->d_prof);
@@ -948,7 +954,33 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.consts_mma = s->d_consts_mma;
     args.n_tiles = s->n_tiles;
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
-    MDA_CUDA(shape.mma ? launch_ensemble_mma(args, shape, s->stream) : launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
+    if (shape.mma) {
+        // (chunk of steps, bin) units, chunk-major, unit u on CTA u mod grid.  Every bin has its own CTA
+        // when there are no more bins than SMs; otherwise one CTA per SM walks the list, so that each
+        // SM carries the same share of the run (MDA_ENS_GRID / MDA_ENS_CHUNK override, for experiments).
+        const int capacity = ensemble_mma_capacity(s->n_l, shape, g_rt.sm_count);
+        if (capacity < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
+        int grid = s->bins <= g_rt.sm_count ? s->bins : std::min(capacity, g_rt.sm_count);
+        const int force_grid = env_int("MDA_ENS_GRID", 0);
+        if (force_grid > 0) grid = force_grid;
+        grid = std::max(1, std::min(grid, std::min(capacity, s->bins)));
+        int chunk_steps = nSteps;
+        if (grid < s->bins) {
+            const int rounds_wanted = 16, min_chunk = 8;
+            int n_chunks = (rounds_wanted * grid + s->bins - 1) / s->bins;
+            n_chunks = std::max(1, std::min(n_chunks, nSteps / min_chunk));
+            chunk_steps = (nSteps + n_chunks - 1) / n_chunks;
+        }
+        const int force_chunk = env_int("MDA_ENS_CHUNK", 0);
+        if (force_chunk > 0) chunk_steps = std::min(force_chunk, nSteps);
+        args.chunk_steps = chunk_steps;
+        args.n_chunks = (nSteps + chunk_steps - 1) / chunk_steps;
+        args.progress = e->d_progress;
+        args.launch_serial = (++e->launches) << 32;
+        MDA_CUDA(launch_ensemble_mma(args, shape, grid, s->stream), "ensemble stepping launch (DMMA)");
+    } else {
+        MDA_CUDA(launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const long long new_keeps = (e->steps + nSteps) / thin - e->steps / thin;
     e->steps += nSteps;

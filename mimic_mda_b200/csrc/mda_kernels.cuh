@@ -68,6 +68,9 @@ struct EnsembleArgs {
     int bins, walkers, n_l, n_pad;
     int n_tiles;               // angle tiles of 8 in consts_mma
     int n_steps, thin;
+    int chunk_steps, n_chunks; // DMMA stepper: units of work are (chunk of steps, bin), chunk-major
+    unsigned long long *progress;      // [bins] launch_serial + chunks done: the hand-over word between units of a bin
+    unsigned long long launch_serial;  // distinct per launch, low 32 bits zero
     int groups;                // angle groups per walker tile (filled in by launch_ensemble)
     long long step0;           // index of the first step of this launch (RNG counter)
     long long keep0, keep_cap; // next free slot / capacity of the chain
@@ -91,14 +94,16 @@ cudaError_t configure_ensemble_kernels(size_t smem_optin);
 cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream);
 
 // DMMA variant (ensemble_mma_kernel.cu).  Constants per bin and angle tile t (8 angles, zero padded):
-//   rows 0..R  (R = L % 4): [8] data, then D_l for l < R            -> 8 (1 + R) doubles
-//   k-step ks < L / 4     : [32] B fragment, lane (g, tig) holds D_{R + 4 ks + tig}[8 t + g]
-// i.e. 8 (1 + L) doubles per tile.  Returns false when the shape cannot run (numL < kMinMmaL,
+//   rows 0..R  (R = L % 4): [8] data, then -D_l for l < R           -> 8 (1 + R) doubles
+//   k-step ks < L / 4     : [32] B fragment, lane (g, tig) holds -D_{R + 4 ks + tig}[8 t + g]
+// i.e. 8 (1 + L) doubles per tile; the distributions are stored negated so that the residual
+// d - sum a_l D_l is a pure multiply-accumulate onto d.  Returns false when the shape cannot run (numL < kMinMmaL,
 // numL > kMaxRegL or the double-buffered ensemble does not fit shared memory).
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
                                EnsembleShape *out);
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin);
-cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, cudaStream_t stream);
+int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count);   // co-resident CTAs on the device
+cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);
 
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
 // gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.
