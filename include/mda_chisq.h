@@ -238,9 +238,11 @@ MDA_API int   mdaEnsembleSummarize(void *ens, long long firstKept, double confid
 /* Device pointers of the chain / state, for device-side consumers. */
 MDA_API const double *mdaEnsembleDeviceChain(void *ens);
 MDA_API const double *mdaEnsembleDevicePositions(void *ens);
-/* Debug: per-bin cycle counters of the last Advance, cycles[bin][8] =
- * {proposal+RNG, likelihood, accept, barrier, chain store, 0, 0, 0} as seen by thread 0
- * of each CTA.  The first call (cycles may be NULL) switches the counters on. */
+/* Debug: cycles[bin][128] of the last Advance.  DMMA stepper: clock stamps of one half-step,
+ * [warp < 16][8] = {start, proposals staged | proposals seen, draw made | chi^2 loop done,
+ * chi^2 seen | chi^2 posted, accepted, -, at the barrier, past the barrier}; DFMA stepper: the
+ * first 8 words are section cycle counters of thread 0 {proposal, likelihood, accept, chi^2 loop,
+ * draw}.  The first call (cycles may be NULL) switches the counters on. */
 MDA_API int mdaEnsembleProfile(void *ens, long long *cycles);
 /* The generator itself, evaluated on the host from the same source the kernels compile
  * (csrc/philox.cuh): out[4] = Philox4x32-10(counter[4], key[2]).  For known-answer tests. */

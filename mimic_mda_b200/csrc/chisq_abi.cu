@@ -421,7 +421,7 @@ EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
     EnsembleShape shape{};
     if (!(impl && strcmp(impl, "dfma") == 0) &&
-        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), &shape))
+        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), env_int("MDA_ENS_STAGE", 0), &shape))
         return shape;
     return choose_ensemble_shape(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
 }
@@ -1045,7 +1045,7 @@ int mdaEnsembleProfile(void *ens, long long *cycles) {
     if (!e) return MDA_ERR_BAD_ARGUMENT;
     int rc = ensure_runtime();
     if (rc) return rc;
-    const size_t bytes = sizeof(long long) * 8 * (size_t)(e->store->bins ? e->store->bins : 1);
+    const size_t bytes = sizeof(long long) * 128 * (size_t)(e->store->bins ? e->store->bins : 1);
     if (!e->d_prof) {                                   // first call switches the counters on
         MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleProfile");
         MDA_CUDA(cudaMalloc((void **)&e->d_prof, bytes), "profile counters");

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
         bulk_wait_all();
     }
     if (prof) {
-        long long *o = args.prof + (size_t)bin * 8;
+        long long *o = args.prof + (size_t)bin * 128;
         o[0] = t_prop; o[1] = t_like; o[2] = t_acc; o[3] = t_chi; o[4] = t_draw;
     }
 #undef MDA_SECTION

@@ -1,28 +1,27 @@
 // ensemble_mma_kernel.cu -- device-resident ensemble stepping with the chi-square contraction on
-// the fp64 tensor path (DMMA.8x8x4), SURVEY.md 8f-1.
+// the fp64 tensor path (DMMA.8x8x4) and warp-specialised bookkeeping, SURVEY.md 8f-1.
 //
 // Same job and same random streams as ensemble_kernel.cu (the reference's host loop
 // emcee.EnsembleSampler.run_mcmc -> ln_post_prob per walker, mda.py:1128-1131, 1540-1578, as ONE
-// persistent launch).  How a half-step is laid out here:
+// persistent launch).  A CTA has two kinds of warps:
 //
-//   * A warp owns work items of WT tiles of 8 walkers.  Two register layouts are used:
-//       fragment layout      lane (g, tig) = (lane / 4, lane % 4) holds, for walker g of tile k, the
-//                            proposal elements l = R + 4 ks + tig (ks < Q = L / 4) -- the A fragment of
-//                            mma.m8n8k4 -- and, replicated over the quad, the R = L % 4 leading ones;
-//       walker layout        lane j < 8 WT stands for walker j of the item (Philox draw, accept test).
-//   * residuals of an 8-walker x 8-angle tile: c = d + sum_{l<R} q_l (-D_l) by DFMA, then Q DMMAs
-//     against B fragments of the NEGATED distributions staged fragment-major in shared memory;
-//     chi^2 is accumulated from the C fragment and reduced over the quad by a transposing butterfly.
-//     Every term of the reference's sum (C/ChiSquare.c:188-210) is evaluated exactly once, only the
-//     order of the fp64 additions differs (|error| ~ 1e-16 relative, tested against the oracle).
-//     Why: a DFMA with three distinct register operands is register-bandwidth bound at ~72 % of
-//     the fp64 pipe on sm_100a; DMMA.8x8x4 runs on the same pipe at its full rate with 1/8 of the
-//     issue slots (tools/ubench/dmma_ubench.cu).
-//   * the Philox rounds of the NEXT item's draw are issued between the DMMAs of the current item
-//     (integer work in the issue slots the fp64 pipe leaves free); the warp that evaluated an item
-//     also proposes and accepts it: no staging of proposals or partial sums, ONE barrier per half-step.
-//   * a warp owns the same walkers for a whole chunk of steps: it alone writes their rows (in place,
-//     on acceptance) and bulk-stores them (cp.async.bulk shared -> global) to the HBM chain.
+//   * walker warps (lane = walker of a group of 32): Philox draw, proposal q = c - z (c - x), box
+//     prior, accept / reject, in-place update and the bulk store of kept steps to the HBM chain.
+//     Everything a walker needs between its proposal and its accept test stays in its lane.
+//   * math warps: chi^2 of items of 16 walkers.  Lane (g, tig) = (lane / 4, lane % 4) loads, for
+//     walker g of a tile of 8, the proposal elements l = R + 4 ks + tig (ks < Q = L / 4) -- the A
+//     fragment of mma.m8n8k4 -- and the R = L % 4 leading ones; residuals of an 8-walker x 8-angle
+//     tile are c = d + sum_{l<R} q_l (-D_l) by DFMA, then Q DMMAs against B fragments of the NEGATED
+//     distributions staged fragment-major in shared memory; chi^2 is accumulated from the C fragment
+//     and reduced over the quad.  Every term of the reference's sum (C/ChiSquare.c:188-210) is
+//     evaluated exactly once, only the order of the fp64 additions differs (|error| ~ 1e-16
+//     relative, tested against the oracle).  Why DMMA: a DFMA with three distinct register operands
+//     is register-bandwidth bound at ~72 % of the fp64 pipe on sm_100a; DMMA.8x8x4 runs on the same
+//     pipe at its full rate with 1/8 of the issue slots (tools/ubench/dmma_ubench.cu).
+//   * the two kinds meet through shared memory and one mbarrier pair per group of 32 walkers
+//     (proposals ready -> chi^2 ready), so the fp64 pipe works on the first groups while the others
+//     are still being proposed, and the draw of the next half-step is made while the pipe is busy.
+//     ONE CTA-wide barrier per half-step (the stretch move needs the other half complete).
 //   * CTAs walk a list of (step chunk, bin) units in chunk-major order, unit u on CTA u mod grid; a
 //     unit waits for the previous chunk of its bin through a release/acquire word per bin and hands
 //     the ensemble state over through HBM/L2.  With more bins than SMs (C4: 200 on 148) every SM
@@ -35,15 +34,25 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
-constexpr int kMaxWarps = 8;
+constexpr int kWalkerWarps = 8;        // at most: one group of 32 walkers each at C4
+constexpr int kMathWarps = 8;          // at most: two per scheduler keep the fp64 pipe fed
+constexpr int kMaxGroups = 64;         // groups of 32 walkers per half (mbarrier pairs)
+constexpr int GW = 32;                 // walkers of a group (a walker warp's lanes)
+constexpr size_t kStaticSmem = 8 * (2 + 2 * kMaxGroups + kWalkerWarps) + 16;   // the mbarriers (static __shared__)
 
 struct EnsembleMmaSmem {
-    size_t consts, pos, lnp, acc, total;
+    size_t consts, pos, q, lnp, chi, z, fast, partner, acc, total;
     __host__ __device__ EnsembleMmaSmem(int walkers, int n_l, int n_tiles) {
+        const size_t h = (size_t)walkers / 2;
         size_t off = 0;
         consts = off;  off += (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8;     // [tiles][8 (1+L)] fragment-major
-        pos = off;     off += (size_t)walkers * (size_t)n_l * 8;               // [W][L] dense, updated in place
-        lnp = off;     off += (size_t)walkers * 8;                             // [W]
+        pos = off;     off += (size_t)walkers * (size_t)n_l * 8;               // [W][L] dense, updated in place; bulk-stored as is
+        lnp = off;     off += (size_t)walkers * 8;                             // [W] (16-byte aligned: W is even)
+        q = off;       off += h * (size_t)n_l * 8;                             // [H][L] proposals of the half-step
+        chi = off;     off += h * 8;                                           // [H] chi^2 of the proposals
+        z = off;       off += h * 8;                                           // [H] stretch factor of the next proposal
+        fast = off;    off += 2 * h * 4;                                       // [2][H] float (L-1) ln z - ln u'
+        partner = off; off += h * 4;                                           // [H]
         acc = off;     off += (size_t)walkers * 4;                             // [W] accepted proposals
         total = (off + 15) & ~(size_t)15;
     }
@@ -62,6 +71,24 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Wait on an mbarrier phase that is expected to take hundreds of cycles: the warp sleeps between
+// tests, so that waiting warps do not fill the shared-memory pipeline with barrier probes.
+#ifndef MDA_WAIT_SLEEP_NS
+#define MDA_WAIT_SLEEP_NS 32
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(MDA_WAIT_SLEEP_NS);
+    }
+}
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -75,52 +102,55 @@ __host__ __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uin
     return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
 }
 
-// Philox4x32-10 (philox.cuh) as a state that is advanced a round at a time.
-struct PhiloxState { uint32_t x, y, z, w, k0, k1; };
-__device__ __forceinline__ void philox_round(PhiloxState &s) {
-    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-    const uint32_t hi0 = __umulhi(M0, s.x), lo0 = M0 * s.x;
-    const uint32_t hi1 = __umulhi(M1, s.z), lo1 = M1 * s.z;
-    s.x = hi1 ^ s.y ^ s.k0;
-    s.y = lo1;
-    s.z = hi0 ^ s.w ^ s.k1;
-    s.w = lo0;
-    s.k0 += W0;
-    s.k1 += W1;
-}
-
-// what the stretch move of one walker needs (walker layout)
-struct Draw { double z; float fast; int partner; };
-
-// Work of a warp: items item = warp, warp + n_warps, ... of BOTH halves, for a whole chunk of steps.
-// Only their owner writes the rows of these walkers (in place, on acceptance); the other warps read
+// blockDim = 32 (n_walker_warps + n_math_warps); warps [0, n_walker_warps) are walker warps.
+// A walker warp owns groups grp = warp, warp + n_walker_warps, ... of BOTH halves for a whole chunk of
+// steps: only it writes the rows of these walkers (in place, on acceptance); every other warp reads
 // them as partners, and only in the half-step in which they are not being updated.
-template <int L, int WT>
-__global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const EnsembleArgs args) {
+template <int L, int WT>                        // WT: tiles of 8 walkers per math item (4: a whole group)
+__global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_mma_kernel(const EnsembleArgs args) {
     constexpr int Q = L / 4, R = L % 4, RR = R > 0 ? R : 1;
+    constexpr int IW = 8 * WT;                    // walkers of a math item
     constexpr int TS = 8 * (L + 1);               // doubles per angle tile of the constants
-    constexpr int IW = 8 * WT;                    // walkers of a work item
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar;                 // constants of a unit have landed
+    __shared__ __align__(8) uint64_t full_bar[kMaxGroups]; // proposals of a group are staged
+    __shared__ __align__(8) uint64_t done_bar[kMaxGroups]; // chi^2 of a group is there
+    __shared__ __align__(8) uint64_t store_bar;            // the bulk store of a kept step has read the state
+    __shared__ __align__(8) uint64_t turn_bar[kWalkerWarps]; // walker warp w may queue its gathers
 
     const int tid = threadIdx.x;
     const int T = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, n_warps = T >> 5;
-    const int g = lane >> 2, tig = lane & 3;
+    const int lane = tid & 31, warp = tid >> 5;
     const int W = args.walkers;
     const int H = W >> 1;
     const int NT = args.n_tiles;
+    const int n_groups = (H + GW - 1) / GW;
     const int n_items = (H + IW - 1) / IW;
+    const int n_ww = args.groups & 0xff;          // walker warps (the launch sets it)
+    const int stage_w = max(1, args.groups >> 8); // walker warps that gather at the same time
+    const int n_mw = (T >> 5) - n_ww;
+    const bool walker_warp = warp < n_ww;
 
     const EnsembleMmaSmem lay(W, L, NT);
     const double *sC = reinterpret_cast<const double *>(smem_raw + lay.consts);
     double *sPos = reinterpret_cast<double *>(smem_raw + lay.pos);
+    double *sQ = reinterpret_cast<double *>(smem_raw + lay.q);
     double *sLnp = reinterpret_cast<double *>(smem_raw + lay.lnp);
+    double *sChi = reinterpret_cast<double *>(smem_raw + lay.chi);
+    double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
+    float *sFast = reinterpret_cast<float *>(smem_raw + lay.fast);
+    int *sPartner = reinterpret_cast<int *>(smem_raw + lay.partner);
     unsigned int *sAcc = reinterpret_cast<unsigned int *>(smem_raw + lay.acc);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
+        mbar_init(&store_bar, 1);
+        for (int w = 0; w < kWalkerWarps; ++w) mbar_init(&turn_bar[w], 1);
+        for (int grp = 0; grp < n_groups; ++grp) {
+            mbar_init(&full_bar[grp], 1);
+            mbar_init(&done_bar[grp], (uint32_t)min(GW / IW, n_items - grp * (GW / IW)));   // math items of the group
+        }
         fence_mbar_init();
     }
     __syncthreads();
@@ -130,19 +160,10 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
     const double dim_m1 = (double)(L - 1);
     const float dim_m1f = (float)(L - 1);
 
-    // box prior of the elements this lane holds (mda.py:1124, 1574-1576)
-    double lo_r[RR], hi_r[RR], lo_q[Q], hi_q[Q];
-#pragma unroll
-    for (int l = 0; l < R; ++l) { lo_r[l] = args.lo[l]; hi_r[l] = args.hi[l]; }
-#pragma unroll
-    for (int ks = 0; ks < Q; ++ks) { lo_q[ks] = args.lo[R + 4 * ks + tig]; hi_q[ks] = args.hi[R + 4 * ks + tig]; }
-    const int elem0 = R + tig;                            // first DMMA element of this lane within a row
-    // walker layout: lane j < IW is walker j of the item; its chi^2 arrives from lane 4 (j % 8) + j / 8
-    const int wl_src = 4 * (lane & 7) + ((lane >> 3) & (WT - 1));
-    const bool bulk_ok = (H & 1) == 0;                    // 16-byte alignment of both halves' rows
-
     bool saw_nan = false;
-    uint32_t mbar_phase = 0;
+    uint32_t unit_phase = 0;                               // parity of mbar
+    uint32_t hs_phase = 0;                                 // parity of full_bar / done_bar: one phase per half-step
+    uint32_t stores_issued = 0, stores_seen = 0;           // bulk stores of kept steps (store_bar: one phase each)
     const bool keeping = args.chain != nullptr;
 
     const long long n_units = (long long)args.n_chunks * args.bins;
@@ -179,234 +200,255 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
         const uint32_t t_begin = 2u * (uint32_t)step_first;
         const uint32_t t_end = t_begin + 2u * (uint32_t)steps_here;
 
-        auto philox_start = [&](uint32_t t, int item) {
+        // The Philox draw of walker i of the half updated in half-step t (counter based: it does not
+        // depend on positions), in two parts so that half of the walker warps can put the integer
+        // part before their proposals and the other half after (see below).
+        auto draw_bits = [&](uint32_t t, int i) {
             const int s_base = (t & 1u) ? H : 0;
-            const int i = min(item * IW + (lane & (IW - 1)), H - 1);
-            return PhiloxState{(uint32_t)(s_base + i), bin_id, t, 0u, seed0, seed1};
+            return philox4x32_10(Philox4{(uint32_t)(s_base + i), bin_id, t, 0u}, seed0, seed1);
         };
         // emcee draws per half: u -> z, the partner index, then u'
-        auto philox_finish = [&](const PhiloxState &r, uint32_t t) {
+        auto draw_finish = [&](const Philox4 &r, uint32_t t, int i) {
             const int c_base = (t & 1u) ? 0 : H;
             const double u = uniform53(r.x, r.y);
             // numpy arithmetic is one rounding per operation: no FMA contraction here
             const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);
             const double z2 = __dmul_rn(zr, zr);
-            Draw d;
-            d.z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;                  // ((a-1) u + 1)^2 / a
+            const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;              // ((a-1) u + 1)^2 / a
             const double ua = uniform43(r.w, r.x, r.y);
+            sZ[i] = z;
             // single-precision estimate of (L-1) ln z - ln u'; decides all but near-ties
-            d.fast = dim_m1f * __logf((float)d.z) - __logf((float)ua);
-            d.partner = c_base + (int)__umulhi(r.z, (uint32_t)H);
-            return d;
+            sFast[(t & 1u) * H + i] = dim_m1f * __logf((float)z) - __logf((float)ua);
+            sPartner[i] = c_base + (int)__umulhi(r.z, (uint32_t)H);
         };
 
-        mbar_wait(&mbar, mbar_phase);
-        mbar_phase ^= 1u;
+        mbar_wait(&mbar, unit_phase);
+        unit_phase ^= 1u;
         __syncthreads();
+        if (walker_warp)
+            for (int grp = warp; grp < n_groups; grp += n_ww) {
+                const int i = min(grp * GW + lane, H - 1);
+                draw_finish(draw_bits(t_begin, i), t_begin, i);
+            }
 
-        Draw dr;
-        {
-            PhiloxState ps = philox_start(t_begin, min(warp, n_items - 1));
-#pragma unroll
-            for (int r = 0; r < 10; ++r) philox_round(ps);
-            dr = philox_finish(ps, t_begin);
-        }
-        bool store_in_flight = false;
-
-        for (uint32_t t = t_begin; t < t_end; ++t) {
+        // debug timeline (mdaEnsembleProfile): clock stamps of one half-step, per warp
+        const uint32_t t_prof = (args.prof != nullptr && chunk == 0) ? t_begin + min(81u, 2u * (uint32_t)steps_here - 1u) : 0xffffffffu;
+        for (uint32_t t = t_begin; t < t_end; ++t, hs_phase ^= 1u) {
             const uint32_t half = t & 1u;
+            long long *stamp = (t == t_prof && lane == 0 && warp < 16) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
+#define MDA_STAMP(k) if (stamp) stamp[k] = clock64();
+            MDA_STAMP(0)
             const int s_base = half ? H : 0;          // the half being updated; partners come from the other one
 
-            for (int item = warp; item < n_items; item += n_warps) {
-                const bool last_pass = item + n_warps >= n_items;
-                const uint32_t t_nxt = last_pass ? t + 1 : t;
-                const int item_nxt = last_pass ? warp : item + n_warps;
-                const int w_first = item * IW;            // within the half
-
-                // ---- propose: q = c - z (c - x), in A-fragment order
-                double A[WT][Q], lead[WT][RR];
-                unsigned int out_mask[WT];
+            if (walker_warp) {
+                const bool draw_next = t + 1 < t_end;
+                // ---- proposals of my groups: q = c - z (c - x); box prior
+                unsigned long long out_bits = 0ull;        // bit k: my walker of my k-th group is outside the box
+                int k = 0;
+                for (int grp = warp; grp < n_groups; grp += n_ww, ++k) {
+                    const int i = min(grp * GW + lane, H - 1);
+                    const double z = sZ[i];
+                    const double *xs = sPos + (s_base + i) * L;
+                    const double *xc = sPos + sPartner[i] * L;
+                    double *q = sQ + i * L;
+                    // The gathers of the partner rows are shared-memory-bandwidth bound (random rows: ~3.5-way
+                    // bank conflicts).  The groups take turns at it, in order, so that the first group is staged
+                    // after one group's worth of traffic and the math warps start while the others still load.
+                    if (stamp && z != 123.456) stamp[7] = clock64();                    // debug: my draw has been read
+                    if (k == 0 && warp >= stage_w) mbar_wait_relaxed(&turn_bar[warp], hs_phase);
+                    double c[L], v[L];
 #pragma unroll
-                for (int k = 0; k < WT; ++k) {
-                    const double z = __shfl_sync(0xffffffffu, dr.z, 8 * k + g);
-                    const int partner = __shfl_sync(0xffffffffu, dr.partner, 8 * k + g);
-                    const double *xs = sPos + (s_base + min(w_first + 8 * k + g, H - 1)) * L;
-                    const double *xc = sPos + partner * L;
-                    bool out = false;
+                    for (int l = 0; l < L; ++l) { c[l] = xc[l]; v[l] = xs[l]; }        // all loads before any store
+                    if (k == 0 && warp + stage_w < n_ww) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&turn_bar[warp + stage_w]);          // my loads are queued: next, please
+                    }
+                    // box prior (mda.py:1575): v < lo or v > hi for any element  <=>  the smallest of the margins
+                    // v - lo, hi - v is negative (x - y < 0 <=> x < y exactly; fmin drops NaN margins, and a
+                    // NaN compares false in the reference too).  A min tree instead of 2 L chained compares.
+                    if (stamp && c[L - 1] != 123.456 && v[L - 1] != 123.456) stamp[5] = clock64();   // debug: rows are here
+                    double m[L];
 #pragma unroll
-                    for (int l = 0; l < R; ++l) {
-                        const double c = xc[l];
-                        const double v = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, xs[l])));
-                        lead[k][l] = v;
-                        out = out || (v < lo_r[l]) || (v > hi_r[l]);                    // mda.py:1575
+                    for (int l = 0; l < L; ++l) {
+                        v[l] = __dsub_rn(c[l], __dmul_rn(z, __dsub_rn(c[l], v[l])));
+                        m[l] = fmin(__dsub_rn(v[l], args.lo[l]), __dsub_rn(args.hi[l], v[l]));
                     }
 #pragma unroll
-                    for (int ks = 0; ks < Q; ++ks) {
-                        const double c = xc[elem0 + 4 * ks];
-                        const double v = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, xs[elem0 + 4 * ks])));
-                        A[k][ks] = v;
-                        out = out || (v < lo_q[ks]) || (v > hi_q[ks]);
-                    }
-                    out_mask[k] = __ballot_sync(0xffffffffu, out);
+                    for (int l = 0; l < L; ++l) q[l] = v[l];
+#pragma unroll
+                    for (int w = 1; w < L; w *= 2)
+#pragma unroll
+                        for (int l = 0; l + w < L; l += 2 * w) m[l] = fmin(m[l], m[l + w]);
+                    const bool out = m[0] < 0.0;
+                    if (stamp && (out || m[0] != 123.456)) stamp[6] = clock64();                    // debug: box prior known
+                    out_bits |= (unsigned long long)out << k;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[grp]);
                 }
-                const int my_w = s_base + min(w_first + (lane & (IW - 1)), H - 1);       // walker layout
-                const double oldlnp = sLnp[my_w];
-
-                // ---- chi^2 of WT tiles of 8 walkers against every angle tile, with the Philox rounds of
-                //      the next item's draw in between
-                PhiloxState ps = philox_start(t_nxt, item_nxt);
-                double chi0[WT], chi1[WT];
+                MDA_STAMP(1)
+                // ---- the draw of the next half-step, while the math warps work
+                if (draw_next)
+                    for (int grp = warp; grp < n_groups; grp += n_ww) {
+                        const int i = min(grp * GW + lane, H - 1);
+                        draw_finish(draw_bits(t + 1, i), t + 1, i);
+                    }
+                MDA_STAMP(2)
+                if (stores_seen != stores_issued) {        // the chain store must have read my rows
+                    mbar_wait(&store_bar, (stores_issued - 1u) & 1u);
+                    stores_seen = stores_issued;
+                }
+                // ---- accept / reject
+                k = 0;
+                for (int grp = warp; grp < n_groups; grp += n_ww, ++k) {
+                    const int i = min(grp * GW + lane, H - 1);
+                    const int gw = s_base + i;
+                    const double oldlnp = sLnp[gw];
+                    const float fast = sFast[half * H + i];
+                    double qv[L];
 #pragma unroll
-                for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
-                auto chi_tile = [&](int at) {
-                    const double *tp = sC + at * TS;
-                    const double2 dv = *reinterpret_cast<const double2 *>(tp + 2 * tig);
+                    for (int l = 0; l < L; ++l) qv[l] = sQ[i * L + l];                  // my own proposal, staged above
+                    mbar_wait_relaxed(&done_bar[grp], hs_phase);
+                    MDA_STAMP(3)
+                    // outside the box the log-posterior is -inf (mda.py:1576): never accepted
+                    const double newlnp = ((out_bits >> k) & 1ull) ? -CUDART_INF : sChi[i] * -0.5;    // C/ChiSquare.c:212
+                    saw_nan = saw_nan || (newlnp != newlnp);
+                    const double est = __dsub_rn(newlnp, oldlnp) + (double)fast;
+                    bool accept;
+                    if (fabs(est) > 1e-4) {
+                        accept = est > 0.0;            // far from a tie: the float logs (error < 2e-5) cannot change the sign
+                    } else {                           // emcee's test in full precision (rare: redo the draw)
+                        const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
+                        const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
+                        const double z2 = __dmul_rn(zr, zr);
+                        const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;
+                        const double zlog = __dmul_rn(dim_m1, log(z));
+                        accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(uniform43(r.w, r.x, r.y));
+                    }
+                    if (accept && grp * GW + lane < H) {
+                        double *nx = sPos + gw * L;
+#pragma unroll
+                        for (int l = 0; l < L; ++l) nx[l] = qv[l];
+                        sLnp[gw] = newlnp;
+                        sAcc[gw] += 1u;
+                    }
+                }
+                if (half && until_keep == 1 && keeping) fence_proxy_async_smem();   // a kept step: rows before the bulk store
+                MDA_STAMP(4)
+            } else {
+                // ---- chi^2 of items of WT tiles of 8 walkers against every angle tile
+                const int g = lane >> 2, tig = lane & 3;
+                for (int item = warp - n_ww; item < n_items; item += n_mw) {
+                    const int grp = item / (GW / IW);
+                    const double *row[WT];
+#pragma unroll
+                    for (int k = 0; k < WT; ++k) row[k] = sQ + min(item * IW + 8 * k + g, H - 1) * L;
+                    mbar_wait_relaxed(&full_bar[grp], hs_phase);
+                    MDA_STAMP(1)
+                    double A[WT][Q], lead[WT][RR];
+#pragma unroll
+                    for (int k = 0; k < WT; ++k) {
+#pragma unroll
+                        for (int l = 0; l < R; ++l) lead[k][l] = row[k][l];
+#pragma unroll
+                        for (int ks = 0; ks < Q; ++ks) A[k][ks] = row[k][R + 4 * ks + tig];
+                    }
+                    double chi0[WT], chi1[WT];
+#pragma unroll
+                    for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
+                    // constants of an angle tile are fetched one tile ahead of their use
+                    const double *tp = sC;
+                    double2 dv = *reinterpret_cast<const double2 *>(tp + 2 * tig);
                     double2 Di[RR];
 #pragma unroll
                     for (int l = 0; l < R; ++l) Di[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
                     double Bf[Q];
 #pragma unroll
                     for (int ks = 0; ks < Q; ++ks) Bf[ks] = tp[8 * (1 + R) + 32 * ks + lane];
-                    double c0[WT], c1[WT];
-#pragma unroll
-                    for (int k = 0; k < WT; ++k) {
-                        c0[k] = dv.x;
-                        c1[k] = dv.y;
-#pragma unroll
-                        for (int l = 0; l < R; ++l) {
-                            c0[k] = fma(lead[k][l], Di[l].x, c0[k]);
-                            c1[k] = fma(lead[k][l], Di[l].y, c1[k]);
-                        }
-                    }
-#pragma unroll
-                    for (int ks = 0; ks < Q; ++ks)
-#pragma unroll
-                        for (int k = 0; k < WT; ++k) dmma884(c0[k], c1[k], A[k][ks], Bf[ks]);
-#pragma unroll
-                    for (int k = 0; k < WT; ++k) {
-                        chi0[k] = fma(c0[k], c0[k], chi0[k]);
-                        chi1[k] = fma(c1[k], c1[k], chi1[k]);
-                    }
-                };
-                int at = 0;
-                const int n_fused = min(NT, 5);
-                for (; at < n_fused; ++at) {
-                    chi_tile(at);
-                    philox_round(ps);
-                    philox_round(ps);
-                }
-                for (int r = 2 * n_fused; r < 10; ++r) philox_round(ps);
-                Draw dn;
-                if (at < NT) {                            // the conversions of the draw under one more tile
-                    chi_tile(at);
-                    ++at;
-                    dn = philox_finish(ps, t_nxt);
-                } else {
-                    dn = philox_finish(ps, t_nxt);
-                }
 #pragma unroll 2
-                for (; at < NT; ++at) chi_tile(at);
-
-                // ---- quad sums, transposed into the walker layout
-                double offer;
-                if (WT == 4) {
-                    // lane tig ends up with the quad's sum of tile tig
-                    double s[4];
+                    for (int at = 0; at < NT; ++at) {
+                        tp = sC + min(at + 1, NT - 1) * TS;
+                        const double2 dv_n = *reinterpret_cast<const double2 *>(tp + 2 * tig);
+                        double2 Di_n[RR];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) s[k] = chi0[k & (WT - 1)] + chi1[k & (WT - 1)];
-                    const bool b0 = (tig & 1) != 0, b1 = (tig & 2) != 0;
-                    const double keepA = b0 ? s[1] : s[0], sendA = b0 ? s[0] : s[1];
-                    const double keepB = b0 ? s[3] : s[2], sendB = b0 ? s[2] : s[3];
-                    const double a01 = keepA + __shfl_xor_sync(0xffffffffu, sendA, 1);     // tile tig & 1
-                    const double a23 = keepB + __shfl_xor_sync(0xffffffffu, sendB, 1);     // tile 2 + (tig & 1)
-                    const double keep = b1 ? a23 : a01, send = b1 ? a01 : a23;
-                    offer = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                } else if (WT == 2) {
-                    const double s0 = chi0[0] + chi1[0], s1 = chi0[WT - 1] + chi1[WT - 1];
-                    const bool b0 = (tig & 1) != 0;
-                    const double keep = b0 ? s1 : s0, send = b0 ? s0 : s1;
-                    offer = keep + __shfl_xor_sync(0xffffffffu, send, 1);                  // tile tig & 1
-                    offer += __shfl_xor_sync(0xffffffffu, offer, 2);
-                } else {
-                    offer = chi0[0] + chi1[0];
-                    offer += __shfl_xor_sync(0xffffffffu, offer, 1);
-                    offer += __shfl_xor_sync(0xffffffffu, offer, 2);
-                }
-                const double chi = __shfl_sync(0xffffffffu, offer, wl_src);
-
-                // ---- accept / reject (walker layout)
-                unsigned int om = out_mask[0];
+                        for (int l = 0; l < R; ++l) Di_n[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
+                        double Bf_n[Q];
 #pragma unroll
-                for (int k = 1; k < WT; ++k) om = ((lane >> 3) == k) ? out_mask[k] : om;
-                const bool outside = ((om >> (4 * (lane & 7))) & 0xFu) != 0u;
-                // outside the box the log-posterior is -inf (mda.py:1576): never accepted
-                const double newlnp = outside ? -CUDART_INF : chi * -0.5;                  // C/ChiSquare.c:212
-                saw_nan = saw_nan || (newlnp != newlnp);
-                const double est = __dsub_rn(newlnp, oldlnp) + (double)dr.fast;
-                bool accept;
-                if (fabs(est) > 1e-3) {
-                    accept = est > 0.0;            // far from a tie: the float logs cannot change the sign
-                } else {                           // emcee's test in full precision (rare: redo the draw for u')
-                    const Philox4 r = philox4x32_10(Philox4{(uint32_t)my_w, bin_id, t, 0u}, seed0, seed1);
-                    const double zlog = __dmul_rn(dim_m1, log(dr.z));
-                    accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(uniform43(r.w, r.x, r.y));
-                }
-                accept = accept && (lane < IW) && (w_first + lane < H);
-                const unsigned int acc_mask = __ballot_sync(0xffffffffu, accept);
-                if (store_in_flight) {                     // the chain store must have read these rows
-                    if (lane == 0) bulk_wait_read_all();
-                    __syncwarp();
-                    store_in_flight = false;
-                }
-                if (accept) {
-                    sLnp[my_w] = newlnp;
-                    sAcc[my_w] += 1u;
-                }
+                        for (int ks = 0; ks < Q; ++ks) Bf_n[ks] = tp[8 * (1 + R) + 32 * ks + lane];
+                        double c0[WT], c1[WT];
 #pragma unroll
-                for (int k = 0; k < WT; ++k) {
-                    if ((acc_mask >> (8 * k + g)) & 1u) {
-                        double *nx = sPos + (s_base + w_first + 8 * k + g) * L;
+                        for (int k = 0; k < WT; ++k) {
+                            c0[k] = dv.x;
+                            c1[k] = dv.y;
 #pragma unroll
-                        for (int l = 0; l < R; ++l)
-                            if (tig == l) nx[l] = lead[k][l];
-#pragma unroll
-                        for (int ks = 0; ks < Q; ++ks) nx[elem0 + 4 * ks] = A[k][ks];
-                    }
-                }
-                dr = dn;
-            }
-            if (half && until_keep == 1 && keeping) fence_proxy_async_smem();   // a kept step: order the rows before the bulk store
-            __syncthreads();
-            if (half && --until_keep == 0) {           // a full step is complete and kept: every warp copies out ITS rows
-                until_keep = args.thin;
-                if (keeping && slot < args.keep_cap) {
-                    double *gc = args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L;
-                    double *gl = args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W;
-                    for (int item = warp; item < n_items; item += n_warps) {
-                        const int w0 = item * IW, nw = min(IW, H - w0);
-#pragma unroll
-                        for (int hb = 0; hb < 2; ++hb) {
-                            const int row0 = hb * H + w0;
-                            if (bulk_ok && nw == IW) {
-                                if (lane == 0) {
-                                    bulk_s2g(gc + (size_t)row0 * L, sPos + row0 * L, (uint32_t)(IW * L * 8));
-                                    bulk_s2g(gl + row0, sLnp + row0, (uint32_t)(IW * 8));
-                                }
-                            } else {
-                                for (int i = lane; i < nw * L; i += 32) gc[(size_t)row0 * L + i] = sPos[row0 * L + i];
-                                if (lane < nw) gl[row0 + lane] = sLnp[row0 + lane];
+                            for (int l = 0; l < R; ++l) {
+                                c0[k] = fma(lead[k][l], Di[l].x, c0[k]);
+                                c1[k] = fma(lead[k][l], Di[l].y, c1[k]);
                             }
                         }
+#pragma unroll
+                        for (int ks = 0; ks < Q; ++ks)
+#pragma unroll
+                            for (int k = 0; k < WT; ++k) dmma884(c0[k], c1[k], A[k][ks], Bf[ks]);
+#pragma unroll
+                        for (int k = 0; k < WT; ++k) {
+                            chi0[k] = fma(c0[k], c0[k], chi0[k]);
+                            chi1[k] = fma(c1[k], c1[k], chi1[k]);
+                        }
+                        dv = dv_n;
+#pragma unroll
+                        for (int l = 0; l < R; ++l) Di[l] = Di_n[l];
+#pragma unroll
+                        for (int ks = 0; ks < Q; ++ks) Bf[ks] = Bf_n[ks];
                     }
-                    if (lane == 0) bulk_commit();
-                    store_in_flight = true;
+                    MDA_STAMP(2)
+                    // quad sums by a transposing butterfly: lane tig ends up with the sum of tile tig % WT
+                    double sum;
+                    if (WT == 4) {
+                        double sv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sv[k] = chi0[k & (WT - 1)] + chi1[k & (WT - 1)];
+                        const bool b0 = (tig & 1) != 0, b1 = (tig & 2) != 0;
+                        const double a01 = (b0 ? sv[1] : sv[0]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[0] : sv[1], 1);   // tile tig & 1
+                        const double a23 = (b0 ? sv[3] : sv[2]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[2] : sv[3], 1);   // tile 2 + (tig & 1)
+                        sum = (b1 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b1 ? a01 : a23, 2);
+                    } else if (WT == 2) {
+                        const double s0 = chi0[0] + chi1[0], s1 = chi0[WT - 1] + chi1[WT - 1];
+                        const bool b0 = (tig & 1) != 0;
+                        sum = (b0 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b0 ? s0 : s1, 1);
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    } else {
+                        sum = chi0[0] + chi1[0];
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    }
+                    const int wk = item * IW + 8 * tig + g;
+                    if (tig < WT && wk < H) sChi[wk] = sum;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&done_bar[grp]);
+                    MDA_STAMP(3)
+                }
+            }
+            if (!walker_warp) { MDA_STAMP(5) }
+            __syncthreads();
+            if (!walker_warp) { MDA_STAMP(6) }
+#undef MDA_STAMP
+            if (half && --until_keep == 0) {           // a full step is complete and kept: one bulk store of the whole state
+                until_keep = args.thin;
+                if (keeping && slot < args.keep_cap) {
+                    if (warp == n_ww && lane == 0) {       // a math warp: it would only wait for proposals now
+                        bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
+                        bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
+                        bulk_commit();
+                        bulk_wait_read_all();
+                        mbar_arrive(&store_bar);
+                    }
+                    ++stores_issued;
                 }
                 ++slot;
             }
         }
 
         // ---- hand the bin back: state to HBM/L2, then the progress word
-        if (lane == 0) bulk_wait_read_all();
         __syncthreads();
         for (int i = tid; i < W * L; i += T) gPos[i] = sPos[i];
         for (int w = tid; w < W; w += T) {
@@ -457,23 +499,26 @@ EnsKernel pick_mma_kernel(int n_l, int wt) {
 }  // namespace
 
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
-                               EnsembleShape *out) {
+                               int force_stage, EnsembleShape *out) {
     if (n_l < kMinMmaL || n_l > kMaxRegL) return false;
     EnsembleShape s{};
     const int half = walkers / 2;
-    const int w_tiles = (half + 7) / 8;
-    // a full warp of walkers per item where the ensemble gives every warp one; fewer tiles per item otherwise
-    s.wpt = w_tiles >= 4 * kMaxWarps ? 4 : (w_tiles >= 2 * kMaxWarps ? 2 : 1);
-    if (n_l > 12 && s.wpt == 4) s.wpt = 2;                     // registers: 4 tiles x 4 k-steps of A fragments
-    if (force_wt == 1 || force_wt == 2 || force_wt == 4) s.wpt = force_wt;
-    int warps = (w_tiles + s.wpt - 1) / s.wpt;
-    if (warps > kMaxWarps) warps = kMaxWarps;
-    s.threads = 32 * warps;
-    s.groups = 1;
+    const int n_groups = (half + GW - 1) / GW;
+    if (n_groups > kMaxGroups) return false;
+    // tiles per math item: a whole group where that still gives every scheduler two math warps
+    int wt = n_groups >= kMathWarps ? 4 : (2 * n_groups >= kMathWarps ? 2 : 1);
+    if (n_l > 12 && wt == 4) wt = 2;                                         // registers: A fragments of 4 tiles x 4 k-steps
+    if (force_wt == 1 || force_wt == 2 || force_wt == 4) wt = force_wt;
+    const int n_items = (half + 8 * wt - 1) / (8 * wt);
+    s.wpt = wt;
+    s.groups = n_groups < kWalkerWarps ? n_groups : kWalkerWarps;            // walker warps
+    const int math = n_items < kMathWarps ? n_items : kMathWarps;
+    s.threads = 32 * (s.groups + math);
+    s.stage = force_stage >= 1 ? force_stage : 2;
     s.smem_bytes = EnsembleMmaSmem(walkers, n_l, n_tiles).total;
     s.global_state = false;
     s.mma = true;
-    s.fits = s.smem_bytes <= smem_optin && (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8 < (1u << 20);
+    s.fits = s.smem_bytes + kStaticSmem <= smem_optin && (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8 < (1u << 20);
     (void)bins;
     (void)sm_count;
     if (!s.fits) return false;
@@ -483,11 +528,14 @@ bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int 
 
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin) {
     for (int l = kMinMmaL; l <= kMaxRegL; ++l)
-        for (int wt = 1; wt <= 4; wt *= 2) {
-            cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(pick_mma_kernel(l, wt)),
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
-            if (e != cudaSuccess) return e;
-        }
+      for (int wt = 1; wt <= 4; wt *= 2) {
+        const void *k = reinterpret_cast<const void *>(pick_mma_kernel(l, wt));
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, k);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
+        if (e != cudaSuccess) return e;
+    }
     return cudaSuccess;
 }
 
@@ -508,7 +556,9 @@ cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &s
     if (!k || !shape.fits || !shape.mma || !args.consts_mma || grid < 1 || args.chunk_steps < 1 || args.n_chunks < 1 ||
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;
-    k<<<grid, shape.threads, shape.smem_bytes, stream>>>(args);
+    EnsembleArgs a = args;
+    a.groups = shape.groups | (shape.stage << 8);          // walker warps (the rest of the block are math warps), warps per gather stage
+    k<<<grid, shape.threads, shape.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -82,10 +82,11 @@ struct EnsembleArgs {
 
 struct EnsembleShape {
     int threads, wpt, groups;  // blockDim = walker threads x angle groups
+    int stage;                 // DMMA stepper: walker warps that gather partner rows at the same time
     size_t smem_bytes;
     bool fits;                 // the launch is possible (shared memory, numL <= kMaxRegL)
     bool global_state;         // positions / log-probabilities stay in HBM (ensemble too large for shared memory)
-    bool mma;                  // ensemble_mma_kernel (wpt = walker tiles of 8 in flight per warp)
+    bool mma;                  // ensemble_mma_kernel (groups = walker warps, wpt = tiles of 8 walkers per math item)
 };
 
 EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, int sm_count, size_t smem_optin,
@@ -100,7 +101,7 @@ cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape
 // d - sum a_l D_l is a pure multiply-accumulate onto d.  Returns false when the shape cannot run (numL < kMinMmaL,
 // numL > kMaxRegL or the double-buffered ensemble does not fit shared memory).
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
-                               EnsembleShape *out);
+                               int force_stage, EnsembleShape *out);
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin);
 int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count);   // co-resident CTAs on the device
 cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);

@@ -182,8 +182,9 @@ class DeviceEnsemble:
         return {"points": points, "peaks": peaks, "acceptance_fraction": acc}
 
     def profile(self):
-        """Per-bin section cycle counters of the last advance (first call enables them)."""
-        out = np.zeros((self.n_bins, 8), dtype=np.int64)
+        """Per-bin debug counters [bins, 128] of the last advance (first call enables them; see
+        mdaEnsembleProfile in include/mda_chisq.h)."""
+        out = np.zeros((self.n_bins, 128), dtype=np.int64)
         chisq.check(self.lib, self.lib.mdaEnsembleProfile(self.handle, out.ctypes.data), "mdaEnsembleProfile")
         return out
 

@@ -9,6 +9,8 @@ import os
 import sys
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mimic_mda_b200 import chisq, synth  # noqa: E402
@@ -59,10 +61,15 @@ def main():
            "fp64_peak": peak.value, "acceptance": float(acc)}
     if args.profile:
         cyc = ens.profile().astype(float)
-        per_half = cyc.mean(axis=0) / (2 * args.steps)
-        names = (["propose", "chi+barrier", "accept", "chi_loop", "draw", "barrier", "store"] if os.environ.get("MDA_ENS_IMPL") != "dfma" and args.n_l >= 4
-                 else ["propose+bar", "bar_after_A", "accept+bar", "chi_loop", "draw", "-"])
-        out["cycles_per_half_step"] = dict(zip(names, [round(x, 1) for x in per_half[:7]]))
+        if os.environ.get("MDA_ENS_IMPL") == "dfma" or args.n_l < 4:
+            per_half = cyc[:, :8].mean(axis=0) / (2 * args.steps)
+            out["cycles_per_half_step"] = dict(zip(["propose+bar", "bar_after_A", "accept+bar", "chi_loop", "draw"], [round(x, 1) for x in per_half[:5]]))
+        else:                                           # timeline of one half-step: [bin, warp, stamp], relative to the CTA's first stamp
+            tl = cyc.reshape(args.bins, 16, 8)
+            used = tl[:, :, 0] > 0
+            t0 = np.where(used, tl[:, :, 0], np.inf).min(axis=1)[:, None, None]
+            rel = np.where(tl > 0, tl - t0, np.nan)
+            out["timeline_cycles_median_over_bins"] = [[None if np.isnan(v) else round(float(v)) for v in row] for row in np.nanmedian(rel, axis=0)]
     print(json.dumps(out))
 
 

@@ -91,6 +91,29 @@ float time_it(F launch) {
     return best;
 }
 
+// 8 independent DMMAs + NI dependent-free integer multiply-adds per iteration: does a DMMA hold the issue port?
+template <int NI>
+__global__ void __launch_bounds__(256) k_mix_int(double *sink, int outer, const double *in) {
+    double c[8][2], a[8], b;
+    unsigned u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = in[i] + 1e-9 * threadIdx.x; c[i][0] = in[8 + i]; c[i][1] = in[9 + i]; u[i] = threadIdx.x * 7 + i; }
+    b = in[16];
+    for (int o = 0; o < outer; ++o) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a[i], b);
+#pragma unroll
+            for (int i = 0; i < NI; ++i) u[i % 8] = __umulhi(u[i % 8], 0xD2511F53u) ^ u[(i + 3) % 8];
+        }
+    }
+    double acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += c[i][0] + c[i][1] + u[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 template <int V>
 void rate(const char *name, double *sink, const double *in, int sms, double fma_per_warp_iter, double dfma_per_thread_iter = 0) {
     const int threads = 256, blocks = sms * 8, outer = 256;
@@ -201,6 +224,19 @@ int main() {
         printf("dependent m8n8k4 chain: %.2f ns per DMMA (x SM clock = latency in cycles)\n", ms * 1e6 / (4.0 * outer));
     }
 
+    {
+        const int threads = 256, blocks = sms * 8, outer = 256;
+        auto mix = [&](const char *name, float ms, int ni) {
+            const double warps = (double)blocks * threads / 32;
+            printf("%-34s %8.3f ms  mma %7.2f TFLOP/s  imad %6.2f Tinstr/s (thread level)\n", name, ms, 2 * 8 * 256.0 * 4.0 * outer * warps / (ms * 1e-3) / 1e12,
+                   ni * 4.0 * outer * warps * 32 / (ms * 1e-3) / 1e12);
+        };
+        mix("m8n8k4 x8 + 0 IMAD", time_it([&] { k_mix_int<0><<<blocks, threads>>>(sink, outer, in); }), 0);
+        mix("m8n8k4 x8 + 32 IMAD", time_it([&] { k_mix_int<32><<<blocks, threads>>>(sink, outer, in); }), 32);
+        mix("m8n8k4 x8 + 64 IMAD", time_it([&] { k_mix_int<64><<<blocks, threads>>>(sink, outer, in); }), 64);
+        mix("m8n8k4 x8 + 128 IMAD", time_it([&] { k_mix_int<128><<<blocks, threads>>>(sink, outer, in); }), 128);
+        mix("m8n8k4 x8 + 256 IMAD", time_it([&] { k_mix_int<256><<<blocks, threads>>>(sink, outer, in); }), 256);
+    }
     // ---- likelihood
     const int walkers = 148 * 256 * 32;               // 1.2M walkers
     std::vector<double> hp((size_t)walkers * L), hc((size_t)(L + 1) * NPAD, 0.0);
