@@ -238,6 +238,9 @@ MDA_API int   mdaEnsembleSummarize(void *ens, long long firstKept, double confid
 /* Device pointers of the chain / state, for device-side consumers. */
 MDA_API const double *mdaEnsembleDeviceChain(void *ens);
 MDA_API const double *mdaEnsembleDevicePositions(void *ens);
+/* Which stepping kernel an Advance of nSteps would launch and how its work is laid out
+ * (kernel variant, warps, shared memory, grid, chunking), as text.  For logs and benchmarks. */
+MDA_API int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen);
 /* Debug: cycles[bin][128] of the last Advance.  DMMA stepper: clock stamps of one half-step,
  * [warp < 16][8] = {start, proposals staged | proposals seen, draw made | chi^2 loop done,
  * chi^2 seen | chi^2 posted, accepted, -, at the barrier, past the barrier}; DFMA stepper: the

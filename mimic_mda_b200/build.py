@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden",
     "-fmad=true",
     "-shared", "-cudart", "static",
-]
+] + (os.environ.get("MDA_NVCC_EXTRA", "").split())
 
 
 def nvcc_path():

@@ -421,9 +421,37 @@ EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
     EnsembleShape shape{};
     if (!(impl && strcmp(impl, "dfma") == 0) &&
-        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), env_int("MDA_ENS_STAGE", 0), &shape))
+        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), env_int("MDA_ENS_CPS", 0), &shape))
         return shape;
     return choose_ensemble_shape(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
+}
+
+// Schedule of one launch of the DMMA stepper: (chunk of steps, bin) units, chunk-major, unit u on CTA
+// u mod grid.  Every bin has its own CTA when they are all co-resident; otherwise the resident CTAs walk
+// the list, so that each SM carries the same share of the run (MDA_ENS_GRID / MDA_ENS_CHUNK override,
+// for experiments and tests).
+struct SteppingPlan { int grid, chunk_steps, n_chunks; };
+SteppingPlan plan_stepping(const MdaStore *s, const EnsembleShape &shape, int nSteps) {
+    SteppingPlan p{0, nSteps, 1};
+    const int capacity = ensemble_mma_capacity(s->n_l, shape, g_rt.sm_count);
+    if (capacity < 1) return p;
+    int grid = std::min(s->bins, capacity);
+    const int force_grid = env_int("MDA_ENS_GRID", 0);
+    if (force_grid > 0) grid = force_grid;
+    grid = std::max(1, std::min(grid, std::min(capacity, s->bins)));
+    int chunk_steps = nSteps;
+    if (grid < s->bins) {
+        const int rounds_wanted = 16, min_chunk = 8;
+        int n_chunks = (rounds_wanted * grid + s->bins - 1) / s->bins;
+        n_chunks = std::max(1, std::min(n_chunks, nSteps / min_chunk));
+        chunk_steps = (nSteps + n_chunks - 1) / n_chunks;
+    }
+    const int force_chunk = env_int("MDA_ENS_CHUNK", 0);
+    if (force_chunk > 0) chunk_steps = std::min(force_chunk, nSteps);
+    p.grid = grid;
+    p.chunk_steps = std::max(1, chunk_steps);
+    p.n_chunks = (nSteps + p.chunk_steps - 1) / p.chunk_steps;
+    return p;
 }
 
 MdaEnsemble *as_ensemble(void *p, const char *fn) {
@@ -955,29 +983,13 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.n_tiles = s->n_tiles;
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
     if (shape.mma) {
-        // (chunk of steps, bin) units, chunk-major, unit u on CTA u mod grid.  Every bin has its own CTA
-        // when there are no more bins than SMs; otherwise one CTA per SM walks the list, so that each
-        // SM carries the same share of the run (MDA_ENS_GRID / MDA_ENS_CHUNK override, for experiments).
-        const int capacity = ensemble_mma_capacity(s->n_l, shape, g_rt.sm_count);
-        if (capacity < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
-        int grid = s->bins <= g_rt.sm_count ? s->bins : std::min(capacity, g_rt.sm_count);
-        const int force_grid = env_int("MDA_ENS_GRID", 0);
-        if (force_grid > 0) grid = force_grid;
-        grid = std::max(1, std::min(grid, std::min(capacity, s->bins)));
-        int chunk_steps = nSteps;
-        if (grid < s->bins) {
-            const int rounds_wanted = 16, min_chunk = 8;
-            int n_chunks = (rounds_wanted * grid + s->bins - 1) / s->bins;
-            n_chunks = std::max(1, std::min(n_chunks, nSteps / min_chunk));
-            chunk_steps = (nSteps + n_chunks - 1) / n_chunks;
-        }
-        const int force_chunk = env_int("MDA_ENS_CHUNK", 0);
-        if (force_chunk > 0) chunk_steps = std::min(force_chunk, nSteps);
-        args.chunk_steps = chunk_steps;
-        args.n_chunks = (nSteps + chunk_steps - 1) / chunk_steps;
+        const SteppingPlan plan = plan_stepping(s, shape, nSteps);
+        if (plan.grid < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
+        args.chunk_steps = plan.chunk_steps;
+        args.n_chunks = plan.n_chunks;
         args.progress = e->d_progress;
         args.launch_serial = (++e->launches) << 32;
-        MDA_CUDA(launch_ensemble_mma(args, shape, grid, s->stream), "ensemble stepping launch (DMMA)");
+        MDA_CUDA(launch_ensemble_mma(args, shape, plan.grid, s->stream), "ensemble stepping launch (DMMA)");
     } else {
         MDA_CUDA(launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
     }
@@ -985,6 +997,28 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     const long long new_keeps = (e->steps + nSteps) / thin - e->steps / thin;
     e->steps += nSteps;
     if (e->d_chain) e->kept = std::min(e->keep_cap, e->kept + new_keeps);
+    return MDA_OK;
+}
+
+int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleDescribe");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (!text || textLen < 1 || nSteps < 1) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleDescribe: a buffer and nSteps >= 1 required");
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    MdaStore *s = e->store;
+    const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
+    if (shape.mma) {
+        const SteppingPlan plan = plan_stepping(s, shape, nSteps);
+        snprintf(text, (size_t)textLen,
+                 "ensemble_mma_kernel<L=%d,WT=%d,CPS=%d>: fp64 DMMA.8x8x4 chi^2, %d walker + %d math warps per CTA, %zu B shared memory; "
+                 "%d CTAs walk %d bins x %d chunks of %d steps",
+                 s->n_l, shape.wpt, shape.stage, shape.groups, shape.threads / 32 - shape.groups, shape.smem_bytes, plan.grid, s->bins,
+                 plan.n_chunks, plan.chunk_steps);
+    } else {
+        snprintf(text, (size_t)textLen, "ensemble_kernel<L=%d,WPT=%d,%s>: DFMA chi^2, %d threads x %d angle groups per CTA, %zu B shared memory; one CTA per bin (%d)",
+                 s->n_l, shape.wpt, shape.global_state ? "state in HBM" : "state in shared memory", shape.threads, shape.groups, shape.smem_bytes, s->bins);
+    }
     return MDA_OK;
 }
 

@@ -74,20 +74,16 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Wait on an mbarrier phase that is expected to take hundreds of cycles: the warp sleeps between
-// tests, so that waiting warps do not fill the shared-memory pipeline with barrier probes.
-#ifndef MDA_WAIT_SLEEP_NS
-#define MDA_WAIT_SLEEP_NS 32
-#endif
+// Wait on an mbarrier phase that is expected to take hundreds of cycles.  A DMMA holds the issue port of
+// its scheduler for its whole duration (tools/ubench/dmma_ubench.cu), so every probe of a waiting warp is
+// taken from the math warps: try_wait with a long suspend hint parks the warp in hardware.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
-    for (;;) {
-        uint32_t ok;
-        asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) break;
-        __nanosleep(MDA_WAIT_SLEEP_NS);
-    }
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(100000u) : "memory");
+    } while (!ok);
 }
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -102,12 +98,69 @@ __host__ __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uin
     return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
 }
 
+// chi^2 of WT tiles of 8 walkers (A fragments a[][], leading elements lead[][]) against NTC angle tiles
+// (NTC = 0: nt of them, a run-time count).  Constants are fetched one tile ahead of their use.
+template <int L, int WT, int NTC>
+__device__ __forceinline__ void chi_tiles(const double *sC, int nt, int lane, const double (&a)[WT][L / 4],
+                                          const double (&lead)[WT][(L % 4) > 0 ? (L % 4) : 1], double (&chi0)[WT], double (&chi1)[WT]) {
+    constexpr int Q = L / 4, R = L % 4, RR = R > 0 ? R : 1, TS = 8 * (L + 1);
+    const int tig = lane & 3;
+    const int n = NTC > 0 ? NTC : nt;
+    const double *tp = sC;
+    double2 dv = *reinterpret_cast<const double2 *>(tp + 2 * tig);
+    double2 Di[RR];
+#pragma unroll
+    for (int l = 0; l < R; ++l) Di[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
+    double Bf[Q];
+#pragma unroll
+    for (int ks = 0; ks < Q; ++ks) Bf[ks] = tp[8 * (1 + R) + 32 * ks + lane];
+#pragma unroll(NTC > 0 ? NTC : 2)
+    for (int at = 0; at < n; ++at) {
+        tp = sC + min(at + 1, n - 1) * TS;
+        const double2 dv_n = *reinterpret_cast<const double2 *>(tp + 2 * tig);
+        double2 Di_n[RR];
+#pragma unroll
+        for (int l = 0; l < R; ++l) Di_n[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
+        double Bf_n[Q];
+#pragma unroll
+        for (int ks = 0; ks < Q; ++ks) Bf_n[ks] = tp[8 * (1 + R) + 32 * ks + lane];
+        double c0[WT], c1[WT];
+#pragma unroll
+        for (int k = 0; k < WT; ++k) {
+            c0[k] = dv.x;
+            c1[k] = dv.y;
+#pragma unroll
+            for (int l = 0; l < R; ++l) {
+                c0[k] = fma(lead[k][l], Di[l].x, c0[k]);
+                c1[k] = fma(lead[k][l], Di[l].y, c1[k]);
+            }
+        }
+#pragma unroll
+        for (int ks = 0; ks < Q; ++ks)
+#pragma unroll
+            for (int k = 0; k < WT; ++k) dmma884(c0[k], c1[k], a[k][ks], Bf[ks]);
+#pragma unroll
+        for (int k = 0; k < WT; ++k) {
+            chi0[k] = fma(c0[k], c0[k], chi0[k]);
+            chi1[k] = fma(c1[k], c1[k], chi1[k]);
+        }
+        dv = dv_n;
+#pragma unroll
+        for (int l = 0; l < R; ++l) Di[l] = Di_n[l];
+#pragma unroll
+        for (int ks = 0; ks < Q; ++ks) Bf[ks] = Bf_n[ks];
+    }
+}
+
 // blockDim = 32 (n_walker_warps + n_math_warps); warps [0, n_walker_warps) are walker warps.
 // A walker warp owns groups grp = warp, warp + n_walker_warps, ... of BOTH halves for a whole chunk of
 // steps: only it writes the rows of these walkers (in place, on acceptance); every other warp reads
 // them as partners, and only in the half-step in which they are not being updated.
-template <int L, int WT>                        // WT: tiles of 8 walkers per math item (4: a whole group)
-__global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_mma_kernel(const EnsembleArgs args) {
+// CPS = 1: up to 8 walker + 8 math warps, one CTA per SM.  CPS = 2: up to 8 + 4 warps and at most 80
+// registers, so that two CTAs (two bins) share an SM and the serial head and tail of one bin's
+// half-step (proposals; accept tests) run under the chi^2 loop of the other.
+template <int L, int WT, int CPS>               // WT: tiles of 8 walkers per math item (4: a whole group)
+__global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps / CPS), CPS) ensemble_mma_kernel(const EnsembleArgs args) {
     constexpr int Q = L / 4, R = L % 4, RR = R > 0 ? R : 1;
     constexpr int IW = 8 * WT;                    // walkers of a math item
     constexpr int TS = 8 * (L + 1);               // doubles per angle tile of the constants
@@ -355,52 +408,8 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                     double chi0[WT], chi1[WT];
 #pragma unroll
                     for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
-                    // constants of an angle tile are fetched one tile ahead of their use
-                    const double *tp = sC;
-                    double2 dv = *reinterpret_cast<const double2 *>(tp + 2 * tig);
-                    double2 Di[RR];
-#pragma unroll
-                    for (int l = 0; l < R; ++l) Di[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
-                    double Bf[Q];
-#pragma unroll
-                    for (int ks = 0; ks < Q; ++ks) Bf[ks] = tp[8 * (1 + R) + 32 * ks + lane];
-#pragma unroll 2
-                    for (int at = 0; at < NT; ++at) {
-                        tp = sC + min(at + 1, NT - 1) * TS;
-                        const double2 dv_n = *reinterpret_cast<const double2 *>(tp + 2 * tig);
-                        double2 Di_n[RR];
-#pragma unroll
-                        for (int l = 0; l < R; ++l) Di_n[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
-                        double Bf_n[Q];
-#pragma unroll
-                        for (int ks = 0; ks < Q; ++ks) Bf_n[ks] = tp[8 * (1 + R) + 32 * ks + lane];
-                        double c0[WT], c1[WT];
-#pragma unroll
-                        for (int k = 0; k < WT; ++k) {
-                            c0[k] = dv.x;
-                            c1[k] = dv.y;
-#pragma unroll
-                            for (int l = 0; l < R; ++l) {
-                                c0[k] = fma(lead[k][l], Di[l].x, c0[k]);
-                                c1[k] = fma(lead[k][l], Di[l].y, c1[k]);
-                            }
-                        }
-#pragma unroll
-                        for (int ks = 0; ks < Q; ++ks)
-#pragma unroll
-                            for (int k = 0; k < WT; ++k) dmma884(c0[k], c1[k], A[k][ks], Bf[ks]);
-#pragma unroll
-                        for (int k = 0; k < WT; ++k) {
-                            chi0[k] = fma(c0[k], c0[k], chi0[k]);
-                            chi1[k] = fma(c1[k], c1[k], chi1[k]);
-                        }
-                        dv = dv_n;
-#pragma unroll
-                        for (int l = 0; l < R; ++l) Di[l] = Di_n[l];
-#pragma unroll
-                        for (int ks = 0; ks < Q; ++ks) Bf[ks] = Bf_n[ks];
-                    }
-                    MDA_STAMP(2)
+                    if (NT == 8) chi_tiles<L, WT, 8>(sC, 8, lane, A, lead, chi0, chi1);
+                    else chi_tiles<L, WT, 0>(sC, NT, lane, A, lead, chi0, chi1);
                     // quad sums by a transposing butterfly: lane tig ends up with the sum of tile tig % WT
                     double sum;
                     if (WT == 4) {
@@ -468,30 +477,31 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
 using EnsKernel = void (*)(const EnsembleArgs);
 
 template <int L>
-EnsKernel pick_mma_wt(int wt) {
+EnsKernel pick_mma_wt(int wt, int cps) {
+    if (cps == 2) return wt == 2 ? ensemble_mma_kernel<L, 2, 2> : nullptr;
     switch (wt) {
-        case 1: return ensemble_mma_kernel<L, 1>;
-        case 2: return ensemble_mma_kernel<L, 2>;
-        case 4: return ensemble_mma_kernel<L, 4>;
+        case 1: return ensemble_mma_kernel<L, 1, 1>;
+        case 2: return ensemble_mma_kernel<L, 2, 1>;
+        case 4: return ensemble_mma_kernel<L, 4, 1>;
         default: return nullptr;
     }
 }
 
-EnsKernel pick_mma_kernel(int n_l, int wt) {
+EnsKernel pick_mma_kernel(int n_l, int wt, int cps) {
     switch (n_l) {
-        case 4: return pick_mma_wt<4>(wt);
-        case 5: return pick_mma_wt<5>(wt);
-        case 6: return pick_mma_wt<6>(wt);
-        case 7: return pick_mma_wt<7>(wt);
-        case 8: return pick_mma_wt<8>(wt);
-        case 9: return pick_mma_wt<9>(wt);
-        case 10: return pick_mma_wt<10>(wt);
-        case 11: return pick_mma_wt<11>(wt);
-        case 12: return pick_mma_wt<12>(wt);
-        case 13: return pick_mma_wt<13>(wt);
-        case 14: return pick_mma_wt<14>(wt);
-        case 15: return pick_mma_wt<15>(wt);
-        case 16: return pick_mma_wt<16>(wt);
+        case 4: return pick_mma_wt<4>(wt, cps);
+        case 5: return pick_mma_wt<5>(wt, cps);
+        case 6: return pick_mma_wt<6>(wt, cps);
+        case 7: return pick_mma_wt<7>(wt, cps);
+        case 8: return pick_mma_wt<8>(wt, cps);
+        case 9: return pick_mma_wt<9>(wt, cps);
+        case 10: return pick_mma_wt<10>(wt, cps);
+        case 11: return pick_mma_wt<11>(wt, cps);
+        case 12: return pick_mma_wt<12>(wt, cps);
+        case 13: return pick_mma_wt<13>(wt, cps);
+        case 14: return pick_mma_wt<14>(wt, cps);
+        case 15: return pick_mma_wt<15>(wt, cps);
+        case 16: return pick_mma_wt<16>(wt, cps);
         default: return nullptr;
     }
 }
@@ -499,28 +509,32 @@ EnsKernel pick_mma_kernel(int n_l, int wt) {
 }  // namespace
 
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
-                               int force_stage, EnsembleShape *out) {
+                               int force_cps, EnsembleShape *out) {
     if (n_l < kMinMmaL || n_l > kMaxRegL) return false;
     EnsembleShape s{};
     const int half = walkers / 2;
     const int n_groups = (half + GW - 1) / GW;
     if (n_groups > kMaxGroups) return false;
+    s.smem_bytes = EnsembleMmaSmem(walkers, n_l, n_tiles).total;
+    // two bins per SM when every SM gets two and two ensembles fit its shared memory (measured, C4 shape:
+    // +8 % at 296 bins; with fewer bins the SMs that carry two slower CTAs finish last)
+    int cps = (bins >= 2 * sm_count && 2 * (s.smem_bytes + kStaticSmem + 1024) <= smem_optin + 1024) ? 2 : 1;
+    if (force_cps == 1 || force_cps == 2) cps = force_cps;
     // tiles per math item: a whole group where that still gives every scheduler two math warps
     int wt = n_groups >= kMathWarps ? 4 : (2 * n_groups >= kMathWarps ? 2 : 1);
     if (n_l > 12 && wt == 4) wt = 2;                                         // registers: A fragments of 4 tiles x 4 k-steps
     if (force_wt == 1 || force_wt == 2 || force_wt == 4) wt = force_wt;
+    if (cps == 2) wt = 2;
     const int n_items = (half + 8 * wt - 1) / (8 * wt);
     s.wpt = wt;
+    s.stage = cps;
     s.groups = n_groups < kWalkerWarps ? n_groups : kWalkerWarps;            // walker warps
-    const int math = n_items < kMathWarps ? n_items : kMathWarps;
+    const int max_math = kMathWarps / cps;
+    const int math = n_items < max_math ? n_items : max_math;
     s.threads = 32 * (s.groups + math);
-    s.stage = force_stage >= 1 ? force_stage : 2;
-    s.smem_bytes = EnsembleMmaSmem(walkers, n_l, n_tiles).total;
     s.global_state = false;
     s.mma = true;
     s.fits = s.smem_bytes + kStaticSmem <= smem_optin && (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8 < (1u << 20);
-    (void)bins;
-    (void)sm_count;
     if (!s.fits) return false;
     *out = s;
     return true;
@@ -528,21 +542,24 @@ bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int 
 
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin) {
     for (int l = kMinMmaL; l <= kMaxRegL; ++l)
-      for (int wt = 1; wt <= 4; wt *= 2) {
-        const void *k = reinterpret_cast<const void *>(pick_mma_kernel(l, wt));
-        cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, k);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
-        if (e != cudaSuccess) return e;
-    }
+        for (int cps = 1; cps <= 2; ++cps)
+            for (int wt = 1; wt <= 4; wt *= 2) {
+                EnsKernel fn = pick_mma_kernel(l, wt, cps);
+                if (!fn) continue;
+                const void *k = reinterpret_cast<const void *>(fn);
+                cudaFuncAttributes fa;
+                cudaError_t e = cudaFuncGetAttributes(&fa, k);
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
+                if (e != cudaSuccess) return e;
+            }
     return cudaSuccess;
 }
 
 // Co-resident CTAs of this kernel on the whole device (the unit list needs every CTA of the grid
 // resident: a unit may wait for one that runs on another CTA).
 int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count) {
-    EnsKernel k = pick_mma_kernel(n_l, shape.wpt);
+    EnsKernel k = pick_mma_kernel(n_l, shape.wpt, shape.stage);
     int per_sm = 0;
     if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(k), shape.threads,
                                                             shape.smem_bytes) != cudaSuccess)
@@ -552,12 +569,12 @@ int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count) {
 
 cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream) {
     if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
-    EnsKernel k = pick_mma_kernel(args.n_l, shape.wpt);
+    EnsKernel k = pick_mma_kernel(args.n_l, shape.wpt, shape.stage);
     if (!k || !shape.fits || !shape.mma || !args.consts_mma || grid < 1 || args.chunk_steps < 1 || args.n_chunks < 1 ||
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;
     EnsembleArgs a = args;
-    a.groups = shape.groups | (shape.stage << 8);          // walker warps (the rest of the block are math warps), warps per gather stage
+    a.groups = shape.groups | (2 << 8);                    // walker warps (the rest of the block are math warps); two gather at a time
     k<<<grid, shape.threads, shape.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }

@@ -39,6 +39,7 @@ def _declare(lib):
         "mdaEnsembleGetState": (ct.c_int, [vp, vp, vp, vp]),
         "mdaEnsembleGetChain": (ct.c_int, [vp, ll, ll, vp, vp]),
         "mdaEnsembleProfile": (ct.c_int, [vp, vp]),
+        "mdaEnsembleDescribe": (ct.c_int, [vp, ct.c_int, ct.c_char_p, ct.c_int]),
         "mdaEnsembleSummarize": (ct.c_int, [vp, ll, ct.c_double, ct.c_int, vp, vp, vp]),
         "mdaEnsembleRunToHost": (ct.c_int, [vp, ct.c_int, ct.c_int, ct.c_int, vp, vp]),
         "mdaEnsembleDeviceChain": (vp, [vp]),
@@ -187,6 +188,12 @@ class DeviceEnsemble:
         out = np.zeros((self.n_bins, 128), dtype=np.int64)
         chisq.check(self.lib, self.lib.mdaEnsembleProfile(self.handle, out.ctypes.data), "mdaEnsembleProfile")
         return out
+
+    def describe(self, n_steps=1):
+        """The stepping kernel and schedule an advance of ``n_steps`` would use (text)."""
+        buf = ct.create_string_buffer(512)
+        chisq.check(self.lib, self.lib.mdaEnsembleDescribe(self.handle, int(n_steps), buf, len(buf)), "mdaEnsembleDescribe")
+        return buf.value.decode()
 
     def close(self):
         if getattr(self, "handle", None):

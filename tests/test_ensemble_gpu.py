@@ -81,6 +81,41 @@ def test_split_runs_thinning_and_partition_invariance(cs_lib):
     store.close()
 
 
+@pytest.mark.parametrize("env", [{"MDA_ENS_GRID": "2", "MDA_ENS_CHUNK": "7"},        # 5 bins on 2 CTAs, 9 chunks: hand-over through HBM
+                                 {"MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "1"},
+                                 {"MDA_ENS_CPS": "2"},                               # the two-CTAs-per-SM build of the kernel
+                                 {"MDA_ENS_CPS": "2", "MDA_ENS_GRID": "4", "MDA_ENS_CHUNK": "16"},
+                                 {"MDA_ENS_WT": "2"}, {"MDA_ENS_WT": "1"},
+                                 {"MDA_ENS_IMPL": "dfma"}])
+def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
+    """Units of (chunk of steps, bin) walked by fewer CTAs than bins, other tilings of the chi^2 work and the
+    DFMA stepper: the chains are the same (identical for every schedule of the same kernel; the DFMA
+    stepper sums chi^2 in another order, so it may differ in a measure-zero set of near-tie decisions)."""
+    consts, counts, lo, hi, p0, _ = _problem(5, 9, 60, 128)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    ref = DeviceEnsemble(store, 128, seed=11)
+    ref.run_mcmc(p0, 60, thin=2)
+    want, want_state = ref.chain.copy(), ref.state()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ens = DeviceEnsemble(store, 128, seed=11)
+    ens.set_state(p0)
+    ens.reserve_chain(30)
+    ens.advance(25, thin=2)
+    ens.advance(35, thin=2)
+    if env.get("MDA_ENS_IMPL") == "dfma":
+        same = np.all(ens.chain == want, axis=(1, 3))
+        assert same.mean() > 0.999
+        np.testing.assert_allclose(ens.chain[:, :, :3], want[:, :, :3], rtol=1e-13)
+    else:
+        np.testing.assert_array_equal(ens.chain, want)
+        for a, b in zip(ens.state(), want_state):
+            np.testing.assert_array_equal(a, b)
+    ens.close()
+    ref.close()
+    store.close()
+
+
 def test_posterior_agrees_with_host_driven_emcee_style_sampler(cs_lib, oracle_lib):
     """Different generators (Philox vs Mersenne Twister) => statistical parity:
     posterior means and quantiles within MCMC noise (mda.py:1429-1431)."""
