@@ -582,6 +582,11 @@ def main():
         except Exception:
             traffic = {}
 
+    def traffic_of(key):                     # DRAM bytes per launch from the ncu capture (per step x steps for the sampler)
+        if key + "_per_step" in traffic:
+            return traffic[key + "_per_step"] * args.steps
+        return traffic.get(key)
+
     def roofline_of(kernel, seconds_per_launch, flops_launch, bytes_launch, traffic_key, tensor_note):
         tf = flops_launch / seconds_per_launch / 1e12
         gbs = bytes_launch / seconds_per_launch / 1e9
@@ -591,7 +596,7 @@ def main():
             "achieved": tf if f64 >= fhbm else gbs,
             "peak": peak_tf.value if f64 >= fhbm else hbm_peak,
             "unit": "TFLOP/s" if f64 >= fhbm else "GB/s",
-            "frac": max(f64, fhbm), "traffic": traffic.get(traffic_key),
+            "frac": max(f64, fhbm), "traffic": traffic_of(traffic_key),
             "kernel": kernel, "launch_us": seconds_per_launch * 1e6,
             "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
             "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf.value, "frac": f64,
