@@ -421,7 +421,7 @@ EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
     EnsembleShape shape{};
     if (!(impl && strcmp(impl, "dfma") == 0) &&
-        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), env_int("MDA_ENS_CPS", 0), &shape))
+        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), &shape))
         return shape;
     return choose_ensemble_shape(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
 }
@@ -1011,9 +1011,9 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
     if (shape.mma) {
         const SteppingPlan plan = plan_stepping(s, shape, nSteps);
         snprintf(text, (size_t)textLen,
-                 "ensemble_mma_kernel<L=%d,WT=%d,CPS=%d>: fp64 DMMA.8x8x4 chi^2, %d walker + %d math warps per CTA, %zu B shared memory; "
+                 "ensemble_mma_kernel<L=%d,WT=%d>: fp64 DMMA.8x8x4 chi^2, %d walker + %d math warps per CTA meeting at named barriers, %zu B shared memory; "
                  "%d CTAs walk %d bins x %d chunks of %d steps",
-                 s->n_l, shape.wpt, shape.stage, shape.groups, shape.threads / 32 - shape.groups, shape.smem_bytes, plan.grid, s->bins,
+                 s->n_l, shape.wpt, shape.groups, shape.threads / 32 - shape.groups, shape.smem_bytes, plan.grid, s->bins,
                  plan.n_chunks, plan.chunk_steps);
     } else {
         snprintf(text, (size_t)textLen, "ensemble_kernel<L=%d,WPT=%d,%s>: DFMA chi^2, %d threads x %d angle groups per CTA, %zu B shared memory; one CTA per bin (%d)",

@@ -3,29 +3,43 @@
 //
 // Same job and same random streams as ensemble_kernel.cu (the reference's host loop
 // emcee.EnsembleSampler.run_mcmc -> ln_post_prob per walker, mda.py:1128-1131, 1540-1578, as ONE
-// persistent launch).  A CTA has two kinds of warps:
+// persistent launch).  A CTA owns an Ex bin (for a chunk of steps) and has two kinds of warps:
 //
-//   * walker warps (lane = walker of a group of 32): Philox draw, proposal q = c - z (c - x), box
-//     prior, accept / reject, in-place update and the bulk store of kept steps to the HBM chain.
-//     Everything a walker needs between its proposal and its accept test stays in its lane.
-//   * math warps: chi^2 of items of 16 walkers.  Lane (g, tig) = (lane / 4, lane % 4) loads, for
-//     walker g of a tile of 8, the proposal elements l = R + 4 ks + tig (ks < Q = L / 4) -- the A
-//     fragment of mma.m8n8k4 -- and the R = L % 4 leading ones; residuals of an 8-walker x 8-angle
+//   * math warps: chi^2 of one item of 8 WT walkers per half-step.  Lane (g, tig) = (lane / 4, lane % 4)
+//     loads, for walker g of a tile of 8, the proposal elements l = R + 4 ks + tig (ks < Q = L / 4) -- the
+//     A fragment of mma.m8n8k4 -- and the R = L % 4 leading ones; residuals of an 8-walker x 8-angle
 //     tile are c = d + sum_{l<R} q_l (-D_l) by DFMA, then Q DMMAs against B fragments of the NEGATED
 //     distributions staged fragment-major in shared memory; chi^2 is accumulated from the C fragment
 //     and reduced over the quad.  Every term of the reference's sum (C/ChiSquare.c:188-210) is
 //     evaluated exactly once, only the order of the fp64 additions differs (|error| ~ 1e-16
-//     relative, tested against the oracle).  Why DMMA: a DFMA with three distinct register operands
-//     is register-bandwidth bound at ~72 % of the fp64 pipe on sm_100a; DMMA.8x8x4 runs on the same
-//     pipe at its full rate with 1/8 of the issue slots (tools/ubench/dmma_ubench.cu).
-//   * the two kinds meet through shared memory and one mbarrier pair per group of 32 walkers
-//     (proposals ready -> chi^2 ready), so the fp64 pipe works on the first groups while the others
-//     are still being proposed, and the draw of the next half-step is made while the pipe is busy.
-//     ONE CTA-wide barrier per half-step (the stretch move needs the other half complete).
+//     relative, tested against the oracle).  The box prior (mda.py:1574-1576) is tested on the same
+//     registers: a walker outside gets chi^2 = +inf, i.e. log-posterior -inf.  Why DMMA: a DFMA with
+//     three distinct register operands is register-bandwidth bound at ~72 % of the fp64 pipe on
+//     sm_100a; DMMA.8x8x4 runs on the same pipe at its full rate with 1/8 of the issue slots
+//     (tools/ubench/dmma_ubench.cu).
+//   * walker warps.  Proposals q = c - z (c - x) are staged by ALL walker warps together over the
+//     flattened elements of the half, e = pass * (walker threads) + thread: own rows and proposals are
+//     contiguous runs, only the partner rows c are gathered.  Everything of a proposal that does not
+//     depend on the half being updated right now (its own row x, its stretch factor z, the address of
+//     its partner row) is fetched during the previous half-step, while the fp64 pipe is busy, so that
+//     the stretch between "the other half is complete" and "the math warps run" is one gather, 3 L
+//     fp64 operations and one store per thread.  Decisions stay with lane = walker of warp = group:
+//     Philox draw, accept / reject, in-place update, acceptance counters.
+//   * hand-offs are NAMED BARRIERS (bar.sync / bar.arrive), never polled: barrier 1 completes when the
+//     proposals are staged (walker warps arrive, math warps wait), barrier 2 + g when the chi^2 of group
+//     g is there (its math warps arrive, walker warp g waits), barrier 10 joins the walker warps at the
+//     end of a half-step (the stretch move needs the other half complete).  A bar.arrive costs ~150
+//     cycles (it waits for the thread's shared-memory stores), so there is one per warp and half-step.
+//     An mbarrier wait compiles to a try_wait / NANOSLEEP.SYNCS loop that wakes up every ~100 cycles:
+//     in the mbarrier version of this kernel 25 % of all executed instructions were such probes
+//     (profiles/r01_ncu_full_c4_ensemble_mma.csv), taken from the issue slots of the math warps.
 //   * CTAs walk a list of (step chunk, bin) units in chunk-major order, unit u on CTA u mod grid; a
 //     unit waits for the previous chunk of its bin through a release/acquire word per bin and hands
 //     the ensemble state over through HBM/L2.  With more bins than SMs (C4: 200 on 148) every SM
 //     carries the same share of the work instead of 52 SMs carrying two bins for the whole run.
+//
+// Shapes: every walker warp owns one group of 32 walkers of a half and every math warp one item, so
+// ensembles of up to 512 walkers (all BASELINE.json shapes); larger ones run on ensemble_kernel.cu.
 #include "likelihood.cuh"
 #include "philox.cuh"
 
@@ -34,14 +48,16 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
-constexpr int kWalkerWarps = 8;        // at most: one group of 32 walkers each at C4
+constexpr int kWalkerWarps = 8;        // at most: one group of 32 walkers each
 constexpr int kMathWarps = 8;          // at most: two per scheduler keep the fp64 pipe fed
-constexpr int kMaxGroups = 64;         // groups of 32 walkers per half (mbarrier pairs)
 constexpr int GW = 32;                 // walkers of a group (a walker warp's lanes)
-constexpr size_t kStaticSmem = 8 * (2 + 2 * kMaxGroups + kWalkerWarps) + 16;   // the mbarriers (static __shared__)
+constexpr int kStagedBarrier = 1;      // named barrier: the proposals of the half-step are staged (walker warps arrive, math warps wait)
+constexpr int kDoneBarrier = 2;        // named barriers 2 .. 9: chi^2 of a group is there (its math warps arrive, its walker warp waits)
+constexpr int kJoinBarrier = 10;       // named barrier of the walker warps
+constexpr size_t kStaticSmem = 64;     // the mbarrier of the constants (static __shared__), rounded up
 
 struct EnsembleMmaSmem {
-    size_t consts, pos, q, lnp, chi, z, fast, partner, acc, total;
+    size_t consts, pos, q, lnp, chi, z, bounds, fast, partner, acc, total;
     __host__ __device__ EnsembleMmaSmem(int walkers, int n_l, int n_tiles) {
         const size_t h = (size_t)walkers / 2;
         size_t off = 0;
@@ -49,8 +65,9 @@ struct EnsembleMmaSmem {
         pos = off;     off += (size_t)walkers * (size_t)n_l * 8;               // [W][L] dense, updated in place; bulk-stored as is
         lnp = off;     off += (size_t)walkers * 8;                             // [W] (16-byte aligned: W is even)
         q = off;       off += h * (size_t)n_l * 8;                             // [H][L] proposals of the half-step
-        chi = off;     off += h * 8;                                           // [H] chi^2 of the proposals
+        chi = off;     off += h * 8;                                           // [H] chi^2 of the proposals (+inf: outside the box)
         z = off;       off += h * 8;                                           // [H] stretch factor of the next proposal
+        bounds = off;  off += 2 * (size_t)n_l * 8;                             // [2][L] box prior: lo, hi
         fast = off;    off += 2 * h * 4;                                       // [2][H] float (L-1) ln z - ln u'
         partner = off; off += h * 4;                                           // [H]
         acc = off;     off += (size_t)walkers * 4;                             // [W] accepted proposals
@@ -71,20 +88,6 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Wait on an mbarrier phase that is expected to take hundreds of cycles.  A DMMA holds the issue port of
-// its scheduler for its whole duration (tools/ubench/dmma_ubench.cu), so every probe of a waiting warp is
-// taken from the math warps: try_wait with a long suspend hint parks the warp in hardware.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(a), "r"(parity), "r"(100000u) : "memory");
-    } while (!ok);
-}
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -152,25 +155,21 @@ __device__ __forceinline__ void chi_tiles(const double *sC, int nt, int lane, co
     }
 }
 
-// blockDim = 32 (n_walker_warps + n_math_warps); warps [0, n_walker_warps) are walker warps.
-// A walker warp owns groups grp = warp, warp + n_walker_warps, ... of BOTH halves for a whole chunk of
-// steps: only it writes the rows of these walkers (in place, on acceptance); every other warp reads
-// them as partners, and only in the half-step in which they are not being updated.
-// CPS = 1: up to 8 walker + 8 math warps, one CTA per SM.  CPS = 2: up to 8 + 4 warps and at most 80
-// registers, so that two CTAs (two bins) share an SM and the serial head and tail of one bin's
-// half-step (proposals; accept tests) run under the chi^2 loop of the other.
-template <int L, int WT, int CPS>               // WT: tiles of 8 walkers per math item (4: a whole group)
-__global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps / CPS), CPS) ensemble_mma_kernel(const EnsembleArgs args) {
+// Named barriers: a waiting warp is parked by the hardware and issues nothing.
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// blockDim = 32 (n_walker_warps + n_math_warps); warps [0, n_walker_warps) are walker warps, one per
+// group of 32 walkers of a half; math warp m computes item m (8 WT walkers) of every half-step.
+template <int L, int WT, bool PROF>               // WT: tiles of 8 walkers per math item (4: a whole group)
+__global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_mma_kernel(const EnsembleArgs args) {
     constexpr int Q = L / 4, R = L % 4, RR = R > 0 ? R : 1;
     constexpr int IW = 8 * WT;                    // walkers of a math item
+    constexpr int IPG = GW / IW;                  // math items per group
     constexpr int TS = 8 * (L + 1);               // doubles per angle tile of the constants
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;                 // constants of a unit have landed
-    __shared__ __align__(8) uint64_t full_bar[kMaxGroups]; // proposals of a group are staged
-    __shared__ __align__(8) uint64_t done_bar[kMaxGroups]; // chi^2 of a group is there
-    __shared__ __align__(8) uint64_t store_bar;            // the bulk store of a kept step has read the state
-    __shared__ __align__(8) uint64_t turn_bar[kWalkerWarps]; // walker warp w may queue its gathers
 
     const int tid = threadIdx.x;
     const int T = blockDim.x;
@@ -178,12 +177,12 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps / CPS), CPS) e
     const int W = args.walkers;
     const int H = W >> 1;
     const int NT = args.n_tiles;
-    const int n_groups = (H + GW - 1) / GW;
     const int n_items = (H + IW - 1) / IW;
-    const int n_ww = args.groups & 0xff;          // walker warps (the launch sets it)
-    const int stage_w = max(1, args.groups >> 8); // walker warps that gather at the same time
-    const int n_mw = (T >> 5) - n_ww;
+    const int n_ww = args.groups;                 // walker warps = groups of a half (the launch sets it)
+    const int NWT = 32 * n_ww;                    // walker threads
+    const int E = H * L;                          // elements of a half
     const bool walker_warp = warp < n_ww;
+    const bool full_half = E == NWT * L;          // every group has 32 walkers: no element of a pass is beyond the half
 
     const EnsembleMmaSmem lay(W, L, NT);
     const double *sC = reinterpret_cast<const double *>(smem_raw + lay.consts);
@@ -192,20 +191,17 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps / CPS), CPS) e
     double *sLnp = reinterpret_cast<double *>(smem_raw + lay.lnp);
     double *sChi = reinterpret_cast<double *>(smem_raw + lay.chi);
     double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
+    double *sLo = reinterpret_cast<double *>(smem_raw + lay.bounds);
+    double *sHi = sLo + L;
     float *sFast = reinterpret_cast<float *>(smem_raw + lay.fast);
     int *sPartner = reinterpret_cast<int *>(smem_raw + lay.partner);
     unsigned int *sAcc = reinterpret_cast<unsigned int *>(smem_raw + lay.acc);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
-        mbar_init(&store_bar, 1);
-        for (int w = 0; w < kWalkerWarps; ++w) mbar_init(&turn_bar[w], 1);
-        for (int grp = 0; grp < n_groups; ++grp) {
-            mbar_init(&full_bar[grp], 1);
-            mbar_init(&done_bar[grp], (uint32_t)min(GW / IW, n_items - grp * (GW / IW)));   // math items of the group
-        }
         fence_mbar_init();
     }
+    if (tid < L) { sLo[tid] = args.lo[tid]; sHi[tid] = args.hi[tid]; }
     __syncthreads();
 
     const uint32_t seed0 = args.seed_lo, seed1 = args.seed_hi;
@@ -213,10 +209,24 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps / CPS), CPS) e
     const double dim_m1 = (double)(L - 1);
     const float dim_m1f = (float)(L - 1);
 
+    // threads of both barriers of group g: proposals staged (all walker warps + its math warps), chi^2 there
+    auto items_of = [&](int g) { return min(IPG, n_items - g * IPG); };
+    const int n_staged = T;                       // every warp of the CTA takes part in the staged barrier
+
+    // ---- walker warps: flattened element e = p NWT + tid of pass p is component el_l of walker el_i of the half
+    int el_i[L], el_l[L];
+    if (walker_warp) {
+#pragma unroll
+        for (int p = 0; p < L; ++p) {
+            const int e = min(p * NWT + tid, E - 1);
+            el_i[p] = e / L;
+            el_l[p] = e - el_i[p] * L;
+        }
+    }
+
     bool saw_nan = false;
     uint32_t unit_phase = 0;                               // parity of mbar
-    uint32_t hs_phase = 0;                                 // parity of full_bar / done_bar: one phase per half-step
-    uint32_t stores_issued = 0, stores_seen = 0;           // bulk stores of kept steps (store_bar: one phase each)
+    bool store_pending = false;                            // a bulk store of a kept step may still be reading the state
     const bool keeping = args.chain != nullptr;
 
     const long long n_units = (long long)args.n_chunks * args.bins;
@@ -253,209 +263,215 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps / CPS), CPS) e
         const uint32_t t_begin = 2u * (uint32_t)step_first;
         const uint32_t t_end = t_begin + 2u * (uint32_t)steps_here;
 
-        // The Philox draw of walker i of the half updated in half-step t (counter based: it does not
-        // depend on positions), in two parts so that half of the walker warps can put the integer
-        // part before their proposals and the other half after (see below).
-        auto draw_bits = [&](uint32_t t, int i) {
-            const int s_base = (t & 1u) ? H : 0;
-            return philox4x32_10(Philox4{(uint32_t)(s_base + i), bin_id, t, 0u}, seed0, seed1);
-        };
-        // emcee draws per half: u -> z, the partner index, then u'
-        auto draw_finish = [&](const Philox4 &r, uint32_t t, int i) {
-            const int c_base = (t & 1u) ? 0 : H;
-            const double u = uniform53(r.x, r.y);
-            // numpy arithmetic is one rounding per operation: no FMA contraction here
-            const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);
-            const double z2 = __dmul_rn(zr, zr);
-            const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;              // ((a-1) u + 1)^2 / a
-            const double ua = uniform43(r.w, r.x, r.y);
-            sZ[i] = z;
-            // single-precision estimate of (L-1) ln z - ln u'; decides all but near-ties
-            sFast[(t & 1u) * H + i] = dim_m1f * __logf((float)z) - __logf((float)ua);
-            sPartner[i] = c_base + (int)__umulhi(r.z, (uint32_t)H);
-        };
-
         mbar_wait(&mbar, unit_phase);
         unit_phase ^= 1u;
         __syncthreads();
-        if (walker_warp)
-            for (int grp = warp; grp < n_groups; grp += n_ww) {
-                const int i = min(grp * GW + lane, H - 1);
-                draw_finish(draw_bits(t_begin, i), t_begin, i);
-            }
 
         // debug timeline (mdaEnsembleProfile): clock stamps of one half-step, per warp
-        const uint32_t t_prof = (args.prof != nullptr && chunk == 0) ? t_begin + min(81u, 2u * (uint32_t)steps_here - 1u) : 0xffffffffu;
-        for (uint32_t t = t_begin; t < t_end; ++t, hs_phase ^= 1u) {
-            const uint32_t half = t & 1u;
-            long long *stamp = (t == t_prof && lane == 0 && warp < 16) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
-#define MDA_STAMP(k) if (stamp) stamp[k] = clock64();
-            MDA_STAMP(0)
-            const int s_base = half ? H : 0;          // the half being updated; partners come from the other one
+        const uint32_t t_prof = (PROF && args.prof != nullptr && chunk == 0) ? t_begin + min(81u, 2u * (uint32_t)steps_here - 1u) : 0xffffffffu;
+#define MDA_STAMP(k) if (PROF && stamp) stamp[k] = clock64();
+#define MDA_STAMP_AFTER(k, value) if (PROF && stamp && (value) != 123.456) stamp[k] = clock64();   // once `value` has arrived
 
-            if (walker_warp) {
-                const bool draw_next = t + 1 < t_end;
-                // ---- proposals of my groups: q = c - z (c - x); box prior
-                unsigned long long out_bits = 0ull;        // bit k: my walker of my k-th group is outside the box
-                int k = 0;
-                for (int grp = warp; grp < n_groups; grp += n_ww, ++k) {
-                    const int i = min(grp * GW + lane, H - 1);
-                    const double z = sZ[i];
-                    const double *xs = sPos + (s_base + i) * L;
-                    const double *xc = sPos + sPartner[i] * L;
-                    double *q = sQ + i * L;
-                    // The gathers of the partner rows are shared-memory-bandwidth bound (random rows: ~3.5-way
-                    // bank conflicts).  The groups take turns at it, in order, so that the first group is staged
-                    // after one group's worth of traffic and the math warps start while the others still load.
-                    if (stamp && z != 123.456) stamp[7] = clock64();                    // debug: my draw has been read
-                    if (k == 0 && warp >= stage_w) mbar_wait_relaxed(&turn_bar[warp], hs_phase);
-                    double c[L], v[L];
+        if (walker_warp) {
+            // The Philox draw of walker i of the half updated in half-step t (counter based: it does not
+            // depend on positions).  emcee draws per half: u -> z, the partner index, then u'.
+            auto draw = [&](uint32_t t, int i) {
+                const int s_base = (t & 1u) ? H : 0, c_base = (t & 1u) ? 0 : H;
+                const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + i), bin_id, t, 0u}, seed0, seed1);
+                const double u = uniform53(r.x, r.y);
+                // numpy arithmetic is one rounding per operation: no FMA contraction here
+                const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);
+                const double z2 = __dmul_rn(zr, zr);
+                const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;              // ((a-1) u + 1)^2 / a
+                const double ua = uniform43(r.w, r.x, r.y);
+                sZ[i] = z;
+                // single-precision estimate of (L-1) ln z - ln u'; decides all but near-ties
+                sFast[(t & 1u) * H + i] = dim_m1f * __logf((float)z) - __logf((float)ua);
+                sPartner[i] = c_base + (int)__umulhi(r.z, (uint32_t)H);
+            };
+            // What the proposals of half-step t need and the half-step before does not change: stretch
+            // factor, own component, index of the partner's component (of my element of every pass).
+            double pz[L], px[L];
+            int pc[L];
+            auto prefetch = [&](uint32_t t) {
+                const double *xrow = sPos + ((t & 1u) ? H : 0) * L;
 #pragma unroll
-                    for (int l = 0; l < L; ++l) { c[l] = xc[l]; v[l] = xs[l]; }        // all loads before any store
-                    if (k == 0 && warp + stage_w < n_ww) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&turn_bar[warp + stage_w]);          // my loads are queued: next, please
-                    }
-                    // box prior (mda.py:1575): v < lo or v > hi for any element  <=>  the smallest of the margins
-                    // v - lo, hi - v is negative (x - y < 0 <=> x < y exactly; fmin drops NaN margins, and a
-                    // NaN compares false in the reference too).  A min tree instead of 2 L chained compares.
-                    if (stamp && c[L - 1] != 123.456 && v[L - 1] != 123.456) stamp[5] = clock64();   // debug: rows are here
-                    double m[L];
-#pragma unroll
-                    for (int l = 0; l < L; ++l) {
-                        v[l] = __dsub_rn(c[l], __dmul_rn(z, __dsub_rn(c[l], v[l])));
-                        m[l] = fmin(__dsub_rn(v[l], args.lo[l]), __dsub_rn(args.hi[l], v[l]));
-                    }
-#pragma unroll
-                    for (int l = 0; l < L; ++l) q[l] = v[l];
-#pragma unroll
-                    for (int w = 1; w < L; w *= 2)
-#pragma unroll
-                        for (int l = 0; l + w < L; l += 2 * w) m[l] = fmin(m[l], m[l + w]);
-                    const bool out = m[0] < 0.0;
-                    if (stamp && (out || m[0] != 123.456)) stamp[6] = clock64();                    // debug: box prior known
-                    out_bits |= (unsigned long long)out << k;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[grp]);
+                for (int p = 0; p < L; ++p) {
+                    pz[p] = sZ[el_i[p]];
+                    pc[p] = sPartner[el_i[p]] * L + el_l[p];
+                    px[p] = xrow[min(p * NWT + tid, E - 1)];
                 }
+            };
+            const int my_i = min(warp * GW + lane, H - 1);     // my walker of my group (decisions)
+            const int live_w = min(GW, H - warp * GW);
+            draw(t_begin, my_i);
+            named_sync(kJoinBarrier, NWT);
+            prefetch(t_begin);
+
+            for (uint32_t t = t_begin; t < t_end; ++t) {
+                const uint32_t half = t & 1u;
+                const int s_base = half ? H : 0;              // the half being updated; partners come from the other one
+                long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
+                MDA_STAMP(0)
+                // ---- proposals q = c - z (c - x), pass by pass; a group is announced with its last pass
+                double c[L];
+#pragma unroll
+                for (int p = 0; p < L; ++p) c[p] = sPos[pc[p]];
+                MDA_STAMP_AFTER(5, c[L - 1])
+                // all the fp64 work first: once the math warps of the first groups run, the pipe is theirs
+                // (the empty asm pins every result before the first barrier instruction below)
+                double v[L];
+#pragma unroll
+                for (int p = 0; p < L; ++p) v[p] = __dsub_rn(c[p], __dmul_rn(pz[p], __dsub_rn(c[p], px[p])));
+#pragma unroll
+                for (int p = 0; p < L; ++p) asm volatile("" : "+d"(v[p]));
+                MDA_STAMP(6)
+#pragma unroll
+                for (int p = 0; p < L; ++p)
+                    if (full_half || p * NWT + tid < E) sQ[p * NWT + tid] = v[p];
+                named_arrive(kStagedBarrier, n_staged);    // one arrival per half-step: it waits for the stores above (~150 cycles)
                 MDA_STAMP(1)
-                // ---- the draw of the next half-step, while the math warps work
-                if (draw_next)
-                    for (int grp = warp; grp < n_groups; grp += n_ww) {
-                        const int i = min(grp * GW + lane, H - 1);
-                        draw_finish(draw_bits(t + 1, i), t + 1, i);
-                    }
-                MDA_STAMP(2)
-                if (stores_seen != stores_issued) {        // the chain store must have read my rows
-                    mbar_wait(&store_bar, (stores_issued - 1u) & 1u);
-                    stores_seen = stores_issued;
+                // ---- the draw of the next half-step and what its proposals can fetch already, while the math warps work
+                if (t + 1 < t_end) {
+                    draw(t + 1, my_i);
+                    named_sync(kJoinBarrier, NWT);
+                    prefetch(t + 1);
                 }
-                // ---- accept / reject
-                k = 0;
-                for (int grp = warp; grp < n_groups; grp += n_ww, ++k) {
-                    const int i = min(grp * GW + lane, H - 1);
-                    const int gw = s_base + i;
-                    const double oldlnp = sLnp[gw];
-                    const float fast = sFast[half * H + i];
+                MDA_STAMP_AFTER(2, px[L - 1])
+                if (store_pending) {                       // the chain store must have read the rows before they change
+                    if (tid == 0) bulk_wait_read_all();
+                    named_sync(kJoinBarrier, NWT);
+                    store_pending = false;
+                }
+                // ---- accept / reject my walker
+                const int gw = s_base + my_i;
+                const double oldlnp = sLnp[gw];
+                const float fast = sFast[half * H + my_i];
+                named_sync(kDoneBarrier + warp, 32 * (1 + items_of(warp)));
+                // outside the box the math warps report chi^2 = +inf: log-posterior -inf (mda.py:1576), never accepted
+                const double newlnp = sChi[my_i] * -0.5;       // C/ChiSquare.c:212
+                MDA_STAMP_AFTER(3, newlnp)
+                saw_nan = saw_nan || (newlnp != newlnp);
+                const double est = __dsub_rn(newlnp, oldlnp) + (double)fast;
+                bool accept;
+                if (fabs(est) > 1e-4) {
+                    accept = est > 0.0;                // far from a tie: the float logs (error < 2e-5) cannot change the sign
+                } else {                               // emcee's test in full precision (rare: redo the draw)
+                    const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
+                    const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
+                    const double z2 = __dmul_rn(zr, zr);
+                    const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;
+                    const double zlog = __dmul_rn(dim_m1, log(z));
+                    accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(uniform43(r.w, r.x, r.y));
+                }
+                accept = accept && lane < live_w;
+                if (accept) {                          // my row: proposal -> state (rows are 8 L bytes apart: no bank conflicts)
+                    double *nrow = sPos + gw * L;
+                    const double *qrow = sQ + my_i * L;
                     double qv[L];
 #pragma unroll
-                    for (int l = 0; l < L; ++l) qv[l] = sQ[i * L + l];                  // my own proposal, staged above
-                    mbar_wait_relaxed(&done_bar[grp], hs_phase);
-                    MDA_STAMP(3)
-                    // outside the box the log-posterior is -inf (mda.py:1576): never accepted
-                    const double newlnp = ((out_bits >> k) & 1ull) ? -CUDART_INF : sChi[i] * -0.5;    // C/ChiSquare.c:212
-                    saw_nan = saw_nan || (newlnp != newlnp);
-                    const double est = __dsub_rn(newlnp, oldlnp) + (double)fast;
-                    bool accept;
-                    if (fabs(est) > 1e-4) {
-                        accept = est > 0.0;            // far from a tie: the float logs (error < 2e-5) cannot change the sign
-                    } else {                           // emcee's test in full precision (rare: redo the draw)
-                        const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
-                        const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
-                        const double z2 = __dmul_rn(zr, zr);
-                        const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;
-                        const double zlog = __dmul_rn(dim_m1, log(z));
-                        accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(uniform43(r.w, r.x, r.y));
-                    }
-                    if (accept && grp * GW + lane < H) {
-                        double *nx = sPos + gw * L;
+                    for (int l = 0; l < L; ++l) qv[l] = qrow[l];
 #pragma unroll
-                        for (int l = 0; l < L; ++l) nx[l] = qv[l];
-                        sLnp[gw] = newlnp;
-                        sAcc[gw] += 1u;
-                    }
+                    for (int l = 0; l < L; ++l) nrow[l] = qv[l];
+                    sLnp[gw] = newlnp;
+                    sAcc[gw] += 1u;
                 }
-                if (half && until_keep == 1 && keeping) fence_proxy_async_smem();   // a kept step: rows before the bulk store
                 MDA_STAMP(4)
-            } else {
-                // ---- chi^2 of items of WT tiles of 8 walkers against every angle tile
-                const int g = lane >> 2, tig = lane & 3;
-                for (int item = warp - n_ww; item < n_items; item += n_mw) {
-                    const int grp = item / (GW / IW);
-                    const double *row[WT];
+                const bool kept_step = half && until_keep == 1 && keeping && slot < args.keep_cap;
+                if (kept_step) fence_proxy_async_smem();   // my rows before the bulk store reads them
+                named_sync(kJoinBarrier, NWT);             // the half is complete
+                if (half && --until_keep == 0) {           // a full step is complete and kept: one bulk store of the whole state
+                    until_keep = args.thin;
+                    if (kept_step) {
+                        if (tid == 0) {
+                            bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
+                            bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
+                            bulk_commit();
+                        }
+                        store_pending = true;
+                    }
+                    ++slot;
+                }
+            }
+            if (store_pending) {                           // the last step of the unit was kept: the hand-back waits for its store
+                if (tid == 0) bulk_wait_read_all();
+                store_pending = false;
+            }
+        } else {
+            // ---- chi^2 of my item (WT tiles of 8 walkers) against every angle tile, every half-step
+            const int g = lane >> 2, tig = lane & 3;
+            const int item = warp - n_ww;
+            const int grp = item / IPG;
+            const int n_done = 32 * (1 + items_of(grp));
+            const double *row[WT];
 #pragma unroll
-                    for (int k = 0; k < WT; ++k) row[k] = sQ + min(item * IW + 8 * k + g, H - 1) * L;
-                    mbar_wait_relaxed(&full_bar[grp], hs_phase);
-                    MDA_STAMP(1)
-                    double A[WT][Q], lead[WT][RR];
+            for (int k = 0; k < WT; ++k) row[k] = sQ + min(item * IW + 8 * k + g, H - 1) * L;
+            for (uint32_t t = t_begin; t < t_end; ++t) {
+                long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
+                MDA_STAMP(0)
+                named_sync(kStagedBarrier, n_staged);
+                double A[WT][Q], lead[WT][RR];
+#pragma unroll
+                for (int k = 0; k < WT; ++k) {
+#pragma unroll
+                    for (int l = 0; l < R; ++l) lead[k][l] = row[k][l];
+#pragma unroll
+                    for (int ks = 0; ks < Q; ++ks) A[k][ks] = row[k][R + 4 * ks + tig];
+                }
+                MDA_STAMP_AFTER(1, A[WT - 1][Q - 1])
+                // box prior (mda.py:1575) on the registers just loaded: any component below lo or above hi (a NaN
+                // compares false, as in the reference).  Lane tig will report the walker g of tile tig % WT.
+                bool outside;
+                {
+                    uint32_t out_of[WT];
 #pragma unroll
                     for (int k = 0; k < WT; ++k) {
+                        bool o = false;
 #pragma unroll
-                        for (int l = 0; l < R; ++l) lead[k][l] = row[k][l];
+                        for (int ks = 0; ks < Q; ++ks) o = o | (A[k][ks] < sLo[R + 4 * ks + tig]) | (A[k][ks] > sHi[R + 4 * ks + tig]);
 #pragma unroll
-                        for (int ks = 0; ks < Q; ++ks) A[k][ks] = row[k][R + 4 * ks + tig];
+                        for (int l = 0; l < R; ++l) o = o | (lead[k][l] < sLo[l]) | (lead[k][l] > sHi[l]);
+                        out_of[k] = __ballot_sync(0xffffffffu, o);   // bits 4 g .. 4 g + 3: walker g of tile k
                     }
-                    double chi0[WT], chi1[WT];
+                    uint32_t mine = out_of[0];
 #pragma unroll
-                    for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
-                    if (NT == 8) chi_tiles<L, WT, 8>(sC, 8, lane, A, lead, chi0, chi1);
-                    else chi_tiles<L, WT, 0>(sC, NT, lane, A, lead, chi0, chi1);
-                    // quad sums by a transposing butterfly: lane tig ends up with the sum of tile tig % WT
-                    double sum;
-                    if (WT == 4) {
-                        double sv[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) sv[k] = chi0[k & (WT - 1)] + chi1[k & (WT - 1)];
-                        const bool b0 = (tig & 1) != 0, b1 = (tig & 2) != 0;
-                        const double a01 = (b0 ? sv[1] : sv[0]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[0] : sv[1], 1);   // tile tig & 1
-                        const double a23 = (b0 ? sv[3] : sv[2]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[2] : sv[3], 1);   // tile 2 + (tig & 1)
-                        sum = (b1 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b1 ? a01 : a23, 2);
-                    } else if (WT == 2) {
-                        const double s0 = chi0[0] + chi1[0], s1 = chi0[WT - 1] + chi1[WT - 1];
-                        const bool b0 = (tig & 1) != 0;
-                        sum = (b0 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b0 ? s0 : s1, 1);
-                        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    } else {
-                        sum = chi0[0] + chi1[0];
-                        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    }
-                    const int wk = item * IW + 8 * tig + g;
-                    if (tig < WT && wk < H) sChi[wk] = sum;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&done_bar[grp]);
-                    MDA_STAMP(3)
+                    for (int k = 1; k < WT; ++k) mine = (tig & (WT - 1)) == k ? out_of[k] : mine;
+                    outside = ((mine >> (4 * g)) & 0xfu) != 0u;
                 }
-            }
-            if (!walker_warp) { MDA_STAMP(5) }
-            __syncthreads();
-            if (!walker_warp) { MDA_STAMP(6) }
-#undef MDA_STAMP
-            if (half && --until_keep == 0) {           // a full step is complete and kept: one bulk store of the whole state
-                until_keep = args.thin;
-                if (keeping && slot < args.keep_cap) {
-                    if (warp == n_ww && lane == 0) {       // a math warp: it would only wait for proposals now
-                        bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
-                        bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
-                        bulk_commit();
-                        bulk_wait_read_all();
-                        mbar_arrive(&store_bar);
-                    }
-                    ++stores_issued;
+                double chi0[WT], chi1[WT];
+#pragma unroll
+                for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
+                if (NT == 8) chi_tiles<L, WT, 8>(sC, 8, lane, A, lead, chi0, chi1);
+                else chi_tiles<L, WT, 0>(sC, NT, lane, A, lead, chi0, chi1);
+                // quad sums by a transposing butterfly: lane tig ends up with the sum of tile tig % WT
+                double sum;
+                if (WT == 4) {
+                    double sv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sv[k] = chi0[k & (WT - 1)] + chi1[k & (WT - 1)];
+                    const bool b0 = (tig & 1) != 0, b1 = (tig & 2) != 0;
+                    const double a01 = (b0 ? sv[1] : sv[0]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[0] : sv[1], 1);   // tile tig & 1
+                    const double a23 = (b0 ? sv[3] : sv[2]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[2] : sv[3], 1);   // tile 2 + (tig & 1)
+                    sum = (b1 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b1 ? a01 : a23, 2);
+                } else if (WT == 2) {
+                    const double s0 = chi0[0] + chi1[0], s1 = chi0[WT - 1] + chi1[WT - 1];
+                    const bool b0 = (tig & 1) != 0;
+                    sum = (b0 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b0 ? s0 : s1, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                } else {
+                    sum = chi0[0] + chi1[0];
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                 }
-                ++slot;
+                if (outside) sum = CUDART_INF;
+                const int wk = item * IW + 8 * tig + g;
+                if (tig < WT && wk < H) sChi[wk] = sum;
+                named_arrive(kDoneBarrier + grp, n_done);
+                MDA_STAMP(3)
             }
         }
+#undef MDA_STAMP
+#undef MDA_STAMP_AFTER
 
         // ---- hand the bin back: state to HBM/L2, then the progress word
         __syncthreads();
@@ -470,68 +486,66 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps / CPS), CPS) e
             st_release_u64(args.progress + bin, args.launch_serial + (unsigned long long)(chunk + 1));
         }
     }
-    if (lane == 0) bulk_wait_all();
+    if (tid == 0) bulk_wait_all();
     if (saw_nan) atomicOr(args.status, kStatusNaN);
 }
 
 using EnsKernel = void (*)(const EnsembleArgs);
 
 template <int L>
-EnsKernel pick_mma_wt(int wt, int cps) {
-    if (cps == 2) return wt == 2 ? ensemble_mma_kernel<L, 2, 2> : nullptr;
+EnsKernel pick_mma_wt(int wt) {
     switch (wt) {
-        case 1: return ensemble_mma_kernel<L, 1, 1>;
-        case 2: return ensemble_mma_kernel<L, 2, 1>;
-        case 4: return ensemble_mma_kernel<L, 4, 1>;
+        case 1: return ensemble_mma_kernel<L, 1, false>;
+        case 2: return ensemble_mma_kernel<L, 2, false>;
+        case 4: return ensemble_mma_kernel<L, 4, false>;
         default: return nullptr;
     }
 }
 
-EnsKernel pick_mma_kernel(int n_l, int wt, int cps) {
+EnsKernel pick_mma_kernel(int n_l, int wt) {
     switch (n_l) {
-        case 4: return pick_mma_wt<4>(wt, cps);
-        case 5: return pick_mma_wt<5>(wt, cps);
-        case 6: return pick_mma_wt<6>(wt, cps);
-        case 7: return pick_mma_wt<7>(wt, cps);
-        case 8: return pick_mma_wt<8>(wt, cps);
-        case 9: return pick_mma_wt<9>(wt, cps);
-        case 10: return pick_mma_wt<10>(wt, cps);
-        case 11: return pick_mma_wt<11>(wt, cps);
-        case 12: return pick_mma_wt<12>(wt, cps);
-        case 13: return pick_mma_wt<13>(wt, cps);
-        case 14: return pick_mma_wt<14>(wt, cps);
-        case 15: return pick_mma_wt<15>(wt, cps);
-        case 16: return pick_mma_wt<16>(wt, cps);
+        case 4: return pick_mma_wt<4>(wt);
+        case 5: return pick_mma_wt<5>(wt);
+        case 6: return pick_mma_wt<6>(wt);
+        case 7: return pick_mma_wt<7>(wt);
+        case 8: return pick_mma_wt<8>(wt);
+        case 9: return pick_mma_wt<9>(wt);
+        case 10: return pick_mma_wt<10>(wt);
+        case 11: return pick_mma_wt<11>(wt);
+        case 12: return pick_mma_wt<12>(wt);
+        case 13: return pick_mma_wt<13>(wt);
+        case 14: return pick_mma_wt<14>(wt);
+        case 15: return pick_mma_wt<15>(wt);
+        case 16: return pick_mma_wt<16>(wt);
         default: return nullptr;
     }
 }
+
+// The build with the timeline stamps (mdaEnsembleProfile): the C4 shape only.
+constexpr int kProfL = 9, kProfWT = 4;
+EnsKernel prof_kernel() { return ensemble_mma_kernel<kProfL, kProfWT, true>; }
 
 }  // namespace
 
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
-                               int force_cps, EnsembleShape *out) {
+                               EnsembleShape *out) {
+    (void)bins;
+    (void)sm_count;
     if (n_l < kMinMmaL || n_l > kMaxRegL) return false;
     EnsembleShape s{};
     const int half = walkers / 2;
     const int n_groups = (half + GW - 1) / GW;
-    if (n_groups > kMaxGroups) return false;
+    if (n_groups > kWalkerWarps) return false;                               // one group per walker warp
     s.smem_bytes = EnsembleMmaSmem(walkers, n_l, n_tiles).total;
-    // two bins per SM when every SM gets two and two ensembles fit its shared memory (measured, C4 shape:
-    // +8 % at 296 bins; with fewer bins the SMs that carry two slower CTAs finish last)
-    int cps = (bins >= 2 * sm_count && 2 * (s.smem_bytes + kStaticSmem + 1024) <= smem_optin + 1024) ? 2 : 1;
-    if (force_cps == 1 || force_cps == 2) cps = force_cps;
-    // tiles per math item: a whole group where that still gives every scheduler two math warps
-    int wt = n_groups >= kMathWarps ? 4 : (2 * n_groups >= kMathWarps ? 2 : 1);
-    if (n_l > 12 && wt == 4) wt = 2;                                         // registers: A fragments of 4 tiles x 4 k-steps
+    // tiles per math item: the fewest that give every item its own math warp
+    int wt = 8 * kMathWarps >= half ? 1 : (16 * kMathWarps >= half ? 2 : 4);
     if (force_wt == 1 || force_wt == 2 || force_wt == 4) wt = force_wt;
-    if (cps == 2) wt = 2;
     const int n_items = (half + 8 * wt - 1) / (8 * wt);
+    if (n_items > kMathWarps) return false;                                  // one item per math warp
     s.wpt = wt;
-    s.stage = cps;
-    s.groups = n_groups < kWalkerWarps ? n_groups : kWalkerWarps;            // walker warps
-    const int max_math = kMathWarps / cps;
-    const int math = n_items < max_math ? n_items : max_math;
-    s.threads = 32 * (s.groups + math);
+    s.groups = n_groups;                                                     // walker warps
+    s.stage = 1;
+    s.threads = 32 * (n_groups + n_items);
     s.global_state = false;
     s.mma = true;
     s.fits = s.smem_bytes + kStaticSmem <= smem_optin && (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8 < (1u << 20);
@@ -541,25 +555,25 @@ bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int 
 }
 
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin) {
+    auto raise = [&](EnsKernel fn) -> cudaError_t {
+        const void *k = reinterpret_cast<const void *>(fn);
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, k);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
+    };
     for (int l = kMinMmaL; l <= kMaxRegL; ++l)
-        for (int cps = 1; cps <= 2; ++cps)
-            for (int wt = 1; wt <= 4; wt *= 2) {
-                EnsKernel fn = pick_mma_kernel(l, wt, cps);
-                if (!fn) continue;
-                const void *k = reinterpret_cast<const void *>(fn);
-                cudaFuncAttributes fa;
-                cudaError_t e = cudaFuncGetAttributes(&fa, k);
-                if (e != cudaSuccess) return e;
-                e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
-                if (e != cudaSuccess) return e;
-            }
-    return cudaSuccess;
+        for (int wt = 1; wt <= 4; wt *= 2) {
+            cudaError_t e = raise(pick_mma_kernel(l, wt));
+            if (e != cudaSuccess) return e;
+        }
+    return raise(prof_kernel());
 }
 
 // Co-resident CTAs of this kernel on the whole device (the unit list needs every CTA of the grid
 // resident: a unit may wait for one that runs on another CTA).
 int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count) {
-    EnsKernel k = pick_mma_kernel(n_l, shape.wpt, shape.stage);
+    EnsKernel k = pick_mma_kernel(n_l, shape.wpt);
     int per_sm = 0;
     if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(k), shape.threads,
                                                             shape.smem_bytes) != cudaSuccess)
@@ -569,12 +583,13 @@ int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count) {
 
 cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream) {
     if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
-    EnsKernel k = pick_mma_kernel(args.n_l, shape.wpt, shape.stage);
+    EnsKernel k = pick_mma_kernel(args.n_l, shape.wpt);
+    if (args.prof && args.n_l == kProfL && shape.wpt == kProfWT) k = prof_kernel();
     if (!k || !shape.fits || !shape.mma || !args.consts_mma || grid < 1 || args.chunk_steps < 1 || args.n_chunks < 1 ||
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;
     EnsembleArgs a = args;
-    a.groups = shape.groups | (2 << 8);                    // walker warps (the rest of the block are math warps); two gather at a time
+    a.groups = shape.groups;                               // walker warps (the rest of the block are math warps)
     k<<<grid, shape.threads, shape.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }

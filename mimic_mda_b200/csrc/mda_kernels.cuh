@@ -82,7 +82,7 @@ struct EnsembleArgs {
 
 struct EnsembleShape {
     int threads, wpt, groups;  // blockDim = walker threads x angle groups
-    int stage;                 // DMMA stepper: CTAs per SM the kernel variant is built for (1 or 2)
+    int stage;                 // unused
     size_t smem_bytes;
     bool fits;                 // the launch is possible (shared memory, numL <= kMaxRegL)
     bool global_state;         // positions / log-probabilities stay in HBM (ensemble too large for shared memory)
@@ -99,9 +99,9 @@ cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape
 //   k-step ks < L / 4     : [32] B fragment, lane (g, tig) holds -D_{R + 4 ks + tig}[8 t + g]
 // i.e. 8 (1 + L) doubles per tile; the distributions are stored negated so that the residual
 // d - sum a_l D_l is a pure multiply-accumulate onto d.  Returns false when the shape cannot run (numL < kMinMmaL,
-// numL > kMaxRegL or the double-buffered ensemble does not fit shared memory).
+// numL > kMaxRegL, more than 512 walkers or the ensemble does not fit shared memory).
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
-                               int force_cps, EnsembleShape *out);
+                               EnsembleShape *out);
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin);
 int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count);   // co-resident CTAs on the device
 cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);

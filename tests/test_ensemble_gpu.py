@@ -20,6 +20,8 @@ def _problem(n_bins, n_l, n_pts, walkers, ragged=True, seed=17):
 
 @pytest.mark.parametrize("shape", [(1, 4, 30, 64, 150), (5, 9, 60, 96, 60), (3, 5, 31, 512, 25), (2, 8, 41, 34, 80),
                                    (2, 1, 7, 8, 50), (1, 16, 24, 40, 30),
+                                   # more than 512 walkers: the DFMA stepper with the state in shared memory
+                                   (2, 6, 33, 1100, 8),
                                    # ensembles larger than shared memory (state in HBM/L2): the reference's own
                                    # 2500 walkers x 8 parameters (mda_config0.py:93,105), and a wider one
                                    (1, 8, 41, 2500, 12), (2, 9, 60, 3000, 6)])
@@ -83,9 +85,8 @@ def test_split_runs_thinning_and_partition_invariance(cs_lib):
 
 @pytest.mark.parametrize("env", [{"MDA_ENS_GRID": "2", "MDA_ENS_CHUNK": "7"},        # 5 bins on 2 CTAs, 9 chunks: hand-over through HBM
                                  {"MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "1"},
-                                 {"MDA_ENS_CPS": "2"},                               # the two-CTAs-per-SM build of the kernel
-                                 {"MDA_ENS_CPS": "2", "MDA_ENS_GRID": "4", "MDA_ENS_CHUNK": "16"},
-                                 {"MDA_ENS_WT": "2"}, {"MDA_ENS_WT": "1"},
+                                 {"MDA_ENS_GRID": "4", "MDA_ENS_CHUNK": "16"},
+                                 {"MDA_ENS_WT": "2"}, {"MDA_ENS_WT": "4"},
                                  {"MDA_ENS_IMPL": "dfma"}])
 def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
     """Units of (chunk of steps, bin) walked by fewer CTAs than bins, other tilings of the chi^2 work and the
