@@ -51,7 +51,7 @@ constexpr int kStatusNaN = 1;
 constexpr int kWalkerWarps = 8;        // at most: one group of 32 walkers each
 constexpr int kMathWarps = 8;          // at most: two per scheduler keep the fp64 pipe fed
 constexpr int GW = 32;                 // walkers of a group (a walker warp's lanes)
-constexpr int kStagedBarrier = 1;      // named barrier: the proposals of the half-step are staged (walker warps arrive, math warps wait)
+constexpr int kDrawnBarrier = 1;       // named barrier: the draw of the next half-step is published (walker warps arrive, math warps wait)
 constexpr int kDoneBarrier = 2;        // named barriers 2 .. 9: chi^2 of a group is there (its math warps arrive, its walker warp waits)
 constexpr int kJoinBarrier = 10;       // named barrier of the walker warps
 constexpr size_t kStaticSmem = 64;     // the mbarrier of the constants (static __shared__), rounded up
@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
     constexpr int IW = 8 * WT;                    // walkers of a math item
     constexpr int IPG = GW / IW;                  // math items per group
     constexpr int TS = 8 * (L + 1);               // doubles per angle tile of the constants
+    constexpr int NLE = (WT * R + 3) / 4;         // leading elements (l < R) a lane proposes; the quad shares them
+    constexpr int NLS = NLE > 0 ? NLE : 1;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;                 // constants of a unit have landed
@@ -180,9 +182,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
     const int n_items = (H + IW - 1) / IW;
     const int n_ww = args.groups;                 // walker warps = groups of a half (the launch sets it)
     const int NWT = 32 * n_ww;                    // walker threads
-    const int E = H * L;                          // elements of a half
     const bool walker_warp = warp < n_ww;
-    const bool full_half = E == NWT * L;          // every group has 32 walkers: no element of a pass is beyond the half
 
     const EnsembleMmaSmem lay(W, L, NT);
     const double *sC = reinterpret_cast<const double *>(smem_raw + lay.consts);
@@ -209,20 +209,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
     const double dim_m1 = (double)(L - 1);
     const float dim_m1f = (float)(L - 1);
 
-    // threads of both barriers of group g: proposals staged (all walker warps + its math warps), chi^2 there
     auto items_of = [&](int g) { return min(IPG, n_items - g * IPG); };
-    const int n_staged = T;                       // every warp of the CTA takes part in the staged barrier
-
-    // ---- walker warps: flattened element e = p NWT + tid of pass p is component el_l of walker el_i of the half
-    int el_i[L], el_l[L];
-    if (walker_warp) {
-#pragma unroll
-        for (int p = 0; p < L; ++p) {
-            const int e = min(p * NWT + tid, E - 1);
-            el_i[p] = e / L;
-            el_l[p] = e - el_i[p] * L;
-        }
-    }
 
     bool saw_nan = false;
     uint32_t unit_phase = 0;                               // parity of mbar
@@ -265,7 +252,6 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
 
         mbar_wait(&mbar, unit_phase);
         unit_phase ^= 1u;
-        __syncthreads();
 
         // debug timeline (mdaEnsembleProfile): clock stamps of one half-step, per warp
         const uint32_t t_prof = (PROF && args.prof != nullptr && chunk == 0) ? t_begin + min(81u, 2u * (uint32_t)steps_here - 1u) : 0xffffffffu;
@@ -289,55 +275,22 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                 sFast[(t & 1u) * H + i] = dim_m1f * __logf((float)z) - __logf((float)ua);
                 sPartner[i] = c_base + (int)__umulhi(r.z, (uint32_t)H);
             };
-            // What the proposals of half-step t need and the half-step before does not change: stretch
-            // factor, own component, index of the partner's component (of my element of every pass).
-            double pz[L], px[L];
-            int pc[L];
-            auto prefetch = [&](uint32_t t) {
-                const double *xrow = sPos + ((t & 1u) ? H : 0) * L;
-#pragma unroll
-                for (int p = 0; p < L; ++p) {
-                    pz[p] = sZ[el_i[p]];
-                    pc[p] = sPartner[el_i[p]] * L + el_l[p];
-                    px[p] = xrow[min(p * NWT + tid, E - 1)];
-                }
-            };
-            const int my_i = min(warp * GW + lane, H - 1);     // my walker of my group (decisions)
+            const int my_i = min(warp * GW + lane, H - 1);     // my walker of my group
             const int live_w = min(GW, H - warp * GW);
             draw(t_begin, my_i);
-            named_sync(kJoinBarrier, NWT);
-            prefetch(t_begin);
+            __syncthreads();                                   // state and first draw are there
 
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 const uint32_t half = t & 1u;
                 const int s_base = half ? H : 0;              // the half being updated; partners come from the other one
                 long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
                 MDA_STAMP(0)
-                // ---- proposals q = c - z (c - x), pass by pass; a group is announced with its last pass
-                double c[L];
-#pragma unroll
-                for (int p = 0; p < L; ++p) c[p] = sPos[pc[p]];
-                MDA_STAMP_AFTER(5, c[L - 1])
-                // all the fp64 work first: once the math warps of the first groups run, the pipe is theirs
-                // (the empty asm pins every result before the first barrier instruction below)
-                double v[L];
-#pragma unroll
-                for (int p = 0; p < L; ++p) v[p] = __dsub_rn(c[p], __dmul_rn(pz[p], __dsub_rn(c[p], px[p])));
-#pragma unroll
-                for (int p = 0; p < L; ++p) asm volatile("" : "+d"(v[p]));
-                MDA_STAMP(6)
-#pragma unroll
-                for (int p = 0; p < L; ++p)
-                    if (full_half || p * NWT + tid < E) sQ[p * NWT + tid] = v[p];
-                named_arrive(kStagedBarrier, n_staged);    // one arrival per half-step: it waits for the stores above (~150 cycles)
-                MDA_STAMP(1)
-                // ---- the draw of the next half-step and what its proposals can fetch already, while the math warps work
+                // ---- the draw of the next half-step, while the math warps propose and evaluate this one
                 if (t + 1 < t_end) {
                     draw(t + 1, my_i);
-                    named_sync(kJoinBarrier, NWT);
-                    prefetch(t + 1);
+                    named_arrive(kDrawnBarrier, T);
                 }
-                MDA_STAMP_AFTER(2, px[L - 1])
+                MDA_STAMP(2)
                 if (store_pending) {                       // the chain store must have read the rows before they change
                     if (tid == 0) bulk_wait_read_all();
                     named_sync(kJoinBarrier, NWT);
@@ -379,7 +332,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                 MDA_STAMP(4)
                 const bool kept_step = half && until_keep == 1 && keeping && slot < args.keep_cap;
                 if (kept_step) fence_proxy_async_smem();   // my rows before the bulk store reads them
-                named_sync(kJoinBarrier, NWT);             // the half is complete
+                __syncthreads();                           // the half is complete
                 if (half && --until_keep == 0) {           // a full step is complete and kept: one bulk store of the whole state
                     until_keep = args.thin;
                     if (kept_step) {
@@ -398,29 +351,90 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                 store_pending = false;
             }
         } else {
-            // ---- chi^2 of my item (WT tiles of 8 walkers) against every angle tile, every half-step
+            // ---- my item (WT tiles of 8 walkers) of every half-step: propose, box prior, chi^2 against every angle tile
             const int g = lane >> 2, tig = lane & 3;
             const int item = warp - n_ww;
             const int grp = item / IPG;
             const int n_done = 32 * (1 + items_of(grp));
-            const double *row[WT];
+            int wi[WT];                                        // my walker of tile k (index within the half)
 #pragma unroll
-            for (int k = 0; k < WT; ++k) row[k] = sQ + min(item * IW + 8 * k + g, H - 1) * L;
+            for (int k = 0; k < WT; ++k) wi[k] = min(item * IW + 8 * k + g, H - 1);
+            // leading elements (l < R) of the quad's WT walkers are shared out over its 4 lanes: slot n of lane tig is
+            // element j = tig + 4 n of the list (tile j / R, component j % R)
+            int lw[NLS], ll[NLS];
+#pragma unroll
+            for (int n = 0; n < NLE; ++n) {
+                const int j = min(tig + 4 * n, WT * RR - 1);
+                lw[n] = min(item * IW + 8 * (j / RR) + g, H - 1);
+                ll[n] = j % RR;
+            }
+            // what the proposals of half-step t need and half-step t - 1 does not change: stretch factors, own
+            // components, index of the partner's components
+            double pz[WT], pxa[WT][Q], pzl[NLS], pxl[NLS];
+            int pca[WT][Q], pcl[NLS];
+            auto prefetch = [&](uint32_t t) {
+                const double *xhalf = sPos + ((t & 1u) ? H : 0) * L;
+#pragma unroll
+                for (int k = 0; k < WT; ++k) {
+                    pz[k] = sZ[wi[k]];
+                    const int part = sPartner[wi[k]] * L;
+#pragma unroll
+                    for (int ks = 0; ks < Q; ++ks) {
+                        pca[k][ks] = part + R + 4 * ks + tig;
+                        pxa[k][ks] = xhalf[wi[k] * L + R + 4 * ks + tig];
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < NLE; ++n) {
+                    pzl[n] = sZ[lw[n]];
+                    pcl[n] = sPartner[lw[n]] * L + ll[n];
+                    pxl[n] = xhalf[lw[n] * L + ll[n]];
+                }
+            };
+            __syncthreads();                                   // state and first draw are there
+            prefetch(t_begin);
+
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
                 MDA_STAMP(0)
-                named_sync(kStagedBarrier, n_staged);
-                double A[WT][Q], lead[WT][RR];
+                // ---- proposals q = c - z (c - x) of my elements: gather the partners' components, 3 fp64 operations each
+                double A[WT][Q], lead[WT][RR], myl[NLS];
+                {
+                    double ca[WT][Q], cl[NLS];
 #pragma unroll
-                for (int k = 0; k < WT; ++k) {
+                    for (int k = 0; k < WT; ++k)
 #pragma unroll
-                    for (int l = 0; l < R; ++l) lead[k][l] = row[k][l];
+                        for (int ks = 0; ks < Q; ++ks) ca[k][ks] = sPos[pca[k][ks]];
 #pragma unroll
-                    for (int ks = 0; ks < Q; ++ks) A[k][ks] = row[k][R + 4 * ks + tig];
+                    for (int n = 0; n < NLE; ++n) cl[n] = sPos[pcl[n]];
+#pragma unroll
+                    for (int k = 0; k < WT; ++k)
+#pragma unroll
+                        for (int ks = 0; ks < Q; ++ks)
+                            A[k][ks] = __dsub_rn(ca[k][ks], __dmul_rn(pz[k], __dsub_rn(ca[k][ks], pxa[k][ks])));
+#pragma unroll
+                    for (int n = 0; n < NLE; ++n) myl[n] = __dsub_rn(cl[n], __dmul_rn(pzl[n], __dsub_rn(cl[n], pxl[n])));
                 }
+                // the rows the walker warps copy on acceptance
+#pragma unroll
+                for (int k = 0; k < WT; ++k)
+#pragma unroll
+                    for (int ks = 0; ks < Q; ++ks) sQ[wi[k] * L + R + 4 * ks + tig] = A[k][ks];
+#pragma unroll
+                for (int n = 0; n < NLE; ++n)
+                    if (tig + 4 * n < WT * R) sQ[lw[n] * L + ll[n]] = myl[n];
+#pragma unroll
+                for (int k = 0; k < WT; ++k)
+#pragma unroll
+                    for (int l = 0; l < R; ++l) {
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int j = k * R + l;               // compile-time: lane j % 4 of the quad holds it in slot j / 4
+                        lead[k][l] = __shfl_sync(0xffffffffu, myl[j / 4], (lane & ~3) | (j & 3));
+                    }
                 MDA_STAMP_AFTER(1, A[WT - 1][Q - 1])
-                // box prior (mda.py:1575) on the registers just loaded: any component below lo or above hi (a NaN
-                // compares false, as in the reference).  Lane tig will report the walker g of tile tig % WT.
+                // box prior (mda.py:1575) on these registers: any component below lo or above hi (a NaN compares
+                // false, as in the reference).  Lane tig will report the walker g of tile tig % WT.
                 bool outside;
                 {
                     uint32_t out_of[WT];
@@ -468,6 +482,12 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                 if (tig < WT && wk < H) sChi[wk] = sum;
                 named_arrive(kDoneBarrier + grp, n_done);
                 MDA_STAMP(3)
+                // ---- while the walker warps decide: what the next half-step's proposals can fetch already
+                if (t + 1 < t_end) {
+                    named_sync(kDrawnBarrier, T);
+                    prefetch(t + 1);
+                }
+                __syncthreads();                           // the half is complete
             }
         }
 #undef MDA_STAMP
