@@ -113,6 +113,7 @@ int ensure_runtime() {
     MDA_CUDA(configure_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem)");
     MDA_CUDA(configure_ensemble_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, ensemble)");
     MDA_CUDA(configure_ensemble_mma_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, DMMA ensemble)");
+    MDA_CUDA(configure_ensemble_ws_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, warp-specialised DMMA ensemble)");
     g_rt.ready = true;
     return MDA_OK;
 }
@@ -415,36 +416,46 @@ struct MdaEnsemble {
     cudaEvent_t chunk_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
 };
 
-// The DMMA stepper wherever it can run; MDA_ENS_IMPL=dfma forces the register-tiled DFMA stepper
-// (which also carries numL < 4 and ensembles too large for the double-buffered layout).
+// Which stepper runs an ensemble.  DMMA wherever it can: with two or more bins per SM the homogeneous 8-warp kernel
+// (ensemble_mma_kernel, two CTAs -- two bins -- per SM), below that the warp-specialised 16-warp kernel
+// (ensemble_ws_kernel, one bin per SM at a time).  The register-tiled DFMA stepper carries numL < 4, ensembles of
+// more than 512 walkers and ensembles larger than shared memory.  MDA_ENS_IMPL = mma | ws | dfma forces one.
 EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
+    const bool want_dfma = impl && strcmp(impl, "dfma") == 0, want_ws = impl && strcmp(impl, "ws") == 0,
+               want_mma = impl && strcmp(impl, "mma") == 0;
     EnsembleShape shape{};
-    if (!(impl && strcmp(impl, "dfma") == 0) &&
-        choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_WT", 0), &shape))
-        return shape;
+    if (!want_dfma) {
+        const bool prefer_mma = want_mma || (!want_ws && s->bins >= 2 * g_rt.sm_count);
+        const int wt = env_int("MDA_ENS_WT", 0);
+        if (prefer_mma && choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, &shape)) return shape;
+        if (choose_ensemble_ws_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, &shape)) return shape;
+        if (choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, &shape)) return shape;
+    }
     return choose_ensemble_shape(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
 }
 
 // Schedule of one launch of the DMMA stepper: (chunk of steps, bin) units, chunk-major, unit u on CTA
-// u mod grid.  Every bin has its own CTA when they are all co-resident; otherwise the resident CTAs walk
-// the list, so that each SM carries the same share of the run (MDA_ENS_GRID / MDA_ENS_CHUNK override,
-// for experiments and tests).
+// u mod grid.  Up to one bin per SM every bin simply has its own CTA.  With more bins than SMs the resident CTAs
+// walk the list, so that every SM carries the same share of the run (C4: 200 bins on 148 SMs; from two bins per
+// SM on, the 8-warp kernel keeps two CTAs per SM).  MDA_ENS_GRID / MDA_ENS_CHUNK override, for experiments and tests.
 struct SteppingPlan { int grid, chunk_steps, n_chunks; };
 SteppingPlan plan_stepping(const MdaStore *s, const EnsembleShape &shape, int nSteps) {
     SteppingPlan p{0, nSteps, 1};
-    const int capacity = ensemble_mma_capacity(s->n_l, shape, g_rt.sm_count);
+    const int capacity = shape.ws ? ensemble_ws_capacity(s->n_l, shape, g_rt.sm_count) : ensemble_mma_capacity(s->n_l, shape, g_rt.sm_count);
     if (capacity < 1) return p;
-    int grid = std::min(s->bins, capacity);
+    // between one and two bins per SM a second CTA per SM does not pay (measured: the units that wait for their
+    // predecessor leave SMs idle), so the grid is one CTA per SM there
+    int grid = s->bins <= g_rt.sm_count ? s->bins : (s->bins < capacity ? g_rt.sm_count : capacity);
     const int force_grid = env_int("MDA_ENS_GRID", 0);
     if (force_grid > 0) grid = force_grid;
-    grid = std::max(1, std::min(grid, std::min(capacity, s->bins)));
+    grid = std::max(1, std::min(grid, capacity));
     int chunk_steps = nSteps;
+    const int min_chunk = 8, max_chunks = std::max(1, std::min(96, nSteps / min_chunk));
     if (grid < s->bins) {
         // Units are walked in rounds of `grid`; the last round is only partly filled.  Among the chunk counts that keep a
-        // chunk at 8 steps or more, take the one that wastes the smallest share of CTA time in that last round (C4: 200
-        // bins on 148 CTAs -> 37 chunks, 7400 units = exactly 50 rounds); ties go to the fewer hand-overs.
-        const int min_chunk = 8, max_chunks = std::max(1, std::min(96, nSteps / min_chunk));
+        // chunk at 8 steps or more, take the one that wastes the smallest share of CTA time in that last round; ties go
+        // to the fewer hand-overs.
         double best_waste = 1e30;
         int best = 1;
         for (int n = std::min(4, max_chunks); n <= max_chunks; ++n) {
@@ -998,7 +1009,8 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
         args.n_chunks = plan.n_chunks;
         args.progress = e->d_progress;
         args.launch_serial = (++e->launches) << 32;
-        MDA_CUDA(launch_ensemble_mma(args, shape, plan.grid, s->stream), "ensemble stepping launch (DMMA)");
+        if (shape.ws) MDA_CUDA(launch_ensemble_ws(args, shape, plan.grid, s->stream), "ensemble stepping launch (DMMA, warp-specialised)");
+        else MDA_CUDA(launch_ensemble_mma(args, shape, plan.grid, s->stream), "ensemble stepping launch (DMMA)");
     } else {
         MDA_CUDA(launch_ensemble(args, shape, s->stream), "ensemble stepping launch");
     }
@@ -1019,11 +1031,17 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
     if (shape.mma) {
         const SteppingPlan plan = plan_stepping(s, shape, nSteps);
-        snprintf(text, (size_t)textLen,
-                 "ensemble_mma_kernel<L=%d,WT=%d>: fp64 DMMA.8x8x4 chi^2, %d walker + %d math warps per CTA meeting at named barriers, %zu B shared memory; "
-                 "%d CTAs walk %d bins x %d chunks of %d steps",
-                 s->n_l, shape.wpt, shape.groups, shape.threads / 32 - shape.groups, shape.smem_bytes, plan.grid, s->bins,
-                 plan.n_chunks, plan.chunk_steps);
+        if (shape.ws)
+            snprintf(text, (size_t)textLen,
+                     "ensemble_ws_kernel<L=%d,WT=%d>: fp64 DMMA.8x8x4 chi^2, %d walker + %d math warps per CTA meeting at named barriers, %zu B shared memory; "
+                     "%d CTAs walk %d bins x %d chunks of %d steps",
+                     s->n_l, shape.wpt, shape.groups, shape.threads / 32 - shape.groups, shape.smem_bytes, plan.grid, s->bins,
+                     plan.n_chunks, plan.chunk_steps);
+        else
+            snprintf(text, (size_t)textLen,
+                     "ensemble_mma_kernel<L=%d,WT=%d>: fp64 DMMA.8x8x4 chi^2, %d warps per CTA (one item of %d walkers each, one barrier per half-step), %zu B shared memory; "
+                     "%d CTAs walk %d bins x %d chunks of %d steps",
+                     s->n_l, shape.wpt, shape.threads / 32, 8 * shape.wpt, shape.smem_bytes, plan.grid, s->bins, plan.n_chunks, plan.chunk_steps);
     } else {
         snprintf(text, (size_t)textLen, "ensemble_kernel<L=%d,WPT=%d,%s>: DFMA chi^2, %d threads x %d angle groups per CTA, %zu B shared memory; one CTA per bin (%d)",
                  s->n_l, shape.wpt, shape.global_state ? "state in HBM" : "state in shared memory", shape.threads, shape.groups, shape.smem_bytes, s->bins);

@@ -1,45 +1,43 @@
 // ensemble_mma_kernel.cu -- device-resident ensemble stepping with the chi-square contraction on
-// the fp64 tensor path (DMMA.8x8x4) and warp-specialised bookkeeping, SURVEY.md 8f-1.
+// the fp64 tensor path (DMMA.8x8x4), SURVEY.md 8f-1.
 //
 // Same job and same random streams as ensemble_kernel.cu (the reference's host loop
 // emcee.EnsembleSampler.run_mcmc -> ln_post_prob per walker, mda.py:1128-1131, 1540-1578, as ONE
-// persistent launch).  A CTA owns an Ex bin (for a chunk of steps) and has two kinds of warps:
+// persistent launch).  A CTA owns an Ex bin (for a chunk of steps): constants, positions, log-
+// probabilities and acceptance counters live in shared memory.  Every warp does the whole half-step
+// for its own item of 8 WT walkers, and everything between "the other half is complete" and "my
+// walkers are updated" stays in its registers:
 //
-//   * math warps: chi^2 of one item of 8 WT walkers per half-step.  Lane (g, tig) = (lane / 4, lane % 4)
-//     loads, for walker g of a tile of 8, the proposal elements l = R + 4 ks + tig (ks < Q = L / 4) -- the
-//     A fragment of mma.m8n8k4 -- and the R = L % 4 leading ones; residuals of an 8-walker x 8-angle
-//     tile are c = d + sum_{l<R} q_l (-D_l) by DFMA, then Q DMMAs against B fragments of the NEGATED
-//     distributions staged fragment-major in shared memory; chi^2 is accumulated from the C fragment
-//     and reduced over the quad.  Every term of the reference's sum (C/ChiSquare.c:188-210) is
-//     evaluated exactly once, only the order of the fp64 additions differs (|error| ~ 1e-16
-//     relative, tested against the oracle).  The box prior (mda.py:1574-1576) is tested on the same
-//     registers: a walker outside gets chi^2 = +inf, i.e. log-posterior -inf.  Why DMMA: a DFMA with
-//     three distinct register operands is register-bandwidth bound at ~72 % of the fp64 pipe on
-//     sm_100a; DMMA.8x8x4 runs on the same pipe at its full rate with 1/8 of the issue slots
-//     (tools/ubench/dmma_ubench.cu).
-//   * walker warps.  Proposals q = c - z (c - x) are staged by ALL walker warps together over the
-//     flattened elements of the half, e = pass * (walker threads) + thread: own rows and proposals are
-//     contiguous runs, only the partner rows c are gathered.  Everything of a proposal that does not
-//     depend on the half being updated right now (its own row x, its stretch factor z, the address of
-//     its partner row) is fetched during the previous half-step, while the fp64 pipe is busy, so that
-//     the stretch between "the other half is complete" and "the math warps run" is one gather, 3 L
-//     fp64 operations and one store per thread.  Decisions stay with lane = walker of warp = group:
-//     Philox draw, accept / reject, in-place update, acceptance counters.
-//   * hand-offs are NAMED BARRIERS (bar.sync / bar.arrive), never polled: barrier 1 completes when the
-//     proposals are staged (walker warps arrive, math warps wait), barrier 2 + g when the chi^2 of group
-//     g is there (its math warps arrive, walker warp g waits), barrier 10 joins the walker warps at the
-//     end of a half-step (the stretch move needs the other half complete).  A bar.arrive costs ~150
-//     cycles (it waits for the thread's shared-memory stores), so there is one per warp and half-step.
-//     An mbarrier wait compiles to a try_wait / NANOSLEEP.SYNCS loop that wakes up every ~100 cycles:
-//     in the mbarrier version of this kernel 25 % of all executed instructions were such probes
-//     (profiles/r01_ncu_full_c4_ensemble_mma.csv), taken from the issue slots of the math warps.
+//   * lane (g, tig) = (lane / 4, lane % 4) holds, for walker g of each of the WT tiles of 8, the
+//     components l = R + 4 ks + tig (ks < Q = L / 4) -- the A fragment of mma.m8n8k4 -- and a share of the
+//     R = L % 4 leading ones.  It gathers the partners' components c and forms the proposal
+//     q = c - z (c - x) itself (numpy rounding: __dmul_rn / __dsub_rn, no FMA contraction), from operands
+//     x, z and partner addresses it fetched before the barrier;
+//   * box prior (mda.py:1574-1576) on those registers; residuals of an 8-walker x 8-angle tile are
+//     c = d + sum_{l<R} q_l (-D_l) by DFMA, then Q DMMAs against B fragments of the NEGATED distributions
+//     staged fragment-major in shared memory; chi^2 is accumulated from the C fragment and reduced over
+//     the quad so that lane (g, tig = k) ends up with chi^2 of walker g of tile k: its decision lane.
+//     Every term of the reference's sum (C/ChiSquare.c:188-210) is evaluated exactly once, only the
+//     order of the fp64 additions differs (|error| ~ 1e-16 relative, tested against the oracle);
+//   * the decision lane made the Philox draw of its walker (z, partner, u'), so the accept test needs
+//     nothing from other warps; the accept bits are balloted and every lane writes the components it
+//     holds of the accepted walkers straight into the state.  No proposal, chi^2 or draw ever goes
+//     through shared memory, and the only synchronisation is ONE CTA barrier per half-step (the
+//     stretch move needs the other half complete).
+//   * a CTA is 8 warps with at most 128 registers: two CTAs -- two bins -- share an SM, and the gather,
+//     decision and barrier latencies of one run under the DMMA stream of the other.
 //   * CTAs walk a list of (step chunk, bin) units in chunk-major order, unit u on CTA u mod grid; a
 //     unit waits for the previous chunk of its bin through a release/acquire word per bin and hands
-//     the ensemble state over through HBM/L2.  With more bins than SMs (C4: 200 on 148) every SM
-//     carries the same share of the work instead of 52 SMs carrying two bins for the whole run.
+//     the ensemble state over through HBM/L2, so that every SM carries the same share of the run.
 //
-// Shapes: every walker warp owns one group of 32 walkers of a half and every math warp one item, so
-// ensembles of up to 512 walkers (all BASELINE.json shapes); larger ones run on ensemble_kernel.cu.
+// Why DMMA: a DFMA with three distinct register operands is register-bandwidth bound at ~72 % of the
+// fp64 pipe on sm_100a; DMMA.8x8x4 runs on the same pipe at its full rate with 1/8 of the issue
+// slots and lets integer work of other warps issue underneath (tools/ubench/dmma_ubench.cu,
+// port_ubench.cu).  Earlier versions of this kernel (warp-specialised, mbarrier or named-barrier
+// hand-offs through shared memory) are in the history; profiles/experiments/r01_stepper_variants.md.
+//
+// Shapes: one item per warp, at most 8 warps: ensembles of up to 512 walkers (all BASELINE.json
+// shapes); larger ones run on ensemble_kernel.cu.
 #include "likelihood.cuh"
 #include "philox.cuh"
 
@@ -48,28 +46,17 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
-constexpr int kWalkerWarps = 8;        // at most: one group of 32 walkers each
-constexpr int kMathWarps = 8;          // at most: two per scheduler keep the fp64 pipe fed
-constexpr int GW = 32;                 // walkers of a group (a walker warp's lanes)
-constexpr int kDrawnBarrier = 1;       // named barrier: the draw of the next half-step is published (walker warps arrive, math warps wait)
-constexpr int kDoneBarrier = 2;        // named barriers 2 .. 9: chi^2 of a group is there (its math warps arrive, its walker warp waits)
-constexpr int kJoinBarrier = 10;       // named barrier of the walker warps
-constexpr size_t kStaticSmem = 64;     // the mbarrier of the constants (static __shared__), rounded up
+constexpr int kMaxWarps = 8;           // items (warps) per CTA
+constexpr size_t kStaticSmem = 64;     // the mbarriers (static __shared__), rounded up
 
 struct EnsembleMmaSmem {
-    size_t consts, pos, q, lnp, chi, z, bounds, fast, partner, acc, total;
+    size_t consts, pos, lnp, bounds, acc, total;
     __host__ __device__ EnsembleMmaSmem(int walkers, int n_l, int n_tiles) {
-        const size_t h = (size_t)walkers / 2;
         size_t off = 0;
         consts = off;  off += (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8;     // [tiles][8 (1+L)] fragment-major
         pos = off;     off += (size_t)walkers * (size_t)n_l * 8;               // [W][L] dense, updated in place; bulk-stored as is
         lnp = off;     off += (size_t)walkers * 8;                             // [W] (16-byte aligned: W is even)
-        q = off;       off += h * (size_t)n_l * 8;                             // [H][L] proposals of the half-step
-        chi = off;     off += h * 8;                                           // [H] chi^2 of the proposals (+inf: outside the box)
-        z = off;       off += h * 8;                                           // [H] stretch factor of the next proposal
         bounds = off;  off += 2 * (size_t)n_l * 8;                             // [2][L] box prior: lo, hi
-        fast = off;    off += 2 * h * 4;                                       // [2][H] float (L-1) ln z - ln u'
-        partner = off; off += h * 4;                                           // [H]
         acc = off;     off += (size_t)walkers * 4;                             // [W] accepted proposals
         total = (off + 15) & ~(size_t)15;
     }
@@ -155,50 +142,60 @@ __device__ __forceinline__ void chi_tiles(const double *sC, int nt, int lane, co
     }
 }
 
-// Named barriers: a waiting warp is parked by the hardware and issues nothing.
-__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// Bank conflicts of one 64-bit access of a half-warp to the own rows: 4 rows (consecutive g), 4 consecutive
+// components each, the rows `row_step` rows of L doubles apart.  Returns the worst number of rows sharing a bank.
+__host__ __device__ constexpr int own_row_conflicts(int n_l, int row_step) {
+    int worst = 0;
+    for (int bank = 0; bank < 32; ++bank) {
+        int hits = 0;
+        for (int j = 0; j < 4; ++j) {
+            const int start = (2 * n_l * row_step * j) % 32;
+            if ((bank - start + 32) % 32 < 8) ++hits;
+        }
+        worst = hits > worst ? hits : worst;
+    }
+    return worst;
+}
 
-// blockDim = 32 (n_walker_warps + n_math_warps); warps [0, n_walker_warps) are walker warps, one per
-// group of 32 walkers of a half; math warp m computes item m (8 WT walkers) of every half-step.
-template <int L, int WT, bool PROF>               // WT: tiles of 8 walkers per math item (4: a whole group)
-__global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_mma_kernel(const EnsembleArgs args) {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// blockDim = 32 x items of a half (8 WT walkers each); warp = item.
+template <int L, int WT, bool PROF>               // WT: tiles of 8 walkers per item
+__global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const EnsembleArgs args) {
     constexpr int Q = L / 4, R = L % 4, RR = R > 0 ? R : 1;
-    constexpr int IW = 8 * WT;                    // walkers of a math item
-    constexpr int IPG = GW / IW;                  // math items per group
+    constexpr int IW = 8 * WT;                    // walkers of an item
     constexpr int TS = 8 * (L + 1);               // doubles per angle tile of the constants
     constexpr int NLE = (WT * R + 3) / 4;         // leading elements (l < R) a lane proposes; the quad shares them
     constexpr int NLS = NLE > 0 ? NLE : 1;
+    // Which walker of the item is row g of tile k: 8 k + g, or WT g + k where that spreads a half-warp's accesses to
+    // its own rows (operand fetch, update of accepted rows) over more banks (L = 9: rows 4 apart are 8 banks apart).
+    constexpr bool KMAJOR = own_row_conflicts(L, WT) < own_row_conflicts(L, 1);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;                 // constants of a unit have landed
+    __shared__ __align__(8) uint64_t store_bar;            // the bulk store of a kept step has read the state
 
     const int tid = threadIdx.x;
     const int T = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, item = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3, quad = lane & ~3;
     const int W = args.walkers;
     const int H = W >> 1;
     const int NT = args.n_tiles;
-    const int n_items = (H + IW - 1) / IW;
-    const int n_ww = args.groups;                 // walker warps = groups of a half (the launch sets it)
-    const int NWT = 32 * n_ww;                    // walker threads
-    const bool walker_warp = warp < n_ww;
 
     const EnsembleMmaSmem lay(W, L, NT);
     const double *sC = reinterpret_cast<const double *>(smem_raw + lay.consts);
     double *sPos = reinterpret_cast<double *>(smem_raw + lay.pos);
-    double *sQ = reinterpret_cast<double *>(smem_raw + lay.q);
     double *sLnp = reinterpret_cast<double *>(smem_raw + lay.lnp);
-    double *sChi = reinterpret_cast<double *>(smem_raw + lay.chi);
-    double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
     double *sLo = reinterpret_cast<double *>(smem_raw + lay.bounds);
     double *sHi = sLo + L;
-    float *sFast = reinterpret_cast<float *>(smem_raw + lay.fast);
-    int *sPartner = reinterpret_cast<int *>(smem_raw + lay.partner);
     unsigned int *sAcc = reinterpret_cast<unsigned int *>(smem_raw + lay.acc);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
+        mbar_init(&store_bar, 1);
         fence_mbar_init();
     }
     if (tid < L) { sLo[tid] = args.lo[tid]; sHi[tid] = args.hi[tid]; }
@@ -209,11 +206,29 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
     const double dim_m1 = (double)(L - 1);
     const float dim_m1f = (float)(L - 1);
 
-    auto items_of = [&](int g) { return min(IPG, n_items - g * IPG); };
+    // my walker of tile k (index within the half); rows beyond the half repeat the last walker and are never accepted
+    auto walker_of = [&](int k) { return item * IW + (KMAJOR ? WT * g + k : 8 * k + g); };
+    int wi[WT];
+#pragma unroll
+    for (int k = 0; k < WT; ++k) wi[k] = min(walker_of(k), H - 1);
+    // the walker I decide for: walker g of tile tig
+    const int dw = min(walker_of(tig & (WT - 1)), H - 1);
+    const bool decides = tig < WT && walker_of(tig) < H;
+    // leading elements (l < R) of the quad's WT walkers are shared out over its 4 lanes: slot n of lane tig is
+    // element j = tig + 4 n of the list (tile j / R, component j % R)
+    int lk[NLS], ll[NLS], lw[NLS];
+#pragma unroll
+    for (int n = 0; n < NLE; ++n) {
+        const int j = min(tig + 4 * n, WT * RR - 1);
+        lk[n] = j / RR;
+        ll[n] = j % RR;
+        lw[n] = min(walker_of(lk[n]), H - 1);
+    }
 
     bool saw_nan = false;
     uint32_t unit_phase = 0;                               // parity of mbar
-    bool store_pending = false;                            // a bulk store of a kept step may still be reading the state
+    uint32_t stores_issued = 0, stores_seen = 0;           // bulk stores of kept steps (store_bar: one phase each)
+    bool owe_arrival = false;                              // thread 0: a bulk store is queued and store_bar not yet told
     const bool keeping = args.chain != nullptr;
 
     const long long n_units = (long long)args.n_chunks * args.bins;
@@ -253,247 +268,223 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
         mbar_wait(&mbar, unit_phase);
         unit_phase ^= 1u;
 
+        // ---- what a half-step's proposals need and the half-step before does not change
+        // The Philox draw of the walker I decide for, of the half updated in half-step t, is counter based: it does
+        // not depend on positions.  emcee draws per half: u -> z, the partner index, then u'.
+        double pz[WT], pxa[WT][Q], pzl[NLS], pxl[NLS];     // stretch factors, own components
+        int pca[WT][Q], pcl[NLS];                          // index of the partner's components
+        float fast = 0.f;                                  // decision lane: (L-1) ln z - ln u' in single precision
+        // The Philox draw of the walker I decide for, of the half updated in half-step t (counter based: it
+        // does not depend on positions).  emcee draws per half: u -> z, the partner index, then u'.
+        double zd_next = 0.0;                              // my walker's draw of the coming half-step: stretch factor,
+        int part_next = 0;                                 // L x its partner's row,
+        float fast_next = 0.f;                             // (L-1) ln z - ln u'
+        auto draw = [&](uint32_t t) {
+            const int s_base = (t & 1u) ? H : 0, c_base = (t & 1u) ? 0 : H;
+            const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + dw), bin_id, t, 0u}, seed0, seed1);
+            const double u = uniform53(r.x, r.y);
+            // numpy arithmetic is one rounding per operation: no FMA contraction here
+            const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);
+            const double z2 = __dmul_rn(zr, zr);
+            zd_next = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;                      // ((a-1) u + 1)^2 / a
+            const double ua = uniform43(r.w, r.x, r.y);
+            // single-precision estimate of (L-1) ln z - ln u'; decides all but near-ties
+            fast_next = dim_m1f * __logf((float)zd_next) - __logf((float)ua);
+            part_next = (c_base + (int)__umulhi(r.z, (uint32_t)H)) * L;
+        };
+        // hand the draws round the quad (lane (g, k) decided for walker g of tile k) and fetch the own components
+        auto fetch = [&](uint32_t t) {
+            const double *xhalf = sPos + ((t & 1u) ? H : 0) * L;
+#pragma unroll
+            for (int k = 0; k < WT; ++k) {
+                pz[k] = __shfl_sync(0xffffffffu, zd_next, quad | k);
+                const int part = __shfl_sync(0xffffffffu, part_next, quad | k);
+#pragma unroll
+                for (int ks = 0; ks < Q; ++ks) {
+                    pca[k][ks] = part + R + 4 * ks + tig;
+                    pxa[k][ks] = xhalf[wi[k] * L + R + 4 * ks + tig];
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < NLE; ++n) {
+                pzl[n] = __shfl_sync(0xffffffffu, zd_next, quad | lk[n]);
+                pcl[n] = __shfl_sync(0xffffffffu, part_next, quad | lk[n]) + ll[n];
+                pxl[n] = xhalf[lw[n] * L + ll[n]];
+            }
+            fast = fast_next;
+        };
+        // Two warps share a scheduler (items i and i + 4): the first draws (integer work) before its chi^2 loop, the
+        // second after, so that one's Philox rounds issue under the other's DMMA stream.
+        const bool draws_early = item < 4;
+        __syncthreads();                                   // the state is there
+        draw(t_begin);
+        fetch(t_begin);
+
         // debug timeline (mdaEnsembleProfile): clock stamps of one half-step, per warp
         const uint32_t t_prof = (PROF && args.prof != nullptr && chunk == 0) ? t_begin + min(81u, 2u * (uint32_t)steps_here - 1u) : 0xffffffffu;
 #define MDA_STAMP(k) if (PROF && stamp) stamp[k] = clock64();
 #define MDA_STAMP_AFTER(k, value) if (PROF && stamp && (value) != 123.456) stamp[k] = clock64();   // once `value` has arrived
 
-        if (walker_warp) {
-            // The Philox draw of walker i of the half updated in half-step t (counter based: it does not
-            // depend on positions).  emcee draws per half: u -> z, the partner index, then u'.
-            auto draw = [&](uint32_t t, int i) {
-                const int s_base = (t & 1u) ? H : 0, c_base = (t & 1u) ? 0 : H;
-                const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + i), bin_id, t, 0u}, seed0, seed1);
-                const double u = uniform53(r.x, r.y);
-                // numpy arithmetic is one rounding per operation: no FMA contraction here
-                const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);
-                const double z2 = __dmul_rn(zr, zr);
-                const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;              // ((a-1) u + 1)^2 / a
-                const double ua = uniform43(r.w, r.x, r.y);
-                sZ[i] = z;
-                // single-precision estimate of (L-1) ln z - ln u'; decides all but near-ties
-                sFast[(t & 1u) * H + i] = dim_m1f * __logf((float)z) - __logf((float)ua);
-                sPartner[i] = c_base + (int)__umulhi(r.z, (uint32_t)H);
-            };
-            const int my_i = min(warp * GW + lane, H - 1);     // my walker of my group
-            const int live_w = min(GW, H - warp * GW);
-            draw(t_begin, my_i);
-            __syncthreads();                                   // state and first draw are there
-
-            for (uint32_t t = t_begin; t < t_end; ++t) {
-                const uint32_t half = t & 1u;
-                const int s_base = half ? H : 0;              // the half being updated; partners come from the other one
-                long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
-                MDA_STAMP(0)
-                // ---- the draw of the next half-step, while the math warps propose and evaluate this one
-                if (t + 1 < t_end) {
-                    draw(t + 1, my_i);
-                    named_arrive(kDrawnBarrier, T);
-                }
-                MDA_STAMP(2)
-                if (store_pending) {                       // the chain store must have read the rows before they change
-                    if (tid == 0) bulk_wait_read_all();
-                    named_sync(kJoinBarrier, NWT);
-                    store_pending = false;
-                }
-                // ---- accept / reject my walker
-                const int gw = s_base + my_i;
-                const double oldlnp = sLnp[gw];
-                const float fast = sFast[half * H + my_i];
-                named_sync(kDoneBarrier + warp, 32 * (1 + items_of(warp)));
-                // outside the box the math warps report chi^2 = +inf: log-posterior -inf (mda.py:1576), never accepted
-                const double newlnp = sChi[my_i] * -0.5;       // C/ChiSquare.c:212
-                MDA_STAMP_AFTER(3, newlnp)
-                saw_nan = saw_nan || (newlnp != newlnp);
-                const double est = __dsub_rn(newlnp, oldlnp) + (double)fast;
-                bool accept;
-                if (fabs(est) > 1e-4) {
-                    accept = est > 0.0;                // far from a tie: the float logs (error < 2e-5) cannot change the sign
-                } else {                               // emcee's test in full precision (rare: redo the draw)
-                    const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
-                    const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
-                    const double z2 = __dmul_rn(zr, zr);
-                    const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;
-                    const double zlog = __dmul_rn(dim_m1, log(z));
-                    accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(uniform43(r.w, r.x, r.y));
-                }
-                accept = accept && lane < live_w;
-                if (accept) {                          // my row: proposal -> state (rows are 8 L bytes apart: no bank conflicts)
-                    double *nrow = sPos + gw * L;
-                    const double *qrow = sQ + my_i * L;
-                    double qv[L];
+        for (uint32_t t = t_begin; t < t_end; ++t) {
+            const uint32_t half = t & 1u;
+            const int s_base = half ? H : 0;              // the half being updated; partners come from the other one
+            long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + item) * 8 : nullptr;
+            MDA_STAMP(0)
+            // ---- proposals q = c - z (c - x) of my elements: gather the partners' components, 3 fp64 operations each
+            double A[WT][Q], lead[WT][RR], myl[NLS];
+            {
+                double ca[WT][Q], cl[NLS];
 #pragma unroll
-                    for (int l = 0; l < L; ++l) qv[l] = qrow[l];
+                for (int k = 0; k < WT; ++k)
 #pragma unroll
-                    for (int l = 0; l < L; ++l) nrow[l] = qv[l];
-                    sLnp[gw] = newlnp;
-                    sAcc[gw] += 1u;
-                }
-                MDA_STAMP(4)
-                const bool kept_step = half && until_keep == 1 && keeping && slot < args.keep_cap;
-                if (kept_step) fence_proxy_async_smem();   // my rows before the bulk store reads them
-                __syncthreads();                           // the half is complete
-                if (half && --until_keep == 0) {           // a full step is complete and kept: one bulk store of the whole state
-                    until_keep = args.thin;
-                    if (kept_step) {
-                        if (tid == 0) {
-                            bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
-                            bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
-                            bulk_commit();
-                        }
-                        store_pending = true;
-                    }
-                    ++slot;
-                }
+                    for (int ks = 0; ks < Q; ++ks) ca[k][ks] = sPos[pca[k][ks]];
+#pragma unroll
+                for (int n = 0; n < NLE; ++n) cl[n] = sPos[pcl[n]];
+#pragma unroll
+                for (int k = 0; k < WT; ++k)
+#pragma unroll
+                    for (int ks = 0; ks < Q; ++ks)
+                        A[k][ks] = __dsub_rn(ca[k][ks], __dmul_rn(pz[k], __dsub_rn(ca[k][ks], pxa[k][ks])));
+#pragma unroll
+                for (int n = 0; n < NLE; ++n) myl[n] = __dsub_rn(cl[n], __dmul_rn(pzl[n], __dsub_rn(cl[n], pxl[n])));
             }
-            if (store_pending) {                           // the last step of the unit was kept: the hand-back waits for its store
-                if (tid == 0) bulk_wait_read_all();
-                store_pending = false;
-            }
-        } else {
-            // ---- my item (WT tiles of 8 walkers) of every half-step: propose, box prior, chi^2 against every angle tile
-            const int g = lane >> 2, tig = lane & 3;
-            const int item = warp - n_ww;
-            const int grp = item / IPG;
-            const int n_done = 32 * (1 + items_of(grp));
-            int wi[WT];                                        // my walker of tile k (index within the half)
 #pragma unroll
-            for (int k = 0; k < WT; ++k) wi[k] = min(item * IW + 8 * k + g, H - 1);
-            // leading elements (l < R) of the quad's WT walkers are shared out over its 4 lanes: slot n of lane tig is
-            // element j = tig + 4 n of the list (tile j / R, component j % R)
-            int lw[NLS], ll[NLS];
+            for (int k = 0; k < WT; ++k)
 #pragma unroll
-            for (int n = 0; n < NLE; ++n) {
-                const int j = min(tig + 4 * n, WT * RR - 1);
-                lw[n] = min(item * IW + 8 * (j / RR) + g, H - 1);
-                ll[n] = j % RR;
+                for (int l = 0; l < R; ++l) {
+                    const int j = k * R + l;               // compile-time: lane j % 4 of the quad holds it in slot j / 4
+                    lead[k][l] = __shfl_sync(0xffffffffu, myl[j / 4], quad | (j & 3));
+                }
+            MDA_STAMP_AFTER(1, A[WT - 1][Q - 1])
+            const int gw = s_base + dw;
+            const double oldlnp = sLnp[gw];                // only my own decision below changes it
+            if (draws_early && t + 1 < t_end) draw(t + 1);
+            if (tid == 0 && owe_arrival) {                 // the chain store queued after the last barrier has read the state by now
+                bulk_wait_read_all();
+                mbar_arrive(&store_bar);
+                owe_arrival = false;
             }
-            // what the proposals of half-step t need and half-step t - 1 does not change: stretch factors, own
-            // components, index of the partner's components
-            double pz[WT], pxa[WT][Q], pzl[NLS], pxl[NLS];
-            int pca[WT][Q], pcl[NLS];
-            auto prefetch = [&](uint32_t t) {
-                const double *xhalf = sPos + ((t & 1u) ? H : 0) * L;
+            // box prior (mda.py:1575) on these registers: any component below lo or above hi (a NaN compares
+            // false, as in the reference).  Lane (g, k) will decide for walker g of tile k.
+            bool outside;
+            {
+                uint32_t out_of[WT];
 #pragma unroll
                 for (int k = 0; k < WT; ++k) {
-                    pz[k] = sZ[wi[k]];
-                    const int part = sPartner[wi[k]] * L;
+                    bool o = false;
 #pragma unroll
-                    for (int ks = 0; ks < Q; ++ks) {
-                        pca[k][ks] = part + R + 4 * ks + tig;
-                        pxa[k][ks] = xhalf[wi[k] * L + R + 4 * ks + tig];
-                    }
+                    for (int ks = 0; ks < Q; ++ks) o = o | (A[k][ks] < sLo[R + 4 * ks + tig]) | (A[k][ks] > sHi[R + 4 * ks + tig]);
+#pragma unroll
+                    for (int l = 0; l < R; ++l) o = o | (lead[k][l] < sLo[l]) | (lead[k][l] > sHi[l]);
+                    out_of[k] = __ballot_sync(0xffffffffu, o);   // bits 4 g .. 4 g + 3: walker g of tile k
                 }
+                uint32_t mine = out_of[0];
 #pragma unroll
-                for (int n = 0; n < NLE; ++n) {
-                    pzl[n] = sZ[lw[n]];
-                    pcl[n] = sPartner[lw[n]] * L + ll[n];
-                    pxl[n] = xhalf[lw[n] * L + ll[n]];
-                }
-            };
-            __syncthreads();                                   // state and first draw are there
-            prefetch(t_begin);
-
-            for (uint32_t t = t_begin; t < t_end; ++t) {
-                long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;
-                MDA_STAMP(0)
-                // ---- proposals q = c - z (c - x) of my elements: gather the partners' components, 3 fp64 operations each
-                double A[WT][Q], lead[WT][RR], myl[NLS];
-                {
-                    double ca[WT][Q], cl[NLS];
+                for (int k = 1; k < WT; ++k) mine = (tig & (WT - 1)) == k ? out_of[k] : mine;
+                outside = ((mine >> (4 * g)) & 0xfu) != 0u;
+            }
+            double chi0[WT], chi1[WT];
 #pragma unroll
-                    for (int k = 0; k < WT; ++k)
+            for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
+            if (NT == 8) chi_tiles<L, WT, 8>(sC, 8, lane, A, lead, chi0, chi1);
+            else chi_tiles<L, WT, 0>(sC, NT, lane, A, lead, chi0, chi1);
+            // quad sums by a transposing butterfly: lane tig ends up with the sum of tile tig % WT
+            double sum;
+            if (WT == 4) {
+                double sv[4];
 #pragma unroll
-                        for (int ks = 0; ks < Q; ++ks) ca[k][ks] = sPos[pca[k][ks]];
-#pragma unroll
-                    for (int n = 0; n < NLE; ++n) cl[n] = sPos[pcl[n]];
-#pragma unroll
-                    for (int k = 0; k < WT; ++k)
-#pragma unroll
-                        for (int ks = 0; ks < Q; ++ks)
-                            A[k][ks] = __dsub_rn(ca[k][ks], __dmul_rn(pz[k], __dsub_rn(ca[k][ks], pxa[k][ks])));
-#pragma unroll
-                    for (int n = 0; n < NLE; ++n) myl[n] = __dsub_rn(cl[n], __dmul_rn(pzl[n], __dsub_rn(cl[n], pxl[n])));
-                }
-                // the rows the walker warps copy on acceptance
+                for (int k = 0; k < 4; ++k) sv[k] = chi0[k & (WT - 1)] + chi1[k & (WT - 1)];
+                const bool b0 = (tig & 1) != 0, b1 = (tig & 2) != 0;
+                const double a01 = (b0 ? sv[1] : sv[0]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[0] : sv[1], 1);   // tile tig & 1
+                const double a23 = (b0 ? sv[3] : sv[2]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[2] : sv[3], 1);   // tile 2 + (tig & 1)
+                sum = (b1 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b1 ? a01 : a23, 2);
+            } else if (WT == 2) {
+                const double s0 = chi0[0] + chi1[0], s1 = chi0[WT - 1] + chi1[WT - 1];
+                const bool b0 = (tig & 1) != 0;
+                sum = (b0 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b0 ? s0 : s1, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            } else {
+                sum = chi0[0] + chi1[0];
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            }
+            MDA_STAMP_AFTER(2, sum)
+            // ---- accept / reject the walker I decide for
+            // outside the box the log-posterior is -inf (mda.py:1576): never accepted
+            const double newlnp = outside ? -CUDART_INF : sum * -0.5;    // C/ChiSquare.c:212
+            const double est = __dsub_rn(newlnp, oldlnp) + (double)fast;
+            bool accept;
+            if (fabs(est) > 1e-4 || !decides) {
+                accept = est > 0.0;                    // far from a tie: the float logs (error < 2e-5) cannot change the sign
+            } else {                                   // emcee's test in full precision (rare: redo the draw)
+                const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
+                const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
+                const double z2 = __dmul_rn(zr, zr);
+                const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;
+                const double zlog = __dmul_rn(dim_m1, log(z));
+                accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(uniform43(r.w, r.x, r.y));
+            }
+            accept = accept && decides;
+            saw_nan = saw_nan || (decides && newlnp != newlnp);
+            const uint32_t moved = __ballot_sync(0xffffffffu, accept);       // bit 4 g + k: walker g of tile k moves
+            if (stores_seen != stores_issued) {            // the chain store must have read the rows before they change
+                mbar_wait(&store_bar, (stores_issued - 1u) & 1u);
+                stores_seen = stores_issued;
+            }
+            if (accept) {
+                sLnp[gw] = newlnp;
+                sAcc[gw] += 1u;
+            }
+            // every lane writes the components it holds of the walkers that move
+            {
+                double *nhalf = sPos + s_base * L;
 #pragma unroll
                 for (int k = 0; k < WT; ++k)
+                    if ((moved >> (4 * g + k)) & 1u) {
 #pragma unroll
-                    for (int ks = 0; ks < Q; ++ks) sQ[wi[k] * L + R + 4 * ks + tig] = A[k][ks];
+                        for (int ks = 0; ks < Q; ++ks) nhalf[wi[k] * L + R + 4 * ks + tig] = A[k][ks];
+                    }
 #pragma unroll
                 for (int n = 0; n < NLE; ++n)
-                    if (tig + 4 * n < WT * R) sQ[lw[n] * L + ll[n]] = myl[n];
-#pragma unroll
-                for (int k = 0; k < WT; ++k)
-#pragma unroll
-                    for (int l = 0; l < R; ++l) {
-                        constexpr int dummy = 0;
-                        (void)dummy;
-                        const int j = k * R + l;               // compile-time: lane j % 4 of the quad holds it in slot j / 4
-                        lead[k][l] = __shfl_sync(0xffffffffu, myl[j / 4], (lane & ~3) | (j & 3));
+                    if (tig + 4 * n < WT * R && ((moved >> (4 * g + lk[n])) & 1u)) nhalf[lw[n] * L + ll[n]] = myl[n];
+            }
+            MDA_STAMP(3)
+            // ---- the draw of the next half-step and what its proposals can fetch already (their own rows do not change now)
+            if (t + 1 < t_end) {
+                if (!draws_early) draw(t + 1);
+                fetch(t + 1);
+            }
+            MDA_STAMP_AFTER(4, pz[0])
+            const bool kept_step = half && until_keep == 1 && keeping && slot < args.keep_cap;
+            if (kept_step) fence_proxy_async_smem();       // my rows before the bulk store reads them
+            __syncthreads();                               // the half is complete
+            if (half && --until_keep == 0) {               // a full step is complete and kept: one bulk store of the whole state
+                until_keep = args.thin;
+                if (kept_step) {
+                    if (tid == 0) {
+                        bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
+                        bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
+                        bulk_commit();
+                        owe_arrival = true;
                     }
-                MDA_STAMP_AFTER(1, A[WT - 1][Q - 1])
-                // box prior (mda.py:1575) on these registers: any component below lo or above hi (a NaN compares
-                // false, as in the reference).  Lane tig will report the walker g of tile tig % WT.
-                bool outside;
-                {
-                    uint32_t out_of[WT];
-#pragma unroll
-                    for (int k = 0; k < WT; ++k) {
-                        bool o = false;
-#pragma unroll
-                        for (int ks = 0; ks < Q; ++ks) o = o | (A[k][ks] < sLo[R + 4 * ks + tig]) | (A[k][ks] > sHi[R + 4 * ks + tig]);
-#pragma unroll
-                        for (int l = 0; l < R; ++l) o = o | (lead[k][l] < sLo[l]) | (lead[k][l] > sHi[l]);
-                        out_of[k] = __ballot_sync(0xffffffffu, o);   // bits 4 g .. 4 g + 3: walker g of tile k
-                    }
-                    uint32_t mine = out_of[0];
-#pragma unroll
-                    for (int k = 1; k < WT; ++k) mine = (tig & (WT - 1)) == k ? out_of[k] : mine;
-                    outside = ((mine >> (4 * g)) & 0xfu) != 0u;
+                    ++stores_issued;
                 }
-                double chi0[WT], chi1[WT];
-#pragma unroll
-                for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
-                if (NT == 8) chi_tiles<L, WT, 8>(sC, 8, lane, A, lead, chi0, chi1);
-                else chi_tiles<L, WT, 0>(sC, NT, lane, A, lead, chi0, chi1);
-                // quad sums by a transposing butterfly: lane tig ends up with the sum of tile tig % WT
-                double sum;
-                if (WT == 4) {
-                    double sv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) sv[k] = chi0[k & (WT - 1)] + chi1[k & (WT - 1)];
-                    const bool b0 = (tig & 1) != 0, b1 = (tig & 2) != 0;
-                    const double a01 = (b0 ? sv[1] : sv[0]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[0] : sv[1], 1);   // tile tig & 1
-                    const double a23 = (b0 ? sv[3] : sv[2]) + __shfl_xor_sync(0xffffffffu, b0 ? sv[2] : sv[3], 1);   // tile 2 + (tig & 1)
-                    sum = (b1 ? a23 : a01) + __shfl_xor_sync(0xffffffffu, b1 ? a01 : a23, 2);
-                } else if (WT == 2) {
-                    const double s0 = chi0[0] + chi1[0], s1 = chi0[WT - 1] + chi1[WT - 1];
-                    const bool b0 = (tig & 1) != 0;
-                    sum = (b0 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b0 ? s0 : s1, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                } else {
-                    sum = chi0[0] + chi1[0];
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                }
-                if (outside) sum = CUDART_INF;
-                const int wk = item * IW + 8 * tig + g;
-                if (tig < WT && wk < H) sChi[wk] = sum;
-                named_arrive(kDoneBarrier + grp, n_done);
-                MDA_STAMP(3)
-                // ---- while the walker warps decide: what the next half-step's proposals can fetch already
-                if (t + 1 < t_end) {
-                    named_sync(kDrawnBarrier, T);
-                    prefetch(t + 1);
-                }
-                __syncthreads();                           // the half is complete
+                ++slot;
             }
         }
 #undef MDA_STAMP
 #undef MDA_STAMP_AFTER
 
         // ---- hand the bin back: state to HBM/L2, then the progress word
+        if (tid == 0 && owe_arrival) {                     // the last step of the unit was kept: its store still reads the state
+            bulk_wait_read_all();
+            mbar_arrive(&store_bar);
+            owe_arrival = false;
+        }
+        if (stores_seen != stores_issued) {
+            mbar_wait(&store_bar, (stores_issued - 1u) & 1u);
+            stores_seen = stores_issued;
+        }
         __syncthreads();
         for (int i = tid; i < W * L; i += T) gPos[i] = sPos[i];
         for (int w = tid; w < W; w += T) {
@@ -554,18 +545,16 @@ bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int 
     if (n_l < kMinMmaL || n_l > kMaxRegL) return false;
     EnsembleShape s{};
     const int half = walkers / 2;
-    const int n_groups = (half + GW - 1) / GW;
-    if (n_groups > kWalkerWarps) return false;                               // one group per walker warp
     s.smem_bytes = EnsembleMmaSmem(walkers, n_l, n_tiles).total;
-    // tiles per math item: the fewest that give every item its own math warp
-    int wt = 8 * kMathWarps >= half ? 1 : (16 * kMathWarps >= half ? 2 : 4);
+    // tiles per item: the fewest that give every item its own warp
+    int wt = 8 * kMaxWarps >= half ? 1 : (16 * kMaxWarps >= half ? 2 : 4);
     if (force_wt == 1 || force_wt == 2 || force_wt == 4) wt = force_wt;
     const int n_items = (half + 8 * wt - 1) / (8 * wt);
-    if (n_items > kMathWarps) return false;                                  // one item per math warp
+    if (n_items > kMaxWarps) return false;                                   // one item per warp
     s.wpt = wt;
-    s.groups = n_groups;                                                     // walker warps
+    s.groups = n_items;
     s.stage = 1;
-    s.threads = 32 * (n_groups + n_items);
+    s.threads = 32 * n_items;
     s.global_state = false;
     s.mma = true;
     s.fits = s.smem_bytes + kStaticSmem <= smem_optin && (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8 < (1u << 20);
@@ -609,7 +598,6 @@ cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &s
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;
     EnsembleArgs a = args;
-    a.groups = shape.groups;                               // walker warps (the rest of the block are math warps)
     k<<<grid, shape.threads, shape.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }

@@ -86,7 +86,8 @@ struct EnsembleShape {
     size_t smem_bytes;
     bool fits;                 // the launch is possible (shared memory, numL <= kMaxRegL)
     bool global_state;         // positions / log-probabilities stay in HBM (ensemble too large for shared memory)
-    bool mma;                  // ensemble_mma_kernel (groups = walker warps, wpt = tiles of 8 walkers per math item)
+    bool mma;                  // a DMMA stepper (wpt = tiles of 8 walkers per item)
+    bool ws;                   // the warp-specialised one, ensemble_ws_kernel (groups = walker warps); else ensemble_mma_kernel
 };
 
 EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, int sm_count, size_t smem_optin,
@@ -105,6 +106,12 @@ bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int 
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin);
 int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count);   // co-resident CTAs on the device
 cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);
+// Warp-specialised DMMA variant (ensemble_ws_kernel.cu): same constants, same unit schedule, one CTA of 16 warps per SM.
+bool choose_ensemble_ws_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
+                              EnsembleShape *out);
+cudaError_t configure_ensemble_ws_kernels(size_t smem_optin);
+int ensemble_ws_capacity(int n_l, const EnsembleShape &shape, int sm_count);
+cudaError_t launch_ensemble_ws(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);
 
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
 // gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.
