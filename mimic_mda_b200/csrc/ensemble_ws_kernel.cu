@@ -9,34 +9,30 @@
 // emcee.EnsembleSampler.run_mcmc -> ln_post_prob per walker, mda.py:1128-1131, 1540-1578, as ONE
 // persistent launch).  A CTA owns an Ex bin (for a chunk of steps) and has two kinds of warps:
 //
-//   * math warps: chi^2 of one item of 8 WT walkers per half-step.  Lane (g, tig) = (lane / 4, lane % 4)
-//     loads, for walker g of a tile of 8, the proposal elements l = R + 4 ks + tig (ks < Q = L / 4) -- the
-//     A fragment of mma.m8n8k4 -- and the R = L % 4 leading ones; residuals of an 8-walker x 8-angle
-//     tile are c = d + sum_{l<R} q_l (-D_l) by DFMA, then Q DMMAs against B fragments of the NEGATED
-//     distributions staged fragment-major in shared memory; chi^2 is accumulated from the C fragment
-//     and reduced over the quad.  Every term of the reference's sum (C/ChiSquare.c:188-210) is
-//     evaluated exactly once, only the order of the fp64 additions differs (|error| ~ 1e-16
-//     relative, tested against the oracle).  The box prior (mda.py:1574-1576) is tested on the same
-//     registers: a walker outside gets chi^2 = +inf, i.e. log-posterior -inf.  Why DMMA: a DFMA with
-//     three distinct register operands is register-bandwidth bound at ~72 % of the fp64 pipe on
-//     sm_100a; DMMA.8x8x4 runs on the same pipe at its full rate with 1/8 of the issue slots
-//     (tools/ubench/dmma_ubench.cu).
-//   * walker warps.  Proposals q = c - z (c - x) are staged by ALL walker warps together over the
-//     flattened elements of the half, e = pass * (walker threads) + thread: own rows and proposals are
-//     contiguous runs, only the partner rows c are gathered.  Everything of a proposal that does not
-//     depend on the half being updated right now (its own row x, its stretch factor z, the address of
-//     its partner row) is fetched during the previous half-step, while the fp64 pipe is busy, so that
-//     the stretch between "the other half is complete" and "the math warps run" is one gather, 3 L
-//     fp64 operations and one store per thread.  Decisions stay with lane = walker of warp = group:
-//     Philox draw, accept / reject, in-place update, acceptance counters.
-//   * hand-offs are NAMED BARRIERS (bar.sync / bar.arrive), never polled: barrier 1 completes when the
-//     proposals are staged (walker warps arrive, math warps wait), barrier 2 + g when the chi^2 of group
-//     g is there (its math warps arrive, walker warp g waits), barrier 10 joins the walker warps at the
-//     end of a half-step (the stretch move needs the other half complete).  A bar.arrive costs ~150
-//     cycles (it waits for the thread's shared-memory stores), so there is one per warp and half-step.
-//     An mbarrier wait compiles to a try_wait / NANOSLEEP.SYNCS loop that wakes up every ~100 cycles:
-//     in the mbarrier version of this kernel 25 % of all executed instructions were such probes
-//     (profiles/r01_ncu_full_c4_ensemble_mma.csv), taken from the issue slots of the math warps.
+//   * math warps: one item of 8 WT walkers per half-step.  Lane (g, tig) = (lane / 4, lane % 4) holds, for
+//     walker g of each tile of 8, the proposal components l = R + 4 ks + tig (ks < Q = L / 4) -- the A fragment
+//     of mma.m8n8k4 -- and a share of the R = L % 4 leading ones.  It gathers the partners' components c and
+//     forms q = c - z (c - x) itself (numpy rounding, no FMA contraction) from operands x, z and partner
+//     addresses it fetched while the walker warps decided the half-step before, stages q for the walker
+//     warps' row update, tests the box prior (mda.py:1574-1576) on those registers (outside: chi^2 = +inf,
+//     i.e. log-posterior -inf); residuals of an 8-walker x 8-angle tile are c = d + sum_{l<R} q_l (-D_l) by
+//     DFMA, then Q DMMAs against B fragments of the NEGATED distributions staged fragment-major in shared
+//     memory; chi^2 is accumulated from the C fragment and reduced over the quad.  Every term of the
+//     reference's sum (C/ChiSquare.c:188-210) is evaluated exactly once, only the order of the fp64 additions
+//     differs (|error| ~ 1e-16 relative, tested against the oracle).  Why DMMA: a DFMA with three distinct
+//     register operands is register-bandwidth bound at ~72 % of the fp64 pipe on sm_100a; DMMA.8x8x4 runs on
+//     the same pipe at its full rate with 1/8 of the issue slots (tools/ubench/dmma_ubench.cu).
+//   * walker warps (lane = walker of warp = group of 32): the Philox draw of the NEXT half-step while the
+//     math warps work on this one, then accept / reject, in-place row update from the staged proposals,
+//     acceptance counters and the bulk store of kept steps.
+//   * hand-offs are NAMED BARRIERS (bar.sync / bar.arrive), never polled: barrier 1 completes when the draw of
+//     the next half-step is published (walker warps arrive, math warps wait), barrier 2 + g when the chi^2 of
+//     group g is there (its math warps arrive, walker warp g waits), barrier 10 joins the walker warps around
+//     a pending chain store, and ONE CTA barrier ends a half-step (the stretch move needs the other half
+//     complete).  A bar.arrive costs ~150 cycles (it waits for the thread's shared-memory stores), so there
+//     is one per warp and half-step.  An mbarrier wait compiles to a try_wait / NANOSLEEP.SYNCS loop that
+//     wakes up every ~100 cycles: in the mbarrier version of this kernel 25 % of all executed instructions
+//     were such probes (profiles/r01_ncu_full_c4_ensemble_mma.csv), taken from the math warps' issue slots.
 //   * CTAs walk a list of (step chunk, bin) units in chunk-major order, unit u on CTA u mod grid; a
 //     unit waits for the previous chunk of its bin through a release/acquire word per bin and hands
 //     the ensemble state over through HBM/L2.  With more bins than SMs (C4: 200 on 148) every SM
@@ -157,6 +153,21 @@ __device__ __forceinline__ void chi_tiles(const double *sC, int nt, int lane, co
 #pragma unroll
         for (int ks = 0; ks < Q; ++ks) Bf[ks] = Bf_n[ks];
     }
+}
+
+// Bank conflicts of one 64-bit access of a half-warp to the own rows: 4 rows (consecutive g), 4 consecutive
+// components each, the rows `row_step` rows of L doubles apart.  Returns the worst number of rows sharing a bank.
+__host__ __device__ constexpr int own_row_conflicts(int n_l, int row_step) {
+    int worst = 0;
+    for (int bank = 0; bank < 32; ++bank) {
+        int hits = 0;
+        for (int j = 0; j < 4; ++j) {
+            const int start = (2 * n_l * row_step * j) % 32;
+            if ((bank - start + 32) % 32 < 8) ++hits;
+        }
+        worst = hits > worst ? hits : worst;
+    }
+    return worst;
 }
 
 // Named barriers: a waiting warp is parked by the hardware and issues nothing.
@@ -360,16 +371,20 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
             const int item = warp - n_ww;
             const int grp = item / IPG;
             const int n_done = 32 * (1 + items_of(grp));
+            // Which walker of the item is row g of tile k: 8 k + g, or WT g + k where that spreads a half-warp's accesses
+            // to its own rows (operand prefetch, staged proposals) over more banks (L = 9: rows 4 apart are 8 banks apart).
+            constexpr bool KMAJOR = own_row_conflicts(L, WT) < own_row_conflicts(L, 1);
+            auto walker_of = [&](int k) { return item * IW + (KMAJOR ? WT * g + k : 8 * k + g); };
             int wi[WT];                                        // my walker of tile k (index within the half)
 #pragma unroll
-            for (int k = 0; k < WT; ++k) wi[k] = min(item * IW + 8 * k + g, H - 1);
+            for (int k = 0; k < WT; ++k) wi[k] = min(walker_of(k), H - 1);
             // leading elements (l < R) of the quad's WT walkers are shared out over its 4 lanes: slot n of lane tig is
             // element j = tig + 4 n of the list (tile j / R, component j % R)
             int lw[NLS], ll[NLS];
 #pragma unroll
             for (int n = 0; n < NLE; ++n) {
                 const int j = min(tig + 4 * n, WT * RR - 1);
-                lw[n] = min(item * IW + 8 * (j / RR) + g, H - 1);
+                lw[n] = min(walker_of(j / RR), H - 1);
                 ll[n] = j % RR;
             }
             // what the proposals of half-step t need and half-step t - 1 does not change: stretch factors, own
@@ -482,7 +497,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                 }
                 if (outside) sum = CUDART_INF;
-                const int wk = item * IW + 8 * tig + g;
+                const int wk = walker_of(tig);
                 if (tig < WT && wk < H) sChi[wk] = sum;
                 named_arrive(kDoneBarrier + grp, n_done);
                 MDA_STAMP(3)
