@@ -428,9 +428,9 @@ EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     if (!want_dfma) {
         const bool prefer_mma = want_mma || (!want_ws && s->bins >= 2 * g_rt.sm_count);
         const int wt = env_int("MDA_ENS_WT", 0);
-        if (prefer_mma && choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, &shape)) return shape;
+        if (prefer_mma && choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, env_int("MDA_ENS_DRAWW", 0), &shape)) return shape;
         if (choose_ensemble_ws_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, &shape)) return shape;
-        if (choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, &shape)) return shape;
+        if (choose_ensemble_mma_shape(s->bins, walkers, s->n_l, s->n_tiles, g_rt.sm_count, g_rt.smem_optin, wt, env_int("MDA_ENS_DRAWW", 0), &shape)) return shape;
     }
     return choose_ensemble_shape(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
 }
@@ -1039,9 +1039,10 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
                      plan.n_chunks, plan.chunk_steps);
         else
             snprintf(text, (size_t)textLen,
-                     "ensemble_mma_kernel<L=%d,WT=%d>: fp64 DMMA.8x8x4 chi^2, %d warps per CTA (one item of %d walkers each, one barrier per half-step), %zu B shared memory; "
+                     "ensemble_mma_kernel<L=%d,WT=%d,%s>: fp64 DMMA.8x8x4 chi^2, %d warps per CTA (one item of %d walkers each, one barrier per half-step), %zu B shared memory; "
                      "%d CTAs walk %d bins x %d chunks of %d steps",
-                     s->n_l, shape.wpt, shape.threads / 32, 8 * shape.wpt, shape.smem_bytes, plan.grid, s->bins, plan.n_chunks, plan.chunk_steps);
+                     s->n_l, shape.wpt, shape.stage == 1 ? "draw warps" : "two CTAs per SM", shape.groups, 8 * shape.wpt, shape.smem_bytes, plan.grid, s->bins,
+                     plan.n_chunks, plan.chunk_steps);
     } else {
         snprintf(text, (size_t)textLen, "ensemble_kernel<L=%d,WPT=%d,%s>: DFMA chi^2, %d threads x %d angle groups per CTA, %zu B shared memory; one CTA per bin (%d)",
                  s->n_l, shape.wpt, shape.global_state ? "state in HBM" : "state in shared memory", shape.threads, shape.groups, shape.smem_bytes, s->bins);

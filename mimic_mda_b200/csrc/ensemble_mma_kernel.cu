@@ -47,17 +47,22 @@ namespace {
 
 constexpr int kStatusNaN = 1;
 constexpr int kMaxWarps = 8;           // items (warps) per CTA
+constexpr int kDrawnBarrier = 1;       // named barrier: the draw of the next half-step is published (draw warps arrive, the others wait)
 constexpr size_t kStaticSmem = 64;     // the mbarriers (static __shared__), rounded up
 
 struct EnsembleMmaSmem {
-    size_t consts, pos, lnp, bounds, acc, total;
+    size_t consts, pos, lnp, bounds, z, acc, partner, fast, total;
     __host__ __device__ EnsembleMmaSmem(int walkers, int n_l, int n_tiles) {
+        const size_t h = (size_t)walkers / 2;
         size_t off = 0;
         consts = off;  off += (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8;     // [tiles][8 (1+L)] fragment-major
         pos = off;     off += (size_t)walkers * (size_t)n_l * 8;               // [W][L] dense, updated in place; bulk-stored as is
         lnp = off;     off += (size_t)walkers * 8;                             // [W] (16-byte aligned: W is even)
         bounds = off;  off += 2 * (size_t)n_l * 8;                             // [2][L] box prior: lo, hi
+        z = off;       off += h * 8;                                           // [H] draw warps: stretch factor of the next half-step
         acc = off;     off += (size_t)walkers * 4;                             // [W] accepted proposals
+        partner = off; off += h * 4;                                           // [H] draw warps: L x partner row
+        fast = off;    off += h * 4;                                           // [H] draw warps: float (L-1) ln z - ln u'
         total = (off + 15) & ~(size_t)15;
     }
 };
@@ -157,13 +162,19 @@ __host__ __device__ constexpr int own_row_conflicts(int n_l, int row_step) {
     return worst;
 }
 
+// Named barriers: a waiting warp is parked by the hardware and issues nothing.
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// blockDim = 32 x items of a half (8 WT walkers each); warp = item.
-template <int L, int WT, bool PROF>               // WT: tiles of 8 walkers per item
-__global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const EnsembleArgs args) {
+// blockDim = 32 x items of a half (8 WT walkers each); warp = item.  DW: as many DRAW WARPS again (warps items .. 2 items - 1),
+// which make the Philox draws of the next half-step (lane = walker of item warp - items) and publish them in shared
+// memory while the others propose and evaluate -- the schedule for one bin per SM, where nothing else would hide them.
+template <int L, int WT, bool DW, bool PROF>      // WT: tiles of 8 walkers per item
+__global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ensemble_mma_kernel(const EnsembleArgs args) {
     constexpr int Q = L / 4, R = L % 4, RR = R > 0 ? R : 1;
     constexpr int IW = 8 * WT;                    // walkers of an item
     constexpr int TS = 8 * (L + 1);               // doubles per angle tile of the constants
@@ -180,6 +191,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
     const int tid = threadIdx.x;
     const int T = blockDim.x;
     const int lane = tid & 31, item = tid >> 5;
+    const int n_items = DW ? (T >> 6) : (T >> 5);
+    const bool draw_warp = DW && item >= n_items;
     const int g = lane >> 2, tig = lane & 3, quad = lane & ~3;
     const int W = args.walkers;
     const int H = W >> 1;
@@ -192,6 +205,9 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
     double *sLo = reinterpret_cast<double *>(smem_raw + lay.bounds);
     double *sHi = sLo + L;
     unsigned int *sAcc = reinterpret_cast<unsigned int *>(smem_raw + lay.acc);
+    double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
+    int *sPartner = reinterpret_cast<int *>(smem_raw + lay.partner);
+    float *sFast = reinterpret_cast<float *>(smem_raw + lay.fast);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -228,7 +244,10 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
     bool saw_nan = false;
     uint32_t unit_phase = 0;                               // parity of mbar
     uint32_t stores_issued = 0, stores_seen = 0;           // bulk stores of kept steps (store_bar: one phase each)
-    bool owe_arrival = false;                              // thread 0: a bulk store is queued and store_bar not yet told
+    bool owe_arrival = false;                              // the issuer: a bulk store is queued and store_bar not yet told
+    // The thread that queues the chain stores and later waits until they have read the state: with draw warps one of
+    // theirs (waiting costs it nothing), else thread 0 (the SM's other CTA covers the wait).
+    const bool issuer = DW ? tid == 32 * n_items : tid == 0;
     const bool keeping = args.chain != nullptr;
 
     const long long n_units = (long long)args.n_chunks * args.bins;
@@ -264,10 +283,64 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
         long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
         const uint32_t t_begin = 2u * (uint32_t)step_first;
         const uint32_t t_end = t_begin + 2u * (uint32_t)steps_here;
+        // after the barrier that ends a half-step: a full step that is kept goes to the chain as one bulk store of the state
+        auto end_of_half_step = [&](uint32_t half) {
+            if (half && --until_keep == 0) {
+                until_keep = args.thin;
+                if (keeping && slot < args.keep_cap) {
+                    if (issuer) {
+                        bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
+                        bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
+                        bulk_commit();
+                        owe_arrival = true;
+                    }
+                    ++stores_issued;
+                }
+                ++slot;
+            }
+        };
+        auto settle_store = [&]() {                        // the queued chain store has read the state by now: tell the writers
+            if (issuer && owe_arrival) {
+                bulk_wait_read_all();
+                mbar_arrive(&store_bar);
+                owe_arrival = false;
+            }
+        };
 
         mbar_wait(&mbar, unit_phase);
         unit_phase ^= 1u;
 
+        if (draw_warp) {
+            // ---- draw warps: the Philox draw (counter based: it does not depend on positions) of every walker of the
+            // half updated in half-step t + 1, published while the other warps work on half-step t
+            const int wl = (item - n_items) * IW + lane;   // my walker (index within the half)
+            const bool live = lane < IW && wl < H;
+            auto publish = [&](uint32_t t) {
+                const int s_base = (t & 1u) ? H : 0, c_base = (t & 1u) ? 0 : H;
+                const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + min(wl, H - 1)), bin_id, t, 0u}, seed0, seed1);
+                const double u = uniform53(r.x, r.y);
+                const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);          // numpy: one rounding per operation
+                const double z2 = __dmul_rn(zr, zr);
+                const double zd = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;           // ((a-1) u + 1)^2 / a
+                const double ua = uniform43(r.w, r.x, r.y);
+                if (live) {
+                    sZ[wl] = zd;
+                    sFast[wl] = dim_m1f * __logf((float)zd) - __logf((float)ua);
+                    sPartner[wl] = (c_base + (int)__umulhi(r.z, (uint32_t)H)) * L;
+                }
+            };
+            publish(t_begin);
+            __syncthreads();                               // the state and the first draw are there
+            for (uint32_t t = t_begin; t < t_end; ++t) {
+                if (t + 1 < t_end) {
+                    publish(t + 1);
+                    named_arrive(kDrawnBarrier, T);
+                }
+                settle_store();
+                __syncthreads();                           // the half is complete
+                end_of_half_step(t & 1u);
+            }
+        } else {
         // ---- what a half-step's proposals need and the half-step before does not change
         // The Philox draw of the walker I decide for, of the half updated in half-step t, is counter based: it does
         // not depend on positions.  emcee draws per half: u -> z, the partner index, then u'.
@@ -297,8 +370,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
             const double *xhalf = sPos + ((t & 1u) ? H : 0) * L;
 #pragma unroll
             for (int k = 0; k < WT; ++k) {
-                pz[k] = __shfl_sync(0xffffffffu, zd_next, quad | k);
-                const int part = __shfl_sync(0xffffffffu, part_next, quad | k);
+                pz[k] = DW ? sZ[wi[k]] : __shfl_sync(0xffffffffu, zd_next, quad | k);
+                const int part = DW ? sPartner[wi[k]] : __shfl_sync(0xffffffffu, part_next, quad | k);
 #pragma unroll
                 for (int ks = 0; ks < Q; ++ks) {
                     pca[k][ks] = part + R + 4 * ks + tig;
@@ -307,17 +380,17 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
             }
 #pragma unroll
             for (int n = 0; n < NLE; ++n) {
-                pzl[n] = __shfl_sync(0xffffffffu, zd_next, quad | lk[n]);
-                pcl[n] = __shfl_sync(0xffffffffu, part_next, quad | lk[n]) + ll[n];
+                pzl[n] = DW ? sZ[lw[n]] : __shfl_sync(0xffffffffu, zd_next, quad | lk[n]);
+                pcl[n] = (DW ? sPartner[lw[n]] : __shfl_sync(0xffffffffu, part_next, quad | lk[n])) + ll[n];
                 pxl[n] = xhalf[lw[n] * L + ll[n]];
             }
-            fast = fast_next;
+            fast = DW ? sFast[dw] : fast_next;
         };
         // Two warps share a scheduler (items i and i + 4): the first draws (integer work) before its chi^2 loop, the
         // second after, so that one's Philox rounds issue under the other's DMMA stream.
         const bool draws_early = item < 4;
-        __syncthreads();                                   // the state is there
-        draw(t_begin);
+        __syncthreads();                                   // the state (and with draw warps the first draw) is there
+        if (!DW) draw(t_begin);
         fetch(t_begin);
 
         // debug timeline (mdaEnsembleProfile): clock stamps of one half-step, per warp
@@ -358,12 +431,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
             MDA_STAMP_AFTER(1, A[WT - 1][Q - 1])
             const int gw = s_base + dw;
             const double oldlnp = sLnp[gw];                // only my own decision below changes it
-            if (draws_early && t + 1 < t_end) draw(t + 1);
-            if (tid == 0 && owe_arrival) {                 // the chain store queued after the last barrier has read the state by now
-                bulk_wait_read_all();
-                mbar_arrive(&store_bar);
-                owe_arrival = false;
-            }
+            if (!DW && draws_early && t + 1 < t_end) draw(t + 1);
+            if (!DW) settle_store();
             // box prior (mda.py:1575) on these registers: any component below lo or above hi (a NaN compares
             // false, as in the reference).  Lane (g, k) will decide for walker g of tile k.
             bool outside;
@@ -409,10 +478,12 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             }
             MDA_STAMP_AFTER(2, sum)
+            const float fast_now = fast;
             // ---- accept / reject the walker I decide for
             // outside the box the log-posterior is -inf (mda.py:1576): never accepted
             const double newlnp = outside ? -CUDART_INF : sum * -0.5;    // C/ChiSquare.c:212
-            const double est = __dsub_rn(newlnp, oldlnp) + (double)fast;
+            const double est = __dsub_rn(newlnp, oldlnp) + (double)fast_now;
+            MDA_STAMP_AFTER(6, est)
             bool accept;
             if (fabs(est) > 1e-4 || !decides) {
                 accept = est > 0.0;                    // far from a tie: the float logs (error < 2e-5) cannot change the sign
@@ -427,6 +498,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
             accept = accept && decides;
             saw_nan = saw_nan || (decides && newlnp != newlnp);
             const uint32_t moved = __ballot_sync(0xffffffffu, accept);       // bit 4 g + k: walker g of tile k moves
+            MDA_STAMP_AFTER(7, (double)moved)
             if (stores_seen != stores_issued) {            // the chain store must have read the rows before they change
                 mbar_wait(&store_bar, (stores_issued - 1u) & 1u);
                 stores_seen = stores_issued;
@@ -449,38 +521,26 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
                     if (tig + 4 * n < WT * R && ((moved >> (4 * g + lk[n])) & 1u)) nhalf[lw[n] * L + ll[n]] = myl[n];
             }
             MDA_STAMP(3)
-            // ---- the draw of the next half-step and what its proposals can fetch already (their own rows do not change now)
+            // ---- the draw of the next half-step and what its proposals can fetch already (their own rows do not change now).
+            // After the decision, not before it: a warp issues in order, and the decision's few fp64 operations would
+            // queue behind these loads (measured: 590 instead of ~100 cycles from chi^2 to the accept bits).
             if (t + 1 < t_end) {
-                if (!draws_early) draw(t + 1);
+                if (DW) named_sync(kDrawnBarrier, T);
+                else if (!draws_early) draw(t + 1);
                 fetch(t + 1);
             }
             MDA_STAMP_AFTER(4, pz[0])
             const bool kept_step = half && until_keep == 1 && keeping && slot < args.keep_cap;
             if (kept_step) fence_proxy_async_smem();       // my rows before the bulk store reads them
             __syncthreads();                               // the half is complete
-            if (half && --until_keep == 0) {               // a full step is complete and kept: one bulk store of the whole state
-                until_keep = args.thin;
-                if (kept_step) {
-                    if (tid == 0) {
-                        bulk_s2g(args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L, sPos, (uint32_t)W * L * 8u);
-                        bulk_s2g(args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W, sLnp, (uint32_t)W * 8u);
-                        bulk_commit();
-                        owe_arrival = true;
-                    }
-                    ++stores_issued;
-                }
-                ++slot;
-            }
+            end_of_half_step(half);
         }
+        }   // not a draw warp
 #undef MDA_STAMP
 #undef MDA_STAMP_AFTER
 
         // ---- hand the bin back: state to HBM/L2, then the progress word
-        if (tid == 0 && owe_arrival) {                     // the last step of the unit was kept: its store still reads the state
-            bulk_wait_read_all();
-            mbar_arrive(&store_bar);
-            owe_arrival = false;
-        }
+        settle_store();                                    // the last step of the unit was kept: its store still reads the state
         if (stores_seen != stores_issued) {
             mbar_wait(&store_bar, (stores_issued - 1u) & 1u);
             stores_seen = stores_issued;
@@ -497,51 +557,49 @@ __global__ void __launch_bounds__(32 * kMaxWarps, 2) ensemble_mma_kernel(const E
             st_release_u64(args.progress + bin, args.launch_serial + (unsigned long long)(chunk + 1));
         }
     }
-    if (tid == 0) bulk_wait_all();
+    if (issuer) bulk_wait_all();
     if (saw_nan) atomicOr(args.status, kStatusNaN);
 }
 
 using EnsKernel = void (*)(const EnsembleArgs);
 
 template <int L>
-EnsKernel pick_mma_wt(int wt) {
+EnsKernel pick_mma_wt(int wt, bool dw) {
     switch (wt) {
-        case 1: return ensemble_mma_kernel<L, 1, false>;
-        case 2: return ensemble_mma_kernel<L, 2, false>;
-        case 4: return ensemble_mma_kernel<L, 4, false>;
+        case 1: return dw ? ensemble_mma_kernel<L, 1, true, false> : ensemble_mma_kernel<L, 1, false, false>;
+        case 2: return dw ? ensemble_mma_kernel<L, 2, true, false> : ensemble_mma_kernel<L, 2, false, false>;
+        case 4: return dw ? ensemble_mma_kernel<L, 4, true, false> : ensemble_mma_kernel<L, 4, false, false>;
         default: return nullptr;
     }
 }
 
-EnsKernel pick_mma_kernel(int n_l, int wt) {
+EnsKernel pick_mma_kernel(int n_l, int wt, bool dw) {
     switch (n_l) {
-        case 4: return pick_mma_wt<4>(wt);
-        case 5: return pick_mma_wt<5>(wt);
-        case 6: return pick_mma_wt<6>(wt);
-        case 7: return pick_mma_wt<7>(wt);
-        case 8: return pick_mma_wt<8>(wt);
-        case 9: return pick_mma_wt<9>(wt);
-        case 10: return pick_mma_wt<10>(wt);
-        case 11: return pick_mma_wt<11>(wt);
-        case 12: return pick_mma_wt<12>(wt);
-        case 13: return pick_mma_wt<13>(wt);
-        case 14: return pick_mma_wt<14>(wt);
-        case 15: return pick_mma_wt<15>(wt);
-        case 16: return pick_mma_wt<16>(wt);
+        case 4: return pick_mma_wt<4>(wt, dw);
+        case 5: return pick_mma_wt<5>(wt, dw);
+        case 6: return pick_mma_wt<6>(wt, dw);
+        case 7: return pick_mma_wt<7>(wt, dw);
+        case 8: return pick_mma_wt<8>(wt, dw);
+        case 9: return pick_mma_wt<9>(wt, dw);
+        case 10: return pick_mma_wt<10>(wt, dw);
+        case 11: return pick_mma_wt<11>(wt, dw);
+        case 12: return pick_mma_wt<12>(wt, dw);
+        case 13: return pick_mma_wt<13>(wt, dw);
+        case 14: return pick_mma_wt<14>(wt, dw);
+        case 15: return pick_mma_wt<15>(wt, dw);
+        case 16: return pick_mma_wt<16>(wt, dw);
         default: return nullptr;
     }
 }
 
 // The build with the timeline stamps (mdaEnsembleProfile): the C4 shape only.
 constexpr int kProfL = 9, kProfWT = 4;
-EnsKernel prof_kernel() { return ensemble_mma_kernel<kProfL, kProfWT, true>; }
+EnsKernel prof_kernel(bool dw) { return dw ? ensemble_mma_kernel<kProfL, kProfWT, true, true> : ensemble_mma_kernel<kProfL, kProfWT, false, true>; }
 
 }  // namespace
 
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
-                               EnsembleShape *out) {
-    (void)bins;
-    (void)sm_count;
+                               int force_draw_warps, EnsembleShape *out) {
     if (n_l < kMinMmaL || n_l > kMaxRegL) return false;
     EnsembleShape s{};
     const int half = walkers / 2;
@@ -551,10 +609,14 @@ bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int 
     if (force_wt == 1 || force_wt == 2 || force_wt == 4) wt = force_wt;
     const int n_items = (half + 8 * wt - 1) / (8 * wt);
     if (n_items > kMaxWarps) return false;                                   // one item per warp
+    // draw warps where an SM holds one bin at a time; from two bins per SM on, two 8-warp CTAs share an SM
+    bool dw = bins < 2 * sm_count;
+    if (force_draw_warps == 1) dw = true;
+    if (force_draw_warps == 2) dw = false;
     s.wpt = wt;
     s.groups = n_items;
-    s.stage = 1;
-    s.threads = 32 * n_items;
+    s.stage = dw ? 1 : 0;
+    s.threads = 32 * n_items * (dw ? 2 : 1);
     s.global_state = false;
     s.mma = true;
     s.fits = s.smem_bytes + kStaticSmem <= smem_optin && (size_t)n_tiles * 8 * (size_t)(n_l + 1) * 8 < (1u << 20);
@@ -572,17 +634,19 @@ cudaError_t configure_ensemble_mma_kernels(size_t smem_optin) {
         return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
     };
     for (int l = kMinMmaL; l <= kMaxRegL; ++l)
-        for (int wt = 1; wt <= 4; wt *= 2) {
-            cudaError_t e = raise(pick_mma_kernel(l, wt));
-            if (e != cudaSuccess) return e;
-        }
-    return raise(prof_kernel());
+        for (int dw = 0; dw <= 1; ++dw)
+            for (int wt = 1; wt <= 4; wt *= 2) {
+                cudaError_t e = raise(pick_mma_kernel(l, wt, dw != 0));
+                if (e != cudaSuccess) return e;
+            }
+    cudaError_t e = raise(prof_kernel(false));
+    return e != cudaSuccess ? e : raise(prof_kernel(true));
 }
 
 // Co-resident CTAs of this kernel on the whole device (the unit list needs every CTA of the grid
 // resident: a unit may wait for one that runs on another CTA).
 int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count) {
-    EnsKernel k = pick_mma_kernel(n_l, shape.wpt);
+    EnsKernel k = pick_mma_kernel(n_l, shape.wpt, shape.stage == 1);
     int per_sm = 0;
     if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(k), shape.threads,
                                                             shape.smem_bytes) != cudaSuccess)
@@ -592,8 +656,8 @@ int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count) {
 
 cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream) {
     if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
-    EnsKernel k = pick_mma_kernel(args.n_l, shape.wpt);
-    if (args.prof && args.n_l == kProfL && shape.wpt == kProfWT) k = prof_kernel();
+    EnsKernel k = pick_mma_kernel(args.n_l, shape.wpt, shape.stage == 1);
+    if (args.prof && args.n_l == kProfL && shape.wpt == kProfWT) k = prof_kernel(shape.stage == 1);
     if (!k || !shape.fits || !shape.mma || !args.consts_mma || grid < 1 || args.chunk_steps < 1 || args.n_chunks < 1 ||
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;

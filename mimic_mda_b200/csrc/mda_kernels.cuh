@@ -82,7 +82,7 @@ struct EnsembleArgs {
 
 struct EnsembleShape {
     int threads, wpt, groups;  // blockDim = walker threads x angle groups
-    int stage;                 // unused
+    int stage;                 // ensemble_mma_kernel: 1 = with draw warps (one CTA of 2 x items warps per SM), 0 = two CTAs per SM
     size_t smem_bytes;
     bool fits;                 // the launch is possible (shared memory, numL <= kMaxRegL)
     bool global_state;         // positions / log-probabilities stay in HBM (ensemble too large for shared memory)
@@ -102,7 +102,7 @@ cudaError_t launch_ensemble(const EnsembleArgs &args, const EnsembleShape &shape
 // d - sum a_l D_l is a pure multiply-accumulate onto d.  Returns false when the shape cannot run (numL < kMinMmaL,
 // numL > kMaxRegL, more than 512 walkers or the ensemble does not fit shared memory).
 bool choose_ensemble_mma_shape(int bins, int walkers, int n_l, int n_tiles, int sm_count, size_t smem_optin, int force_wt,
-                               EnsembleShape *out);
+                               int force_draw_warps, EnsembleShape *out);   // force_draw_warps: 0 auto, 1 with, 2 without
 cudaError_t configure_ensemble_mma_kernels(size_t smem_optin);
 int ensemble_mma_capacity(int n_l, const EnsembleShape &shape, int sm_count);   // co-resident CTAs on the device
 cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);

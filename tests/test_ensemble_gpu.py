@@ -25,9 +25,10 @@ def _problem(n_bins, n_l, n_pts, walkers, ragged=True, seed=17):
                                    # ensembles larger than shared memory (state in HBM/L2): the reference's own
                                    # 2500 walkers x 8 parameters (mda_config0.py:93,105), and a wider one
                                    (1, 8, 41, 2500, 12), (2, 9, 60, 3000, 6)])
-@pytest.mark.parametrize("impl", ["ws", "mma"])      # the two DMMA steppers (shapes neither takes run on the DFMA stepper)
+@pytest.mark.parametrize("impl", ["ws", "mma", "mma-2cta"])   # the DMMA steppers (shapes none takes run on the DFMA stepper)
 def test_device_chain_equals_cpu_restatement(cs_lib, oracle_lib, monkeypatch, shape, impl):
-    monkeypatch.setenv("MDA_ENS_IMPL", impl)
+    monkeypatch.setenv("MDA_ENS_IMPL", impl.split("-")[0])
+    monkeypatch.setenv("MDA_ENS_DRAWW", "2" if impl.endswith("2cta") else "0")     # 2: without draw warps (two CTAs per SM)
     n_bins, n_l, n_pts, walkers, steps = shape
     consts, counts, lo, hi, p0, _ = _problem(n_bins, n_l, n_pts, walkers)
     want = dso.run(lambda p: oracle_lib.lnpost_bins(consts, counts, lo, hi, p), p0, steps, seed=0xC0FFEE1234)
@@ -90,6 +91,7 @@ def test_split_runs_thinning_and_partition_invariance(cs_lib):
                                  {"MDA_ENS_GRID": "4", "MDA_ENS_CHUNK": "16"},
                                  {"MDA_ENS_WT": "2"}, {"MDA_ENS_WT": "4"},
                                  {"MDA_ENS_IMPL": "mma"}, {"MDA_ENS_IMPL": "mma", "MDA_ENS_WT": "4"},
+                                 {"MDA_ENS_IMPL": "mma", "MDA_ENS_DRAWW": "2"}, {"MDA_ENS_IMPL": "mma", "MDA_ENS_DRAWW": "2", "MDA_ENS_WT": "2"},
                                  {"MDA_ENS_IMPL": "mma", "MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "5"},
                                  {"MDA_ENS_IMPL": "dfma"}])
 def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
