@@ -190,7 +190,10 @@ MDA_API unsigned long long mdaKernelLaunchCount(void);
  * One persistent launch advances every bin's ensemble of nWalkers walkers by
  * nSteps stretch-move steps (two half-ensemble updates per step, emcee 2.x
  * semantics); positions, log-probabilities and the bin's constants stay in
- * shared memory, random numbers come from Philox4x32-10 with counter
+ * shared memory, chi^2 runs on the fp64 tensor path (DMMA.8x8x4; two schedules
+ * of the same arithmetic, picked by bins per SM; ensembles of
+ * more than 512 walkers or numL < 4 use the DFMA stepper), random numbers come
+ * from Philox4x32-10 with counter
  * (walker, bin id, 2*step+half, draw) and key = seed, so a chain depends only
  * on (seed, bin id, start positions) -- not on launch shape or GPU count.
  * Kept samples are appended to a chain held in HBM.
@@ -241,11 +244,14 @@ MDA_API const double *mdaEnsembleDevicePositions(void *ens);
 /* Which stepping kernel an Advance of nSteps would launch and how its work is laid out
  * (kernel variant, warps, shared memory, grid, chunking), as text.  For logs and benchmarks. */
 MDA_API int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen);
-/* Debug: cycles[bin][128] of the last Advance.  DMMA stepper: clock stamps of one half-step,
- * [warp < 16][8] = {start, proposals staged | proposals seen, draw made | chi^2 loop done,
- * chi^2 seen | chi^2 posted, accepted, -, at the barrier, past the barrier}; DFMA stepper: the
- * first 8 words are section cycle counters of thread 0 {proposal, likelihood, accept, chi^2 loop,
- * draw}.  The first call (cycles may be NULL) switches the counters on. */
+/* Debug: cycles[bin][128] of the last Advance.  DMMA steppers (profiling build: numL = 9, 512 walkers): clock
+ * stamps of one half-step, [warp < 16][8].  Warp-specialised kernel: walker warps {start, -, draw made,
+ * chi^2 seen, accepted}, math warps {start, proposals made, -, chi^2 posted}.  8-warp kernel: {start, proposals
+ * made, chi^2 reduced, rows updated, next operands fetched, -, accept estimate, accept bits}.  DFMA stepper:
+ * the first 8 words are section cycle counters of thread 0 {proposal, likelihood, accept, chi^2 loop, draw}.
+ * The first call (cycles may be NULL) switches the counters on.  Environment switches for experiments:
+ * MDA_ENS_IMPL = ws | mma | dfma (stepper), MDA_ENS_WT (tiles per item), MDA_ENS_DRAWW = 1 | 2 (8-warp kernel
+ * with | without draw warps), MDA_ENS_GRID / MDA_ENS_CHUNK (unit schedule). */
 MDA_API int mdaEnsembleProfile(void *ens, long long *cycles);
 /* The generator itself, evaluated on the host from the same source the kernels compile
  * (csrc/philox.cuh): out[4] = Philox4x32-10(counter[4], key[2]).  For known-answer tests. */
