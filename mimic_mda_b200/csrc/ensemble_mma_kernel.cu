@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
             };
             publish(t_begin);
             __syncthreads();                               // the state and the first draw are there
+            __syncthreads();                               // ... and the item warps have fetched that draw: the next may overwrite it
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 if (t + 1 < t_end) {
                     publish(t + 1);
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
         __syncthreads();                                   // the state (and with draw warps the first draw) is there
         if (!DW) draw(t_begin);
         fetch(t_begin);
+        if (DW) __syncthreads();                           // only now may the draw warps publish the next draw
 
         // debug timeline (mdaEnsembleProfile): clock stamps of one half-step, per warp
         const uint32_t t_prof = (PROF && args.prof != nullptr && chunk == 0) ? t_begin + min(81u, 2u * (uint32_t)steps_here - 1u) : 0xffffffffu;

@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
             const int live_w = min(GW, H - warp * GW);
             draw(t_begin, my_i);
             __syncthreads();                                   // state and first draw are there
+            __syncthreads();                                   // ... and the math warps have fetched that draw: the next may overwrite it
 
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 const uint32_t half = t & 1u;
@@ -412,6 +413,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
             };
             __syncthreads();                                   // state and first draw are there
             prefetch(t_begin);
+            __syncthreads();                                   // only now may the walker warps publish the next draw
 
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 long long *stamp = (PROF && t == t_prof && lane == 0) ? args.prof + ((size_t)bin * 16 + warp) * 8 : nullptr;

@@ -123,6 +123,48 @@ def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
     store.close()
 
 
+def test_full_size_c4_steppers_agree_and_follow_the_restatement(cs_lib, oracle_lib, monkeypatch):
+    """BASELINE.json configs[3] at full size (200 bins x 512 walkers x 9 dists x 60 angles): the three DMMA
+    schedules give bit-identical chains (size-independent property: a chain depends on seed, bin id and start
+    only), three bins spot-checked against the CPU restatement, every sample inside the box prior, and the
+    chain on 2 'ranks' (bins round-robin) is the chain on one."""
+    n_bins, n_l, n_pts, walkers, steps = 200, 9, 60, 512, 24
+    consts, counts, lo, hi, p0, _ = _problem(n_bins, n_l, n_pts, walkers)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    chains = {}
+    for impl, draww in (("ws", "0"), ("mma", "1"), ("mma", "2")):
+        monkeypatch.setenv("MDA_ENS_IMPL", impl)
+        monkeypatch.setenv("MDA_ENS_DRAWW", draww)
+        ens = DeviceEnsemble(store, walkers, seed=20240229)
+        ens.run_mcmc(p0, steps)
+        chains[(impl, draww)] = (ens.chain.copy(), ens.lnprobability.copy(), ens.naccepted.copy())
+        ens.close()
+    ref = chains[("ws", "0")]
+    for key, got in chains.items():
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a, b, err_msg=str(key))
+    assert np.all(ref[0] >= lo) and np.all(ref[0] <= hi)
+    acc = ref[2].sum() / (n_bins * walkers * steps)
+    assert 0.15 < acc < 0.75, acc
+    pick = np.array([0, 77, 199])
+    want = dso.run(lambda p: oracle_lib.lnpost_bins(consts[pick], counts[pick], lo, hi, p), p0[pick], steps,
+                   seed=20240229, bin_ids=pick)
+    got = ref[0][pick].transpose(0, 2, 1, 3)
+    np.testing.assert_allclose(got[:, :3], want["chain"][:, :3], rtol=1e-13, atol=0)
+    assert np.all(got == want["chain"], axis=(2, 3)).mean() > 0.99
+    monkeypatch.setenv("MDA_ENS_IMPL", "ws")
+    monkeypatch.setenv("MDA_ENS_DRAWW", "0")
+    for r in range(2):
+        idx = np.arange(r, n_bins, 2)
+        st = chisq.DeviceStore(consts[idx], counts[idx], (lo, hi), cs_lib=cs_lib)
+        part = DeviceEnsemble(st, walkers, seed=20240229, bin_ids=idx)
+        part.run_mcmc(p0[idx], steps)
+        np.testing.assert_array_equal(part.chain, ref[0][idx])
+        part.close()
+        st.close()
+    store.close()
+
+
 def test_posterior_agrees_with_host_driven_emcee_style_sampler(cs_lib, oracle_lib):
     """Different generators (Philox vs Mersenne Twister) => statistical parity:
     posterior means and quantiles within MCMC noise (mda.py:1429-1431)."""
