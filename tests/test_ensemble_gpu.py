@@ -136,9 +136,11 @@ def test_full_size_steppers_agree_and_follow_the_restatement(cs_lib, oracle_lib,
     n_bins, n_l, n_pts, walkers, steps = shape
     consts, counts, lo, hi, p0, _ = _problem(n_bins, n_l, n_pts, walkers)
     store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
-    def run(impl, draww):
+    def run(impl, draww, grid="", chunk=""):
         monkeypatch.setenv("MDA_ENS_IMPL", impl)
         monkeypatch.setenv("MDA_ENS_DRAWW", draww)
+        monkeypatch.setenv("MDA_ENS_GRID", grid)       # "" = the library's own schedule
+        monkeypatch.setenv("MDA_ENS_CHUNK", chunk)
         ens = DeviceEnsemble(store, walkers, seed=20240229)
         ens.run_mcmc(p0, steps)
         out = (ens.chain.copy(), ens.lnprobability.copy(), ens.naccepted.copy())
@@ -151,6 +153,11 @@ def test_full_size_steppers_agree_and_follow_the_restatement(cs_lib, oracle_lib,
         for a, b in zip(got, ref):
             np.testing.assert_array_equal(a, b, err_msg=impl + " " + draww)
         del got
+    if steps <= 24:                        # many units per CTA, hand-over after every 3 steps
+        for impl, draww in (("ws", "0"), ("mma", "1"), ("mma", "2")):
+            got = run(impl, draww, grid="37", chunk="3")
+            np.testing.assert_array_equal(got[0], ref[0], err_msg=impl + " " + draww + " 37 CTAs")
+            del got
     got = run("dfma", "0")                 # another summation order: may differ in a measure-zero set of near ties
     assert np.all(got[0] == ref[0], axis=(1, 3)).mean() > 0.999
     del got
