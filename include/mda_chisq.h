@@ -137,7 +137,10 @@ MDA_API int   mdaStoreMaxPts(void *store);
 /* Force the kernel tiling (threads per CTA in {32,64,128,256}, walkers per
  * thread in {1,2,4}); 0,0 restores the built-in heuristic. */
 MDA_API int   mdaStoreSetTile(void *store, int threads, int walkersPerThread);
-/* Reports the tiling the next call with walkersPerBin walkers would use. */
+/* Reports the tiling the next call with walkersPerBin walkers would use.  walkersPerThread = 0: the
+ * DMMA kernel (lnpost_mma_kernel: 128 threads, one warp per item of 32 walkers), the default for
+ * numL 4 .. 16 with more than 88 angles; a forced tiling selects the register-tiled DFMA kernel,
+ * MDA_BATCH_IMPL = mma | dfma either one. */
 MDA_API int   mdaStoreGetTile(void *store, int walkersPerBin, int *threads, int *walkersPerThread, int *gridSize);
 
 /* ------------------------------------------------------------------------

@@ -112,6 +112,7 @@ int ensure_runtime() {
     snprintf(g_rt.name, sizeof(g_rt.name), "%s", prop.name);
     MDA_CUDA(configure_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem)");
     MDA_CUDA(configure_ensemble_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, ensemble)");
+    MDA_CUDA(configure_lnpost_mma_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, DMMA batch)");
     MDA_CUDA(configure_ensemble_mma_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, DMMA ensemble)");
     MDA_CUDA(configure_ensemble_ws_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, warp-specialised DMMA ensemble)");
     g_rt.ready = true;
@@ -294,6 +295,19 @@ TileShape tile_for(const MdaStore *s, int walkers) {
                        s->force_wpt);
 }
 
+// The batched evaluation runs on the fp64 tensor path (lnpost_mma_kernel) where that is the faster kernel: from 12
+// angle tiles (more than 88 angles) on -- measured at 200 bins x 8192 walkers: 80 vs 70 % of the fp64 peak at 256
+// angles, 59 vs 65 % at 60, 39 vs 52 % at 30 (profiles/r01_sweep_big_dmma_vs_dfma.txt).  A forced tiling
+// (mdaStoreSetTile) selects the register-tiled DFMA kernel, MDA_BATCH_IMPL = mma | dfma either one.
+bool use_batch_mma(const MdaStore *s) {
+    if (s->force_threads > 0 || s->force_wpt > 0) return false;
+    if (!lnpost_mma_supported(s->n_l, s->n_tiles, g_rt.smem_optin)) return false;
+    const char *impl = getenv("MDA_BATCH_IMPL");
+    if (impl && strcmp(impl, "dfma") == 0) return false;
+    if (impl && strcmp(impl, "mma") == 0) return true;
+    return s->n_tiles >= 12;
+}
+
 // Enqueue one evaluation of device-resident params on the store's stream.
 int enqueue_eval(MdaStore *s, int walkers, const double *d_params, double *d_out, int mode) {
     BatchArgs args;
@@ -309,6 +323,13 @@ int enqueue_eval(MdaStore *s, int walkers, const double *d_params, double *d_out
     args.mode = mode;
     if (s->n_l <= kMaxRegL)
         for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
+    if (use_batch_mma(s)) {
+        args.consts_mma = s->d_consts_mma;
+        args.n_tiles = s->n_tiles;
+        MDA_CUDA(launch_batch_mma(args, g_rt.sm_count, s->stream, nullptr, nullptr), "batched likelihood launch (DMMA)");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return MDA_OK;
+    }
     const TileShape tile = tile_for(s, walkers);
     if (tile.smem_bytes > g_rt.smem_optin)
         return set_error(MDA_ERR_BAD_ARGUMENT, "tile needs %zu bytes of shared memory, device offers %zu",
@@ -726,6 +747,15 @@ int mdaStoreGetTile(void *store, int walkersPerBin, int *threads, int *walkersPe
     if (!s) return MDA_ERR_BAD_ARGUMENT;
     int rc = ensure_runtime();
     if (rc) return rc;
+    if (use_batch_mma(s)) {                            // the DMMA kernel: 128 threads, a warp per 32 walkers -> reported as 0 walkers per thread
+        const long n_items = ((walkersPerBin > 0 ? walkersPerBin : 1) + 31) / 32, total = n_items * s->bins;
+        long passes = (total + 4 * 8L * g_rt.sm_count - 1) / (4 * 8L * g_rt.sm_count);
+        if (passes < 1) passes = 1;
+        if (threads) *threads = 128;
+        if (walkersPerThread) *walkersPerThread = 0;
+        if (gridSize) *gridSize = (int)(s->bins * ((n_items + 4 * passes - 1) / (4 * passes)));
+        return MDA_OK;
+    }
     const TileShape t = tile_for(s, walkersPerBin > 0 ? walkersPerBin : 1);
     if (threads) *threads = t.threads;
     if (walkersPerThread) *walkersPerThread = t.wpt;

@@ -38,7 +38,7 @@
 //
 // Shapes: one item per warp, at most 8 warps: ensembles of up to 512 walkers (all BASELINE.json
 // shapes); larger ones run on ensemble_kernel.cu.
-#include "likelihood.cuh"
+#include "mma_chi.cuh"
 #include "philox.cuh"
 
 namespace mda {
@@ -67,11 +67,6 @@ struct EnsembleMmaSmem {
     }
 };
 
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
@@ -91,60 +86,6 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 
 __host__ __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uint32_t y) {
     return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
-}
-
-// chi^2 of WT tiles of 8 walkers (A fragments a[][], leading elements lead[][]) against NTC angle tiles
-// (NTC = 0: nt of them, a run-time count).  Constants are fetched one tile ahead of their use.
-template <int L, int WT, int NTC>
-__device__ __forceinline__ void chi_tiles(const double *sC, int nt, int lane, const double (&a)[WT][L / 4],
-                                          const double (&lead)[WT][(L % 4) > 0 ? (L % 4) : 1], double (&chi0)[WT], double (&chi1)[WT]) {
-    constexpr int Q = L / 4, R = L % 4, RR = R > 0 ? R : 1, TS = 8 * (L + 1);
-    const int tig = lane & 3;
-    const int n = NTC > 0 ? NTC : nt;
-    const double *tp = sC;
-    double2 dv = *reinterpret_cast<const double2 *>(tp + 2 * tig);
-    double2 Di[RR];
-#pragma unroll
-    for (int l = 0; l < R; ++l) Di[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
-    double Bf[Q];
-#pragma unroll
-    for (int ks = 0; ks < Q; ++ks) Bf[ks] = tp[8 * (1 + R) + 32 * ks + lane];
-#pragma unroll(NTC > 0 ? NTC : 2)
-    for (int at = 0; at < n; ++at) {
-        tp = sC + min(at + 1, n - 1) * TS;
-        const double2 dv_n = *reinterpret_cast<const double2 *>(tp + 2 * tig);
-        double2 Di_n[RR];
-#pragma unroll
-        for (int l = 0; l < R; ++l) Di_n[l] = *reinterpret_cast<const double2 *>(tp + 8 * (1 + l) + 2 * tig);
-        double Bf_n[Q];
-#pragma unroll
-        for (int ks = 0; ks < Q; ++ks) Bf_n[ks] = tp[8 * (1 + R) + 32 * ks + lane];
-        double c0[WT], c1[WT];
-#pragma unroll
-        for (int k = 0; k < WT; ++k) {
-            c0[k] = dv.x;
-            c1[k] = dv.y;
-#pragma unroll
-            for (int l = 0; l < R; ++l) {
-                c0[k] = fma(lead[k][l], Di[l].x, c0[k]);
-                c1[k] = fma(lead[k][l], Di[l].y, c1[k]);
-            }
-        }
-#pragma unroll
-        for (int ks = 0; ks < Q; ++ks)
-#pragma unroll
-            for (int k = 0; k < WT; ++k) dmma884(c0[k], c1[k], a[k][ks], Bf[ks]);
-#pragma unroll
-        for (int k = 0; k < WT; ++k) {
-            chi0[k] = fma(c0[k], c0[k], chi0[k]);
-            chi1[k] = fma(c1[k], c1[k], chi1[k]);
-        }
-        dv = dv_n;
-#pragma unroll
-        for (int l = 0; l < R; ++l) Di[l] = Di_n[l];
-#pragma unroll
-        for (int ks = 0; ks < Q; ++ks) Bf[ks] = Bf_n[ks];
-    }
 }
 
 // Bank conflicts of one 64-bit access of a half-warp to the own rows: 4 rows (consecutive g), 4 consecutive

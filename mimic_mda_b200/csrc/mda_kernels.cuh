@@ -30,6 +30,8 @@ struct BatchArgs {
     int mode;               // EvalMode
     double lo[kMaxRegL];    // box prior, used by the register-tiled kernel (numL <= kMaxRegL)
     double hi[kMaxRegL];
+    const double *consts_mma;   // DMMA kernel: fragment-major constants [bins][n_tiles][8 (1+L)] (see mma_chi.cuh)
+    int n_tiles;                // DMMA kernel: angle tiles of 8
 };
 
 struct TileShape {
@@ -51,6 +53,12 @@ cudaError_t launch_batch(BatchArgs &args, const TileShape &tile, cudaStream_t st
 
 // One-time per device: raise the dynamic shared memory limit of every instantiation.
 cudaError_t configure_kernels(size_t smem_optin);
+
+// The same evaluation on the fp64 tensor path (lnpost_mma_kernel.cu), numL kMinMmaL .. kMaxRegL: a warp per item of
+// 32 walkers, parameters read straight from global memory.  args.consts_mma / n_tiles set by the caller.
+bool lnpost_mma_supported(int n_l, int n_tiles, size_t smem_optin);
+cudaError_t configure_lnpost_mma_kernels(size_t smem_optin);
+cudaError_t launch_batch_mma(BatchArgs &args, int sm_count, cudaStream_t stream, int *grid_out, int *threads_out);
 
 // ---- device-resident ensemble stepping (ensemble_kernel.cu) -----------------------------
 struct EnsembleArgs {

@@ -119,19 +119,66 @@ def test_full_size_configs_against_oracle(cs_lib, oracle_lib, name):
     store.close()
 
 
-def test_every_tiling_is_bit_identical(cs_lib, oracle_lib):
+def test_every_tiling_is_bit_identical(cs_lib, oracle_lib, monkeypatch):
+    """The register-tiled DFMA kernel (a forced tiling selects it): the reference's operation order in every tiling.
+    The DMMA kernel sums in another order: within 1e-14 of it, and still inside the oracle tolerance."""
+    monkeypatch.setenv("MDA_BATCH_IMPL", "mma")
     consts, n_pts, a_true = synth.make_bins(7, 9, 60, ragged=True)
     lo, hi = synth.default_bounds(9)
     params = synth.make_walkers(a_true, 301, seed=5)     # not a multiple of any tile
+    want = oracle_lib.lnpost_bins(consts, n_pts, lo, hi, params)
     store = chisq.DeviceStore(consts, n_pts, (lo, hi), cs_lib=cs_lib)
+    assert store.get_tile(301)[:2] == (128, 0)           # the DMMA kernel
+    default = store.lnpost(params)
+    assert same_special(default, want) and rel_err(default, want) <= TOL
+    store.set_tile(64, 2)
     base = store.lnpost(params)
-    assert rel_err(base, oracle_lib.lnpost_bins(consts, n_pts, lo, hi, params)) <= TOL
+    assert same_special(base, want) and rel_err(base, want) <= TOL
+    assert rel_err(default, base) <= 1e-14
     for threads in (32, 64, 128, 256):
         for wpt in (1, 2, 4):
             store.set_tile(threads, wpt)
             assert store.get_tile(301)[:2] == (threads, wpt)
             np.testing.assert_array_equal(store.lnpost(params), base)
     store.set_tile(0, 0)
+    np.testing.assert_array_equal(store.lnpost(params), default)
+    monkeypatch.setenv("MDA_BATCH_IMPL", "")
+    assert store.get_tile(301)[1] != 0                   # 60 angles: the DFMA kernel is the default
+    np.testing.assert_array_equal(store.lnpost(params), base)
+    store.close()
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 16, 33), (2, 9, 60, 1), (5, 12, 256, 200), (2, 16, 24, 95), (1, 7, 41, 8192),
+                                   (150, 5, 30, 128), (4, 8, 60, 2500)])
+@pytest.mark.parametrize("mode", ["lnpost", "chi"])
+def test_dmma_batched_kernel_against_oracle_and_dfma_kernel(cs_lib, oracle_lib, monkeypatch, shape, mode):
+    """lnpost_mma_kernel at ragged walker counts, every numL % 4, many angle tiles, several passes per warp: within
+    the oracle tolerance, -inf / NaN exactly where the reference has them, within 1e-14 of the DFMA kernel, and a
+    walker's value does not depend on the batch it is evaluated in."""
+    monkeypatch.setenv("MDA_BATCH_IMPL", "mma")
+    n_bins, n_l, n_pts, walkers = shape
+    consts, n_pts_arr, a_true = synth.make_bins(n_bins, n_l, n_pts, ragged=True)
+    lo, hi = synth.default_bounds(n_l)
+    params = synth.make_walkers(a_true, walkers, seed=9)
+    if walkers > 4:
+        params[0, 3, 0] = np.nan                          # a NaN passes the box prior and poisons the sum (mda.py:1574-1576)
+        params[-1, 1, n_l - 1] = hi[n_l - 1]              # on the inclusive bound: inside
+    store = chisq.DeviceStore(consts, n_pts_arr, (lo, hi), cs_lib=cs_lib)
+    fn = store.lnpost if mode == "lnpost" else store.chi
+    if mode == "lnpost":
+        want = oracle_lib.lnpost_bins(consts, n_pts_arr, lo, hi, params)
+    else:                                                 # chi^2 has no prior (C/ChiSquare.c:114-172)
+        want = np.stack([oracle_lib.chi_batch(consts[b, 0, :n_pts_arr[b]], consts[b, 1:, :n_pts_arr[b]], params[b])
+                         for b in range(n_bins)])
+    got = fn(params)
+    assert same_special(got, want), mode
+    assert rel_err(got, want) <= TOL, rel_err(got, want)
+    if walkers > 40:
+        part = np.ascontiguousarray(params[:, 7:40])
+        np.testing.assert_array_equal(fn(part), got[:, 7:40])
+    store.set_tile(64, 2)
+    ref = fn(params)
+    assert same_special(got, ref) and rel_err(got, ref) <= 1e-14
     store.close()
 
 
