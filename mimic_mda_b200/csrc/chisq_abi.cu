@@ -1088,6 +1088,7 @@ int mdaEnsembleSynchronize(void *ens) {
     int status = 0;
     MDA_CUDA(cudaMemcpyAsync(&status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->store->stream), "ensemble status read");
     MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleSynchronize");
+    if (status & 4) return set_error(MDA_ERR_CUDA, "ensemble stepping gave up: a unit of work waited ~3 s for its predecessor (is another kernel holding SMs of this device?)");
     if (status & 1) return set_error(MDA_ERR_BAD_STATE, "lnprob returned NaN during ensemble stepping");
     return MDA_OK;
 }

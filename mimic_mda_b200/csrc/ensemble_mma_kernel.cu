@@ -46,6 +46,7 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
+constexpr int kStatusStalled = 4;        // a unit waited ~3 s for its predecessor: the launch gave up (never seen; a guard against a hung GPU)
 constexpr int kMaxWarps = 8;           // items (warps) per CTA
 constexpr int kDrawnBarrier = 1;       // named barrier: the draw of the next half-step is published (draw warps arrive, the others wait)
 constexpr size_t kStaticSmem = 64;     // the mbarriers (static __shared__), rounded up
@@ -150,7 +151,9 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
     int *sPartner = reinterpret_cast<int *>(smem_raw + lay.partner);
     float *sFast = reinterpret_cast<float *>(smem_raw + lay.fast);
 
+    __shared__ int s_abort;
     if (tid == 0) {
+        s_abort = 0;
         mbar_init(&mbar, 1);
         mbar_init(&store_bar, 1);
         fence_mbar_init();
@@ -208,10 +211,19 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
             bulk_g2s(smem_raw + lay.consts, args.consts_mma + (size_t)bin * NT * TS, cb, &mbar);
             if (chunk > 0) {
                 const unsigned long long want = args.launch_serial + (unsigned long long)chunk;
-                while (ld_acquire_u64(args.progress + bin) != want) __nanosleep(64);
+                unsigned int spins = 0;
+                while (ld_acquire_u64(args.progress + bin) != want) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 25)) { s_abort = 1; break; }     // ~3 s: the predecessor is not coming
+                }
             }
         }
         __syncthreads();
+        if (s_abort) {                                     // every CTA that depends on this bin gives up the same way
+            mbar_wait(&mbar, unit_phase);                  // (the bulk copy of the constants must land before the CTA may exit)
+            if (tid == 0) atomicOr(args.status, kStatusStalled);
+            break;
+        }
         for (int i = tid; i < W * L; i += T) sPos[i] = __ldcg(gPos + i);
         for (int w = tid; w < W; w += T) {
             sLnp[w] = __ldcg(gLnp + w);
