@@ -25,8 +25,10 @@ stretch move, mda.py:1128-1131), i.e. bins x 512 likelihood evaluations.
          while chunk c crosses PCIe.  This is what emcee's run_mcmc leaves on the host.
   batched_half_step  the host-driven alternative (one launch per half-ensemble, parameters
          from the host each time): resident ring > 2x L2, and staged-graph e2e.
-  roofline       the likelihood kernel against the fp64 FMA pipe (measured live by a
-                 DFMA microbenchmark) and against HBM (MEASURED_PEAKS.json).
+  roofline       the sampler kernel (chi^2 on the fp64 tensor path, DMMA.8x8x4, which shares the
+                 DFMA pipe and its peak) against the fp64 pipe (measured live by a DFMA
+                 microbenchmark) and against HBM (MEASURED_PEAKS.json); the kernel and its
+                 schedule are named by the library (mdaEnsembleDescribe).
   cpu_baseline   the unmodified reference library (oracle/_ref) through the Python
                  ctypes path of mda.py:1540-1578 on all host cores (N = 1, rank 0).
 """
@@ -615,9 +617,12 @@ def main():
                            "DFMA pipe and its peak (measured: 36.8 vs 37.1 TFLOP/s) and holds the scheduler's issue port while it runs, so the "
                            "denominator is the same fp64 peak; tcgen05 has no fp64 kind")
     dur_s = ms * 1e-3 / timed_launches
-    b_roofline = roofline_of("lnpost_tile_kernel<L=%d,WPT=%d> %d threads x %d CTAs" % (n_l, tile[1], tile[0], tile[2]), dur_s,
+    b_kernel = ("lnpost_tile_kernel<L=%d,WPT=%d> %d threads x %d CTAs" % (n_l, tile[1], tile[0], tile[2]) if tile[1] > 0 else
+                "lnpost_mma_kernel<L=%d> (fp64 DMMA) %d threads x %d CTAs" % (n_l, tile[0], tile[2]))
+    b_roofline = roofline_of(b_kernel, dur_s,
                              2.0 * n_ang * (n_l + 1) * bins * half, 8.0 * (n_l + 1) * bins * (half + n_ang), args.workload,
-                             "not used by this kernel: register-tiled DFMA (K = L = %d)" % n_l)
+                             ("not used by this kernel: register-tiled DFMA (K = L = %d); the DMMA variant is the default "
+                              "from 12 angle tiles on" % n_l) if tile[1] > 0 else "fp64 tensor path: mma.sync m8n8k4 f64 (DMMA.8x8x4)")
     batched = {
         "value": evals_step * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
         "gpu_launches": timed_launches, "roofline": b_roofline,
