@@ -241,6 +241,18 @@ MDA_API int   mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSte
  * Order statistics are exact; interpolation follows numpy.  Any output may be NULL. */
 MDA_API int   mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterval, int numBins,
                                    double *points, double *peaks, double *acceptFrac);
+/* Integrated autocorrelation time per bin and parameter, computed on the device-resident chain
+ * (replaces sampler.get_autocorr_time(c=CONFIG["ACorr WindSize"], fast=CONFIG["ACorr Use FFT"]),
+ * mda.py:1304-1308; the times go into the diagnostics file, mda.py:253-272).  emcee 2.x semantics:
+ * the series is the mean over the walkers of every kept sample (burn-in included, as sampler.chain
+ * is); f = its normalised linear autocorrelation function over all kept samples, or over the first
+ * 2^floor(log2 kept) of them if `fast`; for M = low, low + step, ... < high (0: int(kept / 2 / c))
+ * tau[l] = 1 + 2 sum(f[1:M]) is accepted once every tau > 1 and M > c max(tau), and abandoned once
+ * c max(tau) >= kept / 2.  tau[bin][l]; window[bin] (may be NULL) = the accepted M, or 0 where emcee
+ * raises AutocorrError ("the chain is too short"): that bin's tau are NaN.  emcee's defaults are
+ * low = 10, high = 0, step = 1, c = 10, fast = 0. */
+MDA_API int   mdaEnsembleAutocorrTime(void *ens, int low, int high, int step, double c, int fast,
+                                      double *tau, int *window);
 /* Device pointers of the chain / state, for device-side consumers. */
 MDA_API const double *mdaEnsembleDeviceChain(void *ens);
 MDA_API const double *mdaEnsembleDevicePositions(void *ens);

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1214,9 +1215,11 @@ int ensure_scratch(MdaEnsemble *e, size_t bytes) {
     if (bytes <= e->scratch_bytes) return MDA_OK;
     MDA_CUDA(cudaStreamSynchronize(e->store->stream), "summary scratch");
     if (e->scratch) cudaFree(e->scratch);
-    if (e->buckets) cudaFree(e->buckets);
+    if (e->buckets) cudaFree(e->buckets);                 // (released too, to make room; re-allocated on demand)
     e->scratch = nullptr;
     e->scratch_bytes = 0;
+    e->buckets = nullptr;
+    e->bucket_bytes = 0;
     MDA_CUDA(cudaMalloc(&e->scratch, bytes), "summary scratch");
     e->scratch_bytes = bytes;
     return MDA_OK;
@@ -1479,6 +1482,79 @@ int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterv
             for (int w = 0; w < e->walkers; ++w) sum += (double)acc[b * e->walkers + w] / (double)(e->steps > 0 ? e->steps : 1);
             acceptFrac[b] = sum / (double)e->walkers;
         }
+    }
+    return MDA_OK;
+}
+
+// emcee 2.x's EnsembleSampler.get_autocorr_time -> autocorr.integrated_time(np.mean(chain, axis=0), axis=0, ...),
+// as mda.py:1307-1308 calls it (emcee is not part of the reference tree: the published algorithm restated, see
+// oracle/autocorr_oracle.py).  The ensemble mean and the autocorrelation sums come from the device chain; the
+// window search below is emcee's loop over M.
+int mdaEnsembleAutocorrTime(void *ens, int low, int high, int step, double c, int fast, double *tau, int *window) {
+    MdaEnsemble *e = as_ensemble(ens, "mdaEnsembleAutocorrTime");
+    if (!e) return MDA_ERR_BAD_ARGUMENT;
+    if (!tau) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleAutocorrTime: NULL result");
+    if (low < 1 || step < 1 || !(c > 0.0) || high < 0)
+        return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleAutocorrTime: low >= 1, step >= 1, c > 0 and high >= 0 (0: default) required");
+    int rc = mdaEnsembleSynchronize(ens);
+    if (rc) return rc;
+    MdaStore *s = e->store;
+    const size_t B = (size_t)s->bins, L = (size_t)s->n_l, cols = B * L;
+    if (cols == 0) return MDA_OK;
+    const long long N = e->kept;                                      // the whole kept chain, burn-in included (sampler.chain)
+    if (N < 1 || !e->d_chain) return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleAutocorrTime: no chain kept");
+    if (N > 0x7fffffffLL) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleAutocorrTime: %lld kept samples", N);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    auto fail_all = [&]() {
+        for (size_t i = 0; i < cols; ++i) tau[i] = nan;
+        if (window) for (size_t b = 0; b < B; ++b) window[b] = 0;
+        return MDA_OK;
+    };
+    const double size = 0.5 * (double)N;
+    if (c * (double)low >= size) return fail_all();                   // emcee: AutocorrError("The chain is too short")
+    int n = (int)N;
+    if (fast) { n = 1; while (2LL * n <= N) n *= 2; }                 // the largest power of two
+    if (high == 0) high = (int)(size / c);
+    if (high <= low) return fail_all();                               // no window to try
+    const int n_lags = std::max(1, std::min(high - 1, n));            // f[1:M] with M < high never reads further
+
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_series = up(8 * cols * (size_t)N), b_acf = up(8 * cols * (size_t)n_lags);
+    if ((rc = ensure_scratch(e, 2 * b_series + b_acf))) return rc;
+    char *base = static_cast<char *>(e->scratch);
+    double *d_series = reinterpret_cast<double *>(base), *d_centred = reinterpret_cast<double *>(base + b_series),
+           *d_acf = reinterpret_cast<double *>(base + 2 * b_series);
+    std::vector<double> acf(cols * (size_t)n_lags);
+    cudaError_t err = launch_ensemble_mean(e->d_chain, N, s->bins, e->walkers, s->n_l, d_series, N, s->stream);
+    if (err == cudaSuccess) err = launch_series_acf(d_series, N, n, (int)cols, n_lags, d_centred, d_acf, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(acf.data(), d_acf, 8 * acf.size(), cudaMemcpyDeviceToHost, s->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
+    if (err != cudaSuccess) return cuda_fail(err, "autocorrelation sums");
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+
+    std::vector<double> run(L);                                       // sum(f[1:M]) per parameter, terms added in order
+    for (size_t b = 0; b < B; ++b) {
+        const double *a = acf.data() + b * L * (size_t)n_lags;
+        std::fill(run.begin(), run.end(), 0.0);
+        int next = 1, accepted = 0;
+        for (long long M = low; M < high; M += step) {
+            for (; next < M && next < n_lags; ++next)
+                for (size_t l = 0; l < L; ++l) run[l] += a[l * n_lags + next] / a[l * n_lags];
+            bool all_above = true, any_nan = false;
+            double tmax = -std::numeric_limits<double>::infinity();
+            for (size_t l = 0; l < L; ++l) {
+                const double t = 1.0 + 2.0 * run[l];
+                tau[b * L + l] = t;
+                all_above = all_above && t > 1.0;
+                any_nan = any_nan || t != t;
+                if (t > tmax) tmax = t;
+            }
+            if (any_nan) tmax = nan;                                  // numpy's max propagates NaN; every test below is then false
+            if (all_above && (double)M > c * tmax) { accepted = (int)M; break; }
+            if (c * tmax >= size) break;                              // too long to be estimated from this chain
+        }
+        if (window) window[b] = accepted;
+        if (!accepted) for (size_t l = 0; l < L; ++l) tau[b * L + l] = nan;
     }
     return MDA_OK;
 }

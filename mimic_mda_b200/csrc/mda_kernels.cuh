@@ -155,6 +155,14 @@ cudaError_t launch_select_finish(const double *chain, long long k0, long long k1
                                  const unsigned char *lead, const long long *offset, unsigned int *cursor,
                                  unsigned long long *buf, int n_ranks, int sm_count, cudaStream_t stream);
 
+// ---- autocorrelation of the ensemble-mean series (autocorr_kernel.cu) ------------------------------
+// series[cols][stride]: mean over the walkers of every kept sample, col = bin * L + l.
+cudaError_t launch_ensemble_mean(const double *chain, long long kept, int bins, int walkers, int n_l, double *series,
+                                 long long stride, cudaStream_t stream);
+// centred = series - mean over its first n samples; acf[cols][n_lags] = linear autocorrelation sums of those n.
+cudaError_t launch_series_acf(const double *series, long long stride, int n, int cols, int n_lags, double *centred, double *acf,
+                              cudaStream_t stream);
+
 // Legacy scalar path (one bin, one parameter vector), see scalar_kernel.cu.
 //   consts [1+L][n] dense (row 0 data, rows 1..L dists), params[L], result[0] = value,
 //   resid (may be null) [n]

@@ -42,6 +42,7 @@ def _declare(lib):
         "mdaEnsembleDescribe": (ct.c_int, [vp, ct.c_int, ct.c_char_p, ct.c_int]),
         "mdaEnsembleSummarize": (ct.c_int, [vp, ll, ct.c_double, ct.c_int, vp, vp, vp]),
         "mdaEnsembleRunToHost": (ct.c_int, [vp, ct.c_int, ct.c_int, ct.c_int, vp, vp]),
+        "mdaEnsembleAutocorrTime": (ct.c_int, [vp, ct.c_int, ct.c_int, ct.c_int, ct.c_double, ct.c_int, vp, vp]),
         "mdaEnsembleDeviceChain": (vp, [vp]),
         "mdaEnsembleDevicePositions": (vp, [vp]),
     }
@@ -49,6 +50,10 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     lib._mda_ensemble_declared = True
+
+
+class AutocorrError(Exception):
+    """The chain is too short to estimate the autocorrelation time (emcee.autocorr.AutocorrError)."""
 
 
 class DeviceEnsemble:
@@ -181,6 +186,24 @@ class DeviceEnsemble:
                                                             points.ctypes.data, peaks.ctypes.data, acc.ctypes.data),
                     "mdaEnsembleSummarize")
         return {"points": points, "peaks": peaks, "acceptance_fraction": acc}
+
+    def get_autocorr_time(self, low=10, high=None, step=1, c=10, fast=False, quiet=False):
+        """emcee 2.x's ``EnsembleSampler.get_autocorr_time`` for every bin (mda.py:1307-1308 passes
+        ``c=CONFIG["ACorr WindSize"], fast=CONFIG["ACorr Use FFT"]``), computed on the device chain:
+        ``tau [B, L]``.  Where emcee raises ``AutocorrError`` this does too, naming the bins; with
+        ``quiet=True`` those bins' rows are NaN instead.  ``self.autocorr_window [B]`` holds the accepted
+        window sizes (0: none)."""
+        tau = np.empty((self.n_bins, self.dim))
+        window = np.zeros(self.n_bins, dtype=np.int32)
+        chisq.check(self.lib, self.lib.mdaEnsembleAutocorrTime(self.handle, int(low), 0 if high is None else int(high), int(step),
+                                                               float(c), int(bool(fast)), tau.ctypes.data, window.ctypes.data),
+                    "mdaEnsembleAutocorrTime")
+        self.autocorr_window = window
+        if not quiet and np.any(window == 0):
+            bad = np.flatnonzero(window == 0)
+            raise AutocorrError("The chain is too short to reliably estimate the autocorrelation time (bins %s)"
+                                % ", ".join(str(b) for b in bad[:8]) + (" ..." if len(bad) > 8 else ""))
+        return tau
 
     def profile(self):
         """Per-bin debug counters [bins, 128] of the last advance (first call enables them; see

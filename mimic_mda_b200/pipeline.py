@@ -9,6 +9,7 @@ bins of a ``DeviceStore`` in a handful of launches:
     walker starts       fits.gen_walker_starts   (mda.py:1122, host numpy, once per bin)
     MCMC                mdaEnsembleAdvance       (mda.py:1128-1131; chain stays in HBM)
     summaries           mdaEnsembleSummarize     (mda.py:1253-1259, 1399-1491, 1316)
+    autocorrelation     mdaEnsembleAutocorrTime  (mda.py:1303-1310, if "Calc AutoCorr")
     chi^2 of estimates  mdaBatchChi              (calculate_fit_chis, mda.py:1321-1354)
 
 and returns, per bin, the tuple the reference's worker returns:
@@ -25,6 +26,7 @@ DEFAULTS = {
     "Number of Walkers": 2500, "Sample Points": 16385, "Burn-in Points": 512,
     "Number Walker Generators": 50, "Sample Spread": 2.0, "Sample Offset Centroid": 0.04,
     "Sample Offset Width": 0.02, "Confidence Interval": 0.682689492, "Num Bins": 1000,
+    "Calc AutoCorr": False, "ACorr WindSize": 3.0, "ACorr Use FFT": True,
 }
 
 
@@ -52,10 +54,13 @@ def fit_and_mcmc_all(store, start_params, config, ewsr=None, seed=0, bin_ids=Non
     # summaries on the device chain (perform_sample_manips, mda.py:1193-1318)
     summ = ens.summarize(cfg["Burn-in Points"] // thin, cfg["Confidence Interval"], cfg["Num Bins"])
     points, peaks = summ["points"], summ["peaks"]
+    # autocorrelation times of the whole chain (mda.py:1303-1310); emcee raises if the chain is too short
+    acor = ens.get_autocorr_time(c=cfg["ACorr WindSize"], fast=cfg["ACorr Use FFT"]) if cfg["Calc AutoCorr"] else None
     # chi^2 of the percentile and peak parameter sets (calculate_fit_chis, mda.py:1350-1353)
     chis = store.chi(np.stack([points[:, :, 0], peaks[:, :, 0]], axis=1))             # [B, 2]
     results = []
     for b in range(store.n_bins):
         values = ([tuple(points[b, l]) for l in range(n_l)], [tuple(peaks[b, l]) for l in range(n_l)])
-        results.append((values, ([], (float(chis[b, 0]), float(chis[b, 1])), float(summ["acceptance_fraction"][b]))))
+        acor_time = [] if acor is None else acor[b].copy()
+        results.append((values, (acor_time, (float(chis[b, 0]), float(chis[b, 1])), float(summ["acceptance_fraction"][b]))))
     return results, ens
