@@ -54,8 +54,10 @@ def fit_and_mcmc_all(store, start_params, config, ewsr=None, seed=0, bin_ids=Non
     # summaries on the device chain (perform_sample_manips, mda.py:1193-1318)
     summ = ens.summarize(cfg["Burn-in Points"] // thin, cfg["Confidence Interval"], cfg["Num Bins"])
     points, peaks = summ["points"], summ["peaks"]
-    # autocorrelation times of the whole chain (mda.py:1303-1310); emcee raises if the chain is too short
-    acor = ens.get_autocorr_time(c=cfg["ACorr WindSize"], fast=cfg["ACorr Use FFT"]) if cfg["Calc AutoCorr"] else None
+    # autocorrelation times of the whole chain (mda.py:1303-1310).  Where the chain is too short emcee raises inside
+    # the bin's worker; with every bin in one call the others' results are worth keeping: NaN times for that bin
+    acor = (ens.get_autocorr_time(c=cfg["ACorr WindSize"], fast=cfg["ACorr Use FFT"], quiet=True)
+            if cfg["Calc AutoCorr"] else None)
     # chi^2 of the percentile and peak parameter sets (calculate_fit_chis, mda.py:1350-1353)
     chis = store.chi(np.stack([points[:, :, 0], peaks[:, :, 0]], axis=1))             # [B, 2]
     results = []

@@ -6,7 +6,8 @@
 ``config.py`` is the reference's configuration format: a Python file that fills a ``CONFIG``
 dictionary (mda.py:50-53, config_example.py).  The keys on the likelihood path are honoured
 (input files, energy window, Max Theta, Maximum L, EWSR Fractions, IVGDR subtraction, start
-grid, walkers, sample points, burn-in, confidence interval, Num Bins); plotting, directory
+grid, walkers, sample points, burn-in, confidence interval, Num Bins, Calc AutoCorr / ACorr WindSize /
+ACorr Use FFT); plotting, directory
 and CSV-format keys are ignored -- this driver prints / saves the per-bin estimates that
 ``fit_and_mcmc`` returns (mda.py:1318) instead of the reference's plot and CSV tree.
 """
@@ -52,9 +53,14 @@ def main(argv=None):
     merged = shard.gather_results(results, n_bins)
     if rank == 0:
         table = []
-        for b, (values, (_, chis, acc)) in enumerate(merged):
+        for b, (values, (acor, chis, acc)) in enumerate(merged):
             row = {"Ex": inputs["energies"][b], "n_points": int(inputs["n_pts"][b]), "acceptance_fraction": acc,
                    "chi2_percentile": chis[0], "chi2_peak": chis[1]}
+            if len(acor):                                      # the diagnostics columns of mda.py:266-272
+                samples = config["Number of Walkers"] * (config["Sample Points"] - config["Burn-in Points"])
+                row["autocorr_times"] = [float(t) for t in acor]
+                row["num_ind_samples"] = float(samples) / max(acor)
+                row["dist_error"] = 1.0 / np.sqrt(row["num_ind_samples"])
             for l in range(n_l):
                 row["a%d" % l] = {"percentile": list(values[0][l]), "peak": list(values[1][l])}
             table.append(row)
