@@ -16,6 +16,8 @@ and returns, per bin, the tuple the reference's worker returns:
 ``((points, peaks), (acor_time, (perc_chi, peak_chi), accept_frac))``.  Only the walker
 starts go to the device and only the summaries come back.
 """
+import os
+
 import numpy as np
 
 from . import fits
@@ -27,13 +29,33 @@ DEFAULTS = {
     "Number Walker Generators": 50, "Sample Spread": 2.0, "Sample Offset Centroid": 0.04,
     "Sample Offset Width": 0.02, "Confidence Interval": 0.682689492, "Num Bins": 1000,
     "Calc AutoCorr": False, "ACorr WindSize": 3.0, "ACorr Use FFT": True,
+    "Save Chain Data": False, "Chain Directory": "chains", "Target A": 0,
 }
 
 
-def fit_and_mcmc_all(store, start_params, config, ewsr=None, seed=0, bin_ids=None, rng=None, thin=1):
+def chain_file_name(config, energy):
+    """The reference's per-bin chain dump (mda.py:1244-1249)."""
+    return os.path.join(config["Chain Directory"], "A{0:d}_chain_E{1:5.2f}.npz".format(config["Target A"], energy))
+
+
+def save_chains(ens, config, energies):
+    """``np.savez_compressed(name, sampler.chain)`` per bin, as perform_sample_manips does when
+    "Save Chain Data" is set (mda.py:1243-1250): ``arr_0`` is emcee's [walker, step, dim] array.  The chain is
+    pulled from HBM once (the fetch the ensemble caches)."""
+    chain = ens.chain                                     # [B, W, kept, L]
+    os.makedirs(config["Chain Directory"], exist_ok=True)
+    names = []
+    for b, energy in enumerate(energies):
+        names.append(chain_file_name(config, energy))
+        np.savez_compressed(names[-1], np.ascontiguousarray(chain[b]))
+    return names
+
+
+def fit_and_mcmc_all(store, start_params, config, ewsr=None, seed=0, bin_ids=None, rng=None, thin=1, energies=None):
     """Returns ``(results, ensemble)``; ``results[b]`` has the shape of the reference worker's
     return value for bin b (mda.py:1318).  ``config`` holds the reference's CONFIG keys (missing
-    ones take mda_config0.py's values); ``ewsr`` defaults to 1 for every multipole."""
+    ones take mda_config0.py's values); ``ewsr`` defaults to 1 for every multipole.  With "Save Chain Data" and the
+    bins' ``energies`` given, every bin's chain is also written in the reference's file format."""
     cfg = dict(DEFAULTS)
     cfg.update(config)
     n_l = store.n_l
@@ -51,6 +73,8 @@ def fit_and_mcmc_all(store, start_params, config, ewsr=None, seed=0, bin_ids=Non
     steps = cfg["Sample Points"]
     ens.reserve_chain(steps // thin)
     ens.advance(steps, thin)
+    if cfg["Save Chain Data"] and energies is not None:
+        save_chains(ens, cfg, energies)
     # summaries on the device chain (perform_sample_manips, mda.py:1193-1318)
     summ = ens.summarize(cfg["Burn-in Points"] // thin, cfg["Confidence Interval"], cfg["Num Bins"])
     points, peaks = summ["points"], summ["peaks"]

@@ -47,7 +47,8 @@ def main(argv=None):
     from . import chisq
     store = chisq.DeviceStore(inputs["consts"][mine], inputs["n_pts"][mine], inputs["bounds"])
     results, ens = pipeline.fit_and_mcmc_all(store, starts, config, ewsr=config["EWSR Fractions"][:n_l], seed=args.seed,
-                                             bin_ids=mine, rng=np.random.RandomState(args.seed + 7919 * rank), thin=args.thin)
+                                             bin_ids=mine, rng=np.random.RandomState(args.seed + 7919 * rank), thin=args.thin,
+                                             energies=[inputs["energies"][b] for b in mine])
     ens.close()
     store.close()
     merged = shard.gather_results(results, n_bins)

@@ -123,15 +123,21 @@ def test_device_autocorr_on_a_known_series(cs_lib):
 
 
 @pytest.mark.gpu
-def test_pipeline_returns_autocorr_times(cs_lib):
+def test_pipeline_returns_autocorr_times_and_dumps_chains(cs_lib, tmp_path):
     from mimic_mda_b200 import chisq, fits, pipeline, synth
     consts, counts, a_true = synth.make_bins(3, 4, 30)
     store = chisq.DeviceStore(consts, counts, synth.default_bounds(4), cs_lib=cs_lib)
     starts = fits.calc_start_params([[0.1, 0.4]] * 4)
     cfg = {"Number of Walkers": 64, "Sample Points": 2048, "Burn-in Points": 256, "Number Walker Generators": 4,
-           "Calc AutoCorr": True, "ACorr WindSize": 3.0, "ACorr Use FFT": True}
-    results, ens = pipeline.fit_and_mcmc_all(store, starts, cfg, seed=3)
+           "Calc AutoCorr": True, "ACorr WindSize": 3.0, "ACorr Use FFT": True,
+           "Save Chain Data": True, "Chain Directory": str(tmp_path / "chains"), "Target A": 116}
+    energies = [8.5, 9.5, 10.5]
+    results, ens = pipeline.fit_and_mcmc_all(store, starts, cfg, seed=3, energies=energies)
     chain = ens.chain
+    # the reference's per-bin dump (mda.py:1244-1249): arr_0 = sampler.chain, [walker, step, dim]
+    for b, energy in enumerate(energies):
+        with np.load(str(tmp_path / "chains" / ("A116_chain_E%5.2f.npz" % energy))) as z:
+            np.testing.assert_array_equal(z["arr_0"], chain[b])
     for b, (values, (acor, chis, acc)) in enumerate(results):
         np.testing.assert_allclose(acor, ao.get_autocorr_time(chain[b], c=3.0, fast=True), rtol=TAU_RTOL)
         assert len(acor) == 4 and max(acor) > 1.0        # what write_fit_diagnostics divides by (mda.py:269)
