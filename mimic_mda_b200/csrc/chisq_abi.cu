@@ -1209,6 +1209,19 @@ int mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double
 }
 
 namespace {
+struct StageTimer {
+    bool on = getenv("MDA_SUMMARY_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mda summary] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
+namespace {
 
 // Device scratch owned by the ensemble: one allocation reused by every summary call.
 int ensure_scratch(MdaEnsemble *e, size_t bytes) {
@@ -1256,7 +1269,7 @@ double numpy_lerp(double a, double b, double t) {
 
 // Exact order statistics for `n_ranks` ranks per column (ranks[cols][n_ranks]) -> values.
 int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<unsigned long long> &mm,
-                 const std::vector<long long> &ranks, int n_ranks, std::vector<double> &values) {
+                 const std::vector<long long> &ranks, int n_ranks, std::vector<double> &values, StageTimer &timer) {
     MdaStore *s = e->store;
     const size_t cols = (size_t)s->bins * (size_t)s->n_l, n_state = cols * (size_t)n_ranks;
     std::vector<int> top(cols);
@@ -1305,6 +1318,7 @@ int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<u
     if (err == cudaSuccess) err = cudaMemcpyAsync(count.data(), d.count, 4 * n_state, cudaMemcpyDeviceToHost, s->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
     if (err != cudaSuccess) return cuda_fail(err, "order-statistic selection (first pass)");
+    timer.lap("  first digit pass");
     g_launches.fetch_add(2, std::memory_order_relaxed);
     // buckets in play: ranks of a column that fell into the same bucket share one buffer
     std::vector<unsigned char> lead(n_state, 0);
@@ -1340,25 +1354,13 @@ int select_ranks(MdaEnsemble *e, long long k0, long long k1, const std::vector<u
     if (err == cudaSuccess) err = cudaMemcpyAsync(prefix.data(), d.prefix, 8 * n_state, cudaMemcpyDeviceToHost, s->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
     if (err != cudaSuccess) return cuda_fail(err, "order-statistic selection (gather / finish)");
+    timer.lap("  gather + finish");
     g_launches.fetch_add(2, std::memory_order_relaxed);
     values.resize(n_state);
     for (size_t i = 0; i < n_state; ++i) values[i] = key_to_double(prefix[i]);
     return MDA_OK;
 }
 
-}  // namespace
-
-namespace {
-struct StageTimer {
-    bool on = getenv("MDA_SUMMARY_TIMING") != nullptr;
-    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-    void lap(const char *what) {
-        if (!on) return;
-        const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[mda summary] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
-        t = now;
-    }
-};
 }  // namespace
 
 int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterval, int numBins,
@@ -1452,7 +1454,7 @@ int mdaEnsembleSummarize(void *ens, long long firstKept, double confidenceInterv
         }
     }
     std::vector<double> vals;
-    if ((rc = select_ranks(e, k0, k1, mm, ranks, n_ranks, vals))) return rc;
+    if ((rc = select_ranks(e, k0, k1, mm, ranks, n_ranks, vals, timer))) return rc;
     for (size_t c = 0; c < cols; ++c) {
         double v[6];
         for (int i = 0; i < n_ranks / 2; ++i)

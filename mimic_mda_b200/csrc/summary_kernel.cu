@@ -16,9 +16,15 @@
 // interpolation) is evaluated on the host from these exact order statistics.
 #include "mda_kernels.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace mda {
 
 namespace {
+
+constexpr int kDigitBits = 12;
+constexpr int kDigits = 1 << kDigitBits;
 
 __device__ __forceinline__ unsigned long long to_key(double x) {
     const unsigned long long u = (unsigned long long)__double_as_longlong(x);
@@ -34,22 +40,34 @@ struct ChainView {
     int bins, walkers, n_l;
 };
 
-// Visit every sample of column (bin, l) owned by this thread: four independent loads are in
-// flight per thread, enough bytes in flight per SM to run at HBM rate with ~1000 threads.
+// Visit every sample of column (bin, l) owned by this thread: eight independent loads are in
+// flight per thread (64 B; ~2000 resident threads per SM keep > 100 KB in flight, HBM rate).
 template <typename F>
 __device__ __forceinline__ void for_each_sample(const ChainView &v, int bin, int l, F visit) {
-    const int stride = blockDim.y;
-    for (long long k = v.k0 + blockIdx.y; k < v.k1; k += gridDim.y) {
+    // The rows of the block (blockDim.y) split into G groups that take different kept samples, so that a
+    // thread's share of a slab is about one batch of eight loads whatever the block and ensemble sizes.
+    int G = ((int)blockDim.y * 8 + v.walkers / 2) / v.walkers;
+    G = G < 1 ? 1 : (G > (int)blockDim.y ? (int)blockDim.y : G);
+    const int stride = (int)blockDim.y / G;
+    const int g = (int)threadIdx.y / stride, wy = (int)threadIdx.y % stride;
+    if (g >= G) return;
+    for (long long k = v.k0 + (long long)blockIdx.y * G + g; k < v.k1; k += (long long)gridDim.y * G) {
         const double *slab = v.chain + ((size_t)k * v.bins + bin) * v.walkers * v.n_l + l;
-        int w = threadIdx.y;
-        for (; w + 3 * stride < v.walkers; w += 4 * stride) {
-            const double x0 = slab[(size_t)w * v.n_l];
-            const double x1 = slab[(size_t)(w + stride) * v.n_l];
-            const double x2 = slab[(size_t)(w + 2 * stride) * v.n_l];
-            const double x3 = slab[(size_t)(w + 3 * stride) * v.n_l];
-            visit(x0); visit(x1); visit(x2); visit(x3);
+        int w = wy;
+        for (; w + 7 * stride < v.walkers; w += 8 * stride) {
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __ldcs(slab + (size_t)(w + i * stride) * v.n_l);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) visit(x[i]);
         }
-        for (; w < v.walkers; w += stride) visit(slab[(size_t)w * v.n_l]);
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (w + i * stride < v.walkers) x[i] = __ldcs(slab + (size_t)(w + i * stride) * v.n_l);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (w + i * stride < v.walkers) visit(x[i]);
     }
 }
 
@@ -76,24 +94,43 @@ __global__ void __launch_bounds__(256) minmax_kernel(ChainView v, unsigned long 
 // numpy.histogram(values, bins=n_bins) for every column: the bin of x is
 // floor((x - first) / (last - first) * n_bins), corrected against the linspace edges exactly
 // as numpy does; edges[col][n_bins + 1] are computed on the host with numpy's formula.
+// SMEM: the CTA counts into a private copy [L][n_bins] in shared memory and adds its non-zero
+// counts to the global histogram once (global atomics: one per populated bin and CTA instead of one per sample).
+template <bool SMEM>
 __global__ void __launch_bounds__(256) hist_kernel(ChainView v, const double *__restrict__ edges, int n_bins,
                                                    unsigned int *__restrict__ hist) {
+    extern __shared__ unsigned int s_hist[];
     const int l = threadIdx.x, bin = blockIdx.x;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     const size_t col = (size_t)bin * v.n_l + l;
     const double *e = edges + col * (size_t)(n_bins + 1);
     const double first = e[0], last = e[n_bins];
     const double norm = (double)n_bins / (last - first);
-    unsigned int *h = hist + col * (size_t)n_bins;
-    if (!(last > first)) return;
-    for_each_sample(v, bin, l, [&](double x) {
-        // any estimate within one bin of the truth will do: numpy corrects its own estimate
-        // against the edges in exactly this way
-        int idx = (int)((x - first) * norm);
-        idx = idx < 0 ? 0 : (idx >= n_bins ? n_bins - 1 : idx);
-        if (x < e[idx]) idx -= 1;
-        else if (idx != n_bins - 1 && x >= e[idx + 1]) idx += 1;
-        atomicAdd(&h[idx], 1u);
-    });
+    // numpy.linspace's edges (edges_kernel) recomputed in registers: two fp64 operations instead of a
+    // data-dependent load per comparison (32 distinct sectors per warp made the loads the bottleneck)
+    const double step = __ddiv_rn(__dsub_rn(last, first), (double)n_bins);
+    auto edge = [&](int i) { return i == n_bins ? last : __dadd_rn(__dmul_rn((double)i, step), first); };
+    unsigned int *h = SMEM ? s_hist + (size_t)l * n_bins : hist + col * (size_t)n_bins;
+    if (SMEM) {
+        for (int i = tid; i < v.n_l * n_bins; i += nthr) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    if (last > first)
+        for_each_sample(v, bin, l, [&](double x) {
+            // any estimate within one bin of the truth will do: numpy corrects its own estimate
+            // against the edges in exactly this way
+            int idx = (int)((x - first) * norm);
+            idx = idx < 0 ? 0 : (idx >= n_bins ? n_bins - 1 : idx);
+            if (x < edge(idx)) idx -= 1;
+            else if (idx != n_bins - 1 && x >= edge(idx + 1)) idx += 1;
+            atomicAdd(&h[idx], 1u);
+        });
+    if (SMEM) {
+        __syncthreads();
+        unsigned int *g = hist + (size_t)bin * v.n_l * (size_t)n_bins;
+        for (int i = tid; i < v.n_l * n_bins; i += nthr)
+            if (s_hist[i]) atomicAdd(&g[i], s_hist[i]);
+    }
 }
 
 // numpy.linspace(first, last, n_bins + 1) per column, with numpy's two roundings per edge
@@ -149,9 +186,6 @@ __global__ void __launch_bounds__(256) peak_kernel(const unsigned int *__restric
     if (threadIdx.x == 0) { peak_bin[col] = ind; peak_cum[col] = s_sum[0]; }
 }
 
-constexpr int kDigitBits = 12;
-constexpr int kDigits = 1 << kDigitBits;
-
 // ---- exact order statistics ---------------------------------------------------------------
 // Keys of a column differ only in their low top[col] bits (everything above is shared by the
 // column's min and max).  Selection of up to kMaxRanks ranks per column:
@@ -162,18 +196,33 @@ constexpr int kDigits = 1 << kDigitBits;
 //                          are appended to exactly-sized buffers (offsets from the counts)
 //   4. finish_kernel       one CTA per (column, rank) finishes the radix selection on its
 //                          bucket buffer, 8 bits per pass
-__global__ void __launch_bounds__(256) first_hist_kernel(ChainView v, const int *__restrict__ top,
-                                                         unsigned int *__restrict__ hist) {
+// SMEM: private counts [L][4096] in shared memory (147 KB at L = 9: one CTA of ~1000 threads per SM),
+// non-zero counts added to the global histogram once per CTA.
+template <bool SMEM>
+__global__ void __launch_bounds__(1024) first_hist_kernel(ChainView v, const int *__restrict__ top,
+                                                          unsigned int *__restrict__ hist) {
+    extern __shared__ unsigned int s_hist[];
     const int l = threadIdx.x, bin = blockIdx.x;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     const size_t col = (size_t)bin * v.n_l + l;
     const int hi_bit = top[col];
-    if (hi_bit <= 0) return;
     const int lo_bit = hi_bit > kDigitBits ? hi_bit - kDigitBits : 0;
-    const unsigned long long digit_mask = (1ull << (hi_bit - lo_bit)) - 1ull;
-    unsigned int *h = hist + col * kDigits;
-    for_each_sample(v, bin, l, [&](double x) {
-        atomicAdd(&h[(unsigned int)((to_key(x) >> lo_bit) & digit_mask)], 1u);
-    });
+    const unsigned long long digit_mask = hi_bit > 0 ? (1ull << (hi_bit - lo_bit)) - 1ull : 0ull;
+    unsigned int *h = SMEM ? s_hist + (size_t)l * kDigits : hist + col * kDigits;
+    if (SMEM) {
+        for (int i = tid; i < v.n_l * kDigits; i += nthr) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    if (hi_bit > 0)
+        for_each_sample(v, bin, l, [&](double x) {
+            atomicAdd(&h[(unsigned int)((to_key(x) >> lo_bit) & digit_mask)], 1u);
+        });
+    if (SMEM) {
+        __syncthreads();
+        unsigned int *g = hist + (size_t)bin * v.n_l * kDigits;
+        for (int i = tid; i < v.n_l * kDigits; i += nthr)
+            if (s_hist[i]) atomicAdd(&g[i], s_hist[i]);
+    }
 }
 
 struct SelectState {
@@ -216,38 +265,35 @@ __global__ void __launch_bounds__(256) first_scan_kernel(SelectState st, const u
 
 // lead[cols][R]: 1 if this rank owns its bucket's buffer (ranks in the same bucket share the
 // first one's); offset[cols][R]: start of the buffer; cursor[cols][R]: append position.
-template <int NR>
+// A sample is in play if its first digit is that of a bucket in play (every key of a column shares the bits above
+// top[col], so the digit identifies the bucket): a byte per digit and column in shared memory holds the owning
+// rank + 1, or 0 for the ~90-99 % of the samples that are in no bucket.  (Comparing every key with up to 12
+// prefixes made this pass instruction bound.)
 __global__ void __launch_bounds__(256) gather_kernel(ChainView v, SelectState st, const unsigned char *__restrict__ lead,
                                                      const long long *__restrict__ offset, unsigned int *__restrict__ cursor,
                                                      unsigned long long *__restrict__ buf) {
+    extern __shared__ unsigned char s_slot[];            // [L][4096]
     const int l = threadIdx.x, bin = blockIdx.x;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     const size_t col = (size_t)bin * v.n_l + l;
     const int hi_bit = st.top[col];
-    if (hi_bit <= kDigitBits) return;                    // nothing left to decide below the first digit
-    const unsigned long long above = ~0ull << (hi_bit - kDigitBits);
-    unsigned long long pre[NR];
-    long long off[NR];
-    unsigned int is_lead = 0;
-    unsigned long long pre_min = ~0ull, pre_max = 0ull;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const bool on = r < st.n_ranks && lead[col * st.n_ranks + (r < st.n_ranks ? r : 0)];
-        pre[r] = on ? st.prefix[col * st.n_ranks + r] : ~0ull;
-        off[r] = on ? offset[col * st.n_ranks + r] : 0;
-        if (on) {
-            is_lead |= 1u << r;
-            pre_min = pre[r] < pre_min ? pre[r] : pre_min;
-            pre_max = pre[r] > pre_max ? pre[r] : pre_max;
-        }
-    }
-    unsigned int *cur = cursor + col * st.n_ranks;
+    const bool active = hi_bit > kDigitBits;             // else nothing is left to decide below the first digit
+    const int lo_bit = active ? hi_bit - kDigitBits : 0;
+    for (int i = tid; i < v.n_l * (kDigits / 4); i += nthr) reinterpret_cast<unsigned int *>(s_slot)[i] = 0u;
+    __syncthreads();
+    const size_t base = col * st.n_ranks;
+    unsigned char *slot = s_slot + (size_t)l * kDigits;
+    if (active && threadIdx.y == 0)
+        for (int r = 0; r < st.n_ranks; ++r)
+            if (lead[base + r]) slot[(unsigned int)(st.prefix[base + r] >> lo_bit) & (kDigits - 1)] = (unsigned char)(r + 1);
+    __syncthreads();
+    if (!active) return;
+    unsigned int *cur = cursor + base;
+    const long long *off = offset + base;
     for_each_sample(v, bin, l, [&](double x) {
         const unsigned long long key = to_key(x);
-        const unsigned long long kp = key & above;
-        if (kp < pre_min || kp > pre_max) return;        // outside every bucket in play
-#pragma unroll
-        for (int r = 0; r < NR; ++r)
-            if ((is_lead >> r & 1u) && kp == pre[r]) buf[off[r] + atomicAdd(&cur[r], 1u)] = key;
+        const unsigned int r1 = slot[(unsigned int)(key >> lo_bit) & (kDigits - 1)];
+        if (r1) buf[off[r1 - 1] + atomicAdd(&cur[r1 - 1], 1u)] = key;
     });
 }
 
@@ -290,18 +336,34 @@ __global__ void __launch_bounds__(256) finish_kernel(SelectState st, const long 
 
 }  // namespace
 
-static dim3 summary_block(int n_l) {
-    int ty = 256 / n_l;
+static dim3 summary_block(int n_l, int threads = 256) {
+    int ty = threads / n_l;
     if (ty < 1) ty = 1;
     return dim3((unsigned)n_l, (unsigned)ty);
 }
 
-static dim3 summary_grid(int bins, long long kept, int sm_count) {
-    long long chunks = (4LL * sm_count + bins - 1) / (bins > 0 ? bins : 1);
+// grid = (bins, chunks): about `per_sm` CTAs per SM and `rounds` rounds of them, so that the last round's
+// partial occupancy costs little.
+static dim3 summary_grid(int bins, long long kept, int sm_count, int per_sm = 8, int rounds = 2) {
+    long long chunks = ((long long)per_sm * rounds * sm_count + bins - 1) / (bins > 0 ? bins : 1);
     if (chunks > kept) chunks = kept;
     if (chunks < 1) chunks = 1;
     if (chunks > 65535) chunks = 65535;
     return dim3((unsigned)bins, (unsigned)chunks);
+}
+
+// Dynamic shared memory a kernel may use (opt-in limit minus its static part), raised once per kernel.
+template <typename K>
+static size_t smem_room(K kernel) {
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(kernel)) != cudaSuccess)
+        return 0;
+    const size_t room = (size_t)optin - fa.sharedSizeBytes;
+    if (cudaFuncSetAttribute(reinterpret_cast<const void *>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room) != cudaSuccess)
+        return 0;
+    return room;
 }
 
 cudaError_t launch_chain_minmax(const double *chain, long long k0, long long k1, int bins, int walkers, int n_l,
@@ -323,7 +385,12 @@ cudaError_t launch_chain_hist(const double *chain, long long k0, long long k1, i
     cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(unsigned int) * cols * (size_t)n_bins, stream);
     if (e != cudaSuccess) return e;
     edges_kernel<<<(unsigned)cols, 256, 0, stream>>>(minmax, n_bins, edges);
-    hist_kernel<<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, edges, n_bins, hist);
+    static const size_t room = smem_room(hist_kernel<true>);
+    const size_t need = sizeof(unsigned int) * (size_t)n_l * (size_t)n_bins;
+    if (need <= room && need <= 56 * 1024)               // four or more CTAs per SM next to the private counts
+        hist_kernel<true><<<summary_grid(bins, k1 - k0, sm_count, 4, 3), summary_block(n_l), need, stream>>>(v, edges, n_bins, hist);
+    else
+        hist_kernel<false><<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, edges, n_bins, hist);
     peak_kernel<<<(unsigned)cols, 256, 0, stream>>>(hist, n_bins, peak_bin, peak_cum);
     return cudaGetLastError();
 }
@@ -338,7 +405,12 @@ cudaError_t launch_select_first(const double *chain, long long k0, long long k1,
     const size_t cols = (size_t)bins * n_l;
     cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(unsigned int) * cols * kDigits, stream);
     if (e != cudaSuccess) return e;
-    first_hist_kernel<<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, top, hist);
+    static const size_t room = smem_room(first_hist_kernel<true>);
+    const size_t need = sizeof(unsigned int) * (size_t)n_l * kDigits;
+    if (need <= room)                                    // one CTA of up to 1024 threads per SM
+        first_hist_kernel<true><<<summary_grid(bins, k1 - k0, sm_count, 1, 8), summary_block(n_l, 1024), need, stream>>>(v, top, hist);
+    else
+        first_hist_kernel<false><<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, top, hist);
     first_scan_kernel<<<dim3((unsigned)cols, (unsigned)n_ranks), 256, 0, stream>>>(st, hist);
     return cudaGetLastError();
 }
@@ -353,11 +425,22 @@ cudaError_t launch_select_finish(const double *chain, long long k0, long long k1
     const size_t cols = (size_t)bins * n_l;
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int) * cols * n_ranks, stream);
     if (e != cudaSuccess) return e;
-    if (n_ranks <= 6)
-        gather_kernel<6><<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, st, lead, offset, cursor, buf);
-    else
-        gather_kernel<kMaxRanks><<<summary_grid(bins, k1 - k0, sm_count), summary_block(n_l), 0, stream>>>(v, st, lead, offset, cursor, buf);
+    static const size_t room = smem_room(gather_kernel);
+    const size_t need = (size_t)n_l * kDigits;
+    if (need > room) return cudaErrorInvalidValue;       // n_l <= 32 is 128 KB
+    gather_kernel<<<summary_grid(bins, k1 - k0, sm_count, 4, 3), summary_block(n_l), need, stream>>>(v, st, lead, offset, cursor, buf);
+    static const bool timing = getenv("MDA_SUMMARY_TIMING") != nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing) { for (auto &x : ev) cudaEventCreate(&x); cudaEventRecord(ev[1], stream); }
     finish_kernel<<<dim3((unsigned)cols, (unsigned)n_ranks), 256, 0, stream>>>(st, offset, buf);
+    if (timing) {
+        cudaEventRecord(ev[2], stream);
+        cudaEventSynchronize(ev[2]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]);
+        fprintf(stderr, "[mda summary]     finish_kernel alone        %8.3f ms\n", ms);
+        for (auto &x : ev) cudaEventDestroy(x);
+    }
     return cudaGetLastError();
 }
 
