@@ -389,14 +389,6 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
 #pragma unroll
                     for (int n = 0; n < NLE; ++n) myl[n] = __dsub_rn(cl[n], __dmul_rn(pzl[n], __dsub_rn(cl[n], pxl[n])));
                 }
-                // the rows the walker warps copy on acceptance
-#pragma unroll
-                for (int k = 0; k < WT; ++k)
-#pragma unroll
-                    for (int ks = 0; ks < Q; ++ks) sQ[wi[k] * L + R + 4 * ks + tig] = A[k][ks];
-#pragma unroll
-                for (int n = 0; n < NLE; ++n)
-                    if (tig + 4 * n < WT * R) sQ[lw[n] * L + ll[n]] = myl[n];
 #pragma unroll
                 for (int k = 0; k < WT; ++k)
 #pragma unroll
@@ -407,9 +399,24 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                         lead[k][l] = __shfl_sync(0xffffffffu, myl[j / 4], (lane & ~3) | (j & 3));
                     }
                 MDA_STAMP_AFTER(1, A[WT - 1][Q - 1])
+                double chi0[WT], chi1[WT];
+#pragma unroll
+                for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
+                // Staging the proposals for the walker warps and the box prior are independent of the contraction: placed
+                // in the middle of it (8 angle tiles: two unrolled halves) their shared-memory traffic and compares
+                // issue under the DMMA stream instead of ahead of it.
+                bool outside;
+                auto stage_and_test = [&]() {
+                // the rows the walker warps copy on acceptance
+#pragma unroll
+                for (int k = 0; k < WT; ++k)
+#pragma unroll
+                    for (int ks = 0; ks < Q; ++ks) sQ[wi[k] * L + R + 4 * ks + tig] = A[k][ks];
+#pragma unroll
+                for (int n = 0; n < NLE; ++n)
+                    if (tig + 4 * n < WT * R) sQ[lw[n] * L + ll[n]] = myl[n];
                 // box prior (mda.py:1575) on these registers: any component below lo or above hi (a NaN compares
                 // false, as in the reference).  Lane tig will report the walker g of tile tig % WT.
-                bool outside;
                 {
                     uint32_t out_of[WT];
 #pragma unroll
@@ -426,11 +433,15 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                     for (int k = 1; k < WT; ++k) mine = (tig & (WT - 1)) == k ? out_of[k] : mine;
                     outside = ((mine >> (4 * g)) & 0xfu) != 0u;
                 }
-                double chi0[WT], chi1[WT];
-#pragma unroll
-                for (int k = 0; k < WT; ++k) { chi0[k] = 0.0; chi1[k] = 0.0; }
-                if (NT == 8) chi_tiles<L, WT, 8>(sC, 8, lane, A, lead, chi0, chi1);
-                else chi_tiles<L, WT, 0>(sC, NT, lane, A, lead, chi0, chi1);
+                };
+                if (NT == 8) {                             // one straight-line block: the scheduler interleaves the three parts
+                    chi_tiles<L, WT, 4>(sC, 4, lane, A, lead, chi0, chi1);
+                    stage_and_test();
+                    chi_tiles<L, WT, 4>(sC + 4 * TS, 4, lane, A, lead, chi0, chi1);
+                } else {
+                    stage_and_test();
+                    chi_tiles<L, WT, 0>(sC, NT, lane, A, lead, chi0, chi1);
+                }
                 // quad sums by a transposing butterfly: lane tig ends up with the sum of tile tig % WT
                 double sum;
                 if (WT == 4) {
