@@ -116,6 +116,7 @@ int ensure_runtime() {
     MDA_CUDA(configure_lnpost_mma_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, DMMA batch)");
     MDA_CUDA(configure_ensemble_mma_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, DMMA ensemble)");
     MDA_CUDA(configure_ensemble_ws_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, warp-specialised DMMA ensemble)");
+    MDA_CUDA(configure_ensemble_quad_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, triangular-factor ensemble)");
     g_rt.ready = true;
     return MDA_OK;
 }
@@ -193,6 +194,8 @@ struct MdaStore {
     std::vector<double> host;        // [bins][n_pad/2][1+L][2]  (the HBM layout)
     std::vector<double> host_mma;    // [bins][n_tiles][8 (1+L)]  fragment-major copy for the DMMA stepper
     int n_tiles = 0;                 // angle tiles of 8
+    std::vector<double> host_quad;   // [bins][(L+1)(L+2)/2]  packed triangular factor of [D^T | d] (see factor_bin)
+    double *d_quad = nullptr;
     std::vector<int> n_pts;          // [bins]
     std::vector<double> lo, hi;      // [L]
     double *d_consts = nullptr;
@@ -253,8 +256,50 @@ void write_bin(MdaStore *s, int bin, int n, const double *data, const double *di
     s->dirty = true;
 }
 
+// chi^2(a) = |d - D^T a|^2 (C/ChiSquare.c:188-210) is |M [a; -1]|^2 with M = [D^T | d] (N x (L+1)), and M = Q T with
+// T upper triangular gives chi^2(a) = |T [a; -1]|^2: (L+1)(L+2)/2 multiply-adds per evaluation instead of N (L+1),
+// whatever N is.  No inverse is taken (rank-deficient bins are fine) and every term is a square, so there is no
+// cancellation beyond the one inside a row, which is that of the residuals themselves.  T comes from Householder
+// reflections in long double (64-bit mantissa) and is rounded to double once; packed by rows: T[i][i..L].
+void factor_bin(const MdaStore *s, int bin, double *packed) {
+    const int n = s->n_pts[bin], L = s->n_l, C = L + 1, row = L + 1;
+    const double *blk = s->host.data() + (size_t)bin * bin_stride(s);
+    const int rows = std::max(n, C);
+    std::vector<long double> m((size_t)rows * C, 0.0L);
+    for (int j = 0; j < n; ++j) {
+        const double *cell = blk + ((size_t)(j >> 1) * row) * 2 + (j & 1);
+        for (int l = 0; l < L; ++l) m[(size_t)j * C + l] = cell[(size_t)(1 + l) * 2];
+        m[(size_t)j * C + L] = cell[0];
+    }
+    for (int k = 0; k < C; ++k) {                                    // Householder reflection k zeroes column k below the diagonal
+        long double norm2 = 0.0L;
+        for (int j = k; j < rows; ++j) norm2 += m[(size_t)j * C + k] * m[(size_t)j * C + k];
+        if (norm2 == 0.0L) continue;
+        const long double norm = sqrtl(norm2), x0 = m[(size_t)k * C + k];
+        const long double alpha = x0 > 0.0L ? -norm : norm;
+        std::vector<long double> v((size_t)rows - k);
+        for (int j = k; j < rows; ++j) v[j - k] = m[(size_t)j * C + k];
+        v[0] -= alpha;
+        long double vv = 0.0L;
+        for (long double x : v) vv += x * x;
+        if (vv == 0.0L) continue;
+        for (int c = k; c < C; ++c) {
+            long double dot = 0.0L;
+            for (int j = k; j < rows; ++j) dot += v[j - k] * m[(size_t)j * C + c];
+            const long double f = 2.0L * dot / vv;
+            for (int j = k; j < rows; ++j) m[(size_t)j * C + c] -= f * v[j - k];
+        }
+    }
+    size_t o = 0;
+    for (int i = 0; i < C; ++i)
+        for (int c = i; c < C; ++c) packed[o++] = (double)m[(size_t)i * C + c];
+}
+
 int upload_store(MdaStore *s) {
     if (!s->dirty) return MDA_OK;
+    for (int b = 0; b < s->bins; ++b) factor_bin(s, b, s->host_quad.data() + (size_t)b * (size_t)quad_doubles(s->n_l));
+    MDA_CUDA(cudaMemcpyAsync(s->d_quad, s->host_quad.data(), sizeof(double) * s->host_quad.size(), cudaMemcpyHostToDevice,
+                             s->stream), "store upload (triangular factors)");
     MDA_CUDA(cudaMemcpyAsync(s->d_consts, s->host.data(), sizeof(double) * s->host.size(), cudaMemcpyHostToDevice,
                              s->stream), "store upload (constants)");
     MDA_CUDA(cudaMemcpyAsync(s->d_consts_mma, s->host_mma.data(), sizeof(double) * s->host_mma.size(), cudaMemcpyHostToDevice,
@@ -445,8 +490,10 @@ struct MdaEnsemble {
 EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
     const bool want_dfma = impl && strcmp(impl, "dfma") == 0, want_ws = impl && strcmp(impl, "ws") == 0,
-               want_mma = impl && strcmp(impl, "mma") == 0;
+               want_mma = impl && strcmp(impl, "mma") == 0, want_quad = impl && strcmp(impl, "quad") == 0;
     EnsembleShape shape{};
+    // default: the triangular-factor stepper (fewest operations per evaluation, same chains); the others on request
+    if ((want_quad || !(want_dfma || want_ws || want_mma)) && choose_ensemble_quad_shape(walkers, s->n_l, g_rt.smem_optin, &shape)) return shape;
     if (!want_dfma) {
         const bool prefer_mma = want_mma || (!want_ws && s->bins >= 2 * g_rt.sm_count);
         const int wt = env_int("MDA_ENS_WT", 0);
@@ -651,12 +698,14 @@ void *mdaStoreCreate(int numBins, int numL, int maxPts) {
     s->host.assign((size_t)numBins * bin_stride(s), 0.0);
     s->n_tiles = (s->n_pad + 7) / 8;
     s->host_mma.assign((size_t)numBins * (size_t)s->n_tiles * 8 * (size_t)(numL + 1), 0.0);
+    s->host_quad.assign((size_t)numBins * (size_t)quad_doubles(numL), 0.0);
     s->n_pts.assign((size_t)numBins, 0);
     s->lo.assign((size_t)numL, 0.0);
     s->hi.assign((size_t)numL, 1.0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_consts, sizeof(double) * (s->host.size() ? s->host.size() : 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_consts_mma, sizeof(double) * (s->host_mma.size() ? s->host_mma.size() : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_quad, sizeof(double) * (s->host_quad.size() ? s->host_quad.size() : 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_npts, sizeof(int) * (size_t)(numBins ? numBins : 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_lo, sizeof(double) * (size_t)numL);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_hi, sizeof(double) * (size_t)numL);
@@ -676,6 +725,7 @@ void mdaStoreFree(void *store) {
     if (s->d_out) cudaFree(s->d_out);
     if (s->d_consts) cudaFree(s->d_consts);
     if (s->d_consts_mma) cudaFree(s->d_consts_mma);
+    if (s->d_quad) cudaFree(s->d_quad);
     if (s->d_npts) cudaFree(s->d_npts);
     if (s->d_lo) cudaFree(s->d_lo);
     if (s->d_hi) cudaFree(s->d_hi);
@@ -1032,8 +1082,11 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
     args.consts_mma = s->d_consts_mma;
     args.n_tiles = s->n_tiles;
+    args.quad = s->d_quad;
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
-    if (shape.mma) {
+    if (shape.quad) {
+        MDA_CUDA(launch_ensemble_quad(args, shape, g_rt.sm_count, s->stream), "ensemble stepping launch (triangular factor)");
+    } else if (shape.mma) {
         const SteppingPlan plan = plan_stepping(s, shape, nSteps);
         if (plan.grid < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
         args.chunk_steps = plan.chunk_steps;
@@ -1060,7 +1113,12 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
     if (rc) return rc;
     MdaStore *s = e->store;
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
-    if (shape.mma) {
+    if (shape.quad) {
+        snprintf(text, (size_t)textLen,
+                 "ensemble_quad_kernel<L=%d>: chi^2 = |T [a; -1]|^2 from the bin's triangular factor (%d multiply-adds per evaluation), %d threads x %d walkers, "
+                 "one barrier per half-step, bulk-TMA chain stores, %zu B shared memory; one CTA per bin (%d)",
+                 s->n_l, quad_doubles(s->n_l), shape.threads, shape.wpt, shape.smem_bytes, s->bins);
+    } else if (shape.mma) {
         const SteppingPlan plan = plan_stepping(s, shape, nSteps);
         if (shape.ws)
             snprintf(text, (size_t)textLen,

@@ -64,6 +64,7 @@ cudaError_t launch_batch_mma(BatchArgs &args, int sm_count, cudaStream_t stream,
 struct EnsembleArgs {
     const double *consts;      // store layout [bins][n_pad/2][1+L][2]
     const double *consts_mma;  // fragment-major copy [bins][n_tiles][8 (1+L)] (see mma_tile_doubles), or null
+    const double *quad;        // [bins][quad_doubles(L)] packed triangular factor T of [D^T | d]: chi^2(a) = |T [a; -1]|^2, or null
     const int *n_pts;          // [bins]
     const int *bin_ids;        // [bins] global bin index (Philox counter word; partition invariant)
     double *pos;               // [bins][W][L]   ensemble state, updated in place
@@ -96,7 +97,10 @@ struct EnsembleShape {
     bool global_state;         // positions / log-probabilities stay in HBM (ensemble too large for shared memory)
     bool mma;                  // a DMMA stepper (wpt = tiles of 8 walkers per item)
     bool ws;                   // the warp-specialised one, ensemble_ws_kernel (groups = walker warps); else ensemble_mma_kernel
+    bool quad;                 // ensemble_quad_kernel: chi^2 from the bin's triangular factor, one thread per walker
 };
+
+__host__ __device__ constexpr int quad_doubles(int n_l) { return (n_l + 1) * (n_l + 2) / 2; }
 
 EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, int sm_count, size_t smem_optin,
                                     int force_groups, int force_wpt);
@@ -120,6 +124,11 @@ bool choose_ensemble_ws_shape(int bins, int walkers, int n_l, int n_tiles, int s
 cudaError_t configure_ensemble_ws_kernels(size_t smem_optin);
 int ensemble_ws_capacity(int n_l, const EnsembleShape &shape, int sm_count);
 cudaError_t launch_ensemble_ws(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);
+
+// ensemble_quad_kernel.cu: one CTA per bin at a time, one thread per walker of the half being updated.
+bool choose_ensemble_quad_shape(int walkers, int n_l, size_t smem_optin, EnsembleShape *out);
+cudaError_t configure_ensemble_quad_kernels(size_t smem_optin);
+cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int sm_count, cudaStream_t stream);
 
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
 // gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.

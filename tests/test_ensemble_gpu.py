@@ -25,7 +25,8 @@ def _problem(n_bins, n_l, n_pts, walkers, ragged=True, seed=17):
                                    # ensembles larger than shared memory (state in HBM/L2): the reference's own
                                    # 2500 walkers x 8 parameters (mda_config0.py:93,105), and a wider one
                                    (1, 8, 41, 2500, 12), (2, 9, 60, 3000, 6)])
-@pytest.mark.parametrize("impl", ["ws", "mma", "mma-2cta"])   # the DMMA steppers (shapes none takes run on the DFMA stepper)
+# the triangular-factor stepper (the default) and the DMMA steppers (shapes none of those takes run on the DFMA stepper)
+@pytest.mark.parametrize("impl", ["quad", "ws", "mma", "mma-2cta"])
 def test_device_chain_equals_cpu_restatement(cs_lib, oracle_lib, monkeypatch, shape, impl):
     monkeypatch.setenv("MDA_ENS_IMPL", impl.split("-")[0])
     monkeypatch.setenv("MDA_ENS_DRAWW", "2" if impl.endswith("2cta") else "0")     # 2: without draw warps (two CTAs per SM)
@@ -93,13 +94,14 @@ def test_split_runs_thinning_and_partition_invariance(cs_lib):
                                  {"MDA_ENS_IMPL": "mma"}, {"MDA_ENS_IMPL": "mma", "MDA_ENS_WT": "4"},
                                  {"MDA_ENS_IMPL": "mma", "MDA_ENS_DRAWW": "2"}, {"MDA_ENS_IMPL": "mma", "MDA_ENS_DRAWW": "2", "MDA_ENS_WT": "2"},
                                  {"MDA_ENS_IMPL": "mma", "MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "5"},
-                                 {"MDA_ENS_IMPL": "dfma"}])
+                                 {"MDA_ENS_IMPL": "dfma"}, {"MDA_ENS_IMPL": "quad"}])
 def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
     """Units of (chunk of steps, bin) walked by fewer CTAs than bins, other tilings of the chi^2 work and the
     DFMA stepper: the chains are the same (identical for every schedule of the same kernel; the DFMA
     stepper sums chi^2 in another order, so it may differ in a measure-zero set of near-tie decisions)."""
     consts, counts, lo, hi, p0, _ = _problem(5, 9, 60, 128)
     store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    monkeypatch.setenv("MDA_ENS_IMPL", "ws")
     ref = DeviceEnsemble(store, 128, seed=11)
     ref.run_mcmc(p0, 60, thin=2)
     want, want_state = ref.chain.copy(), ref.state()
@@ -114,6 +116,12 @@ def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
         same = np.all(ens.chain == want, axis=(1, 3))
         assert same.mean() > 0.999
         np.testing.assert_allclose(ens.chain[:, :, :3], want[:, :, :3], rtol=1e-13)
+    elif env.get("MDA_ENS_IMPL") == "quad":
+        # chi^2 from the triangular factor: log-probabilities agree to rounding, positions and decisions exactly
+        np.testing.assert_array_equal(ens.chain, want)
+        np.testing.assert_array_equal(ens.state()[0], want_state[0])
+        np.testing.assert_allclose(ens.state()[1], want_state[1], rtol=1e-12)
+        np.testing.assert_array_equal(ens.state()[2], want_state[2])
     else:
         np.testing.assert_array_equal(ens.chain, want)
         for a, b in zip(ens.state(), want_state):
@@ -158,6 +166,12 @@ def test_full_size_steppers_agree_and_follow_the_restatement(cs_lib, oracle_lib,
             got = run(impl, draww, grid="37", chunk="3")
             np.testing.assert_array_equal(got[0], ref[0], err_msg=impl + " " + draww + " 37 CTAs")
             del got
+    got = run("quad", "0")                 # chi^2 from the triangular factor: same decisions, log-probabilities to rounding
+    assert np.all(got[0] == ref[0], axis=(1, 3)).mean() > 0.999
+    if np.array_equal(got[0], ref[0]):
+        np.testing.assert_allclose(got[1], ref[1], rtol=1e-12)
+        np.testing.assert_array_equal(got[2], ref[2])
+    del got
     got = run("dfma", "0")                 # another summation order: may differ in a measure-zero set of near ties
     assert np.all(got[0] == ref[0], axis=(1, 3)).mean() > 0.999
     del got
