@@ -25,10 +25,13 @@ stretch move, mda.py:1128-1131), i.e. bins x 512 likelihood evaluations.
          while chunk c crosses PCIe.  This is what emcee's run_mcmc leaves on the host.
   batched_half_step  the host-driven alternative (one launch per half-ensemble, parameters
          from the host each time): resident ring > 2x L2, and staged-graph e2e.
-  roofline       the sampler kernel (chi^2 on the fp64 tensor path, DMMA.8x8x4, which shares the
-                 DFMA pipe and its peak) against the fp64 pipe (measured live by a DFMA
+  roofline       the sampler kernel against the fp64 pipe (measured live by a DFMA
                  microbenchmark) and against HBM (MEASURED_PEAKS.json); the kernel and its
-                 schedule are named by the library (mdaEnsembleDescribe).
+                 schedule are named by the library (mdaEnsembleDescribe).  The default stepper
+                 takes chi^2 from the bin's triangular factor (55 instead of 600 multiply-adds
+                 at C4): its ALGORITHMIC flop rate is reported next to the
+                 flops it executes; direct_evaluation is the same run on the angle-by-angle
+                 DMMA stepper (MDA_ENS_IMPL=direct).
   cpu_baseline   the unmodified reference library (oracle/_ref) through the Python
                  ctypes path of mda.py:1540-1578 on all host cores (N = 1, rank 0).
 """
@@ -589,11 +592,19 @@ def main():
             return traffic[key + "_per_step"] * args.steps
         return traffic.get(key)
 
-    def roofline_of(kernel, seconds_per_launch, flops_launch, bytes_launch, traffic_key, tensor_note):
+    def roofline_of(kernel, seconds_per_launch, flops_launch, bytes_launch, traffic_key, tensor_note, executed_flops=None):
         tf = flops_launch / seconds_per_launch / 1e12
         gbs = bytes_launch / seconds_per_launch / 1e9
         f64, fhbm = tf / peak_tf.value, gbs / hbm_peak
-        return {
+        extra = {}
+        if executed_flops is not None:
+            etf = executed_flops / seconds_per_launch / 1e12
+            extra = {"fp64_executed": {"achieved_tflops": etf, "frac": etf / peak_tf.value, "flops_per_launch": executed_flops},
+                     "note": "achieved/frac use the ALGORITHMIC flops of SURVEY.md 8d (2 N (L+1) per evaluation); this kernel obtains "
+                             "the same chi^2 from the bin's triangular factor with (L+1)(L+2) + 5 L flops per evaluation "
+                             "(fp64_executed), so the algorithmic rate is not capped by the pipe peak; what limits it is "
+                             "instruction issue and latency per half-step (1.35 bins per SM at C4) and then the chain's HBM writes (hbm)"}
+        return {**extra, **{
             "bound": "fp64" if f64 >= fhbm else "hbm",
             "achieved": tf if f64 >= fhbm else gbs,
             "peak": peak_tf.value if f64 >= fhbm else hbm_peak,
@@ -605,17 +616,38 @@ def main():
                      "peak_source": "DFMA microbenchmark measured in this run (mdaMeasureFp64Peak); MEASURED_PEAKS.json has no fp64 figure"},
             "hbm": {"achieved_gbs": gbs, "peak_gbs": hbm_peak, "frac": fhbm, "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)"},
             "tensor_cores": tensor_note,
-        }
+        }}
 
     # sampler launch: 2 N (L+1) flop per evaluation; HBM: kept chain + lnprob out,
     # constants + state in/out once
     s_flops = 2.0 * n_ang * (n_l + 1) * bins * cfg["walkers"] * args.steps
     s_bytes = 8.0 * (n_l + 1) * bins * (cfg["walkers"] * (args.steps // s_thin + 2) + n_ang)
-    roofline = roofline_of(work.ens.describe(args.steps) + "; one persistent launch of %d steps" % args.steps,
-                           s_ms * 1e-3, s_flops, s_bytes, args.workload + "_sampler",
-                           "fp64 tensor path: mma.sync m8n8k4 f64 (DMMA.8x8x4) for 8 of the 9 distributions, DFMA for the rest; it shares the "
-                           "DFMA pipe and its peak (measured: 36.8 vs 37.1 TFLOP/s) and holds the scheduler's issue port while it runs, so the "
-                           "denominator is the same fp64 peak; tcgen05 has no fp64 kind")
+    dmma_note = ("fp64 tensor path: mma.sync m8n8k4 f64 (DMMA.8x8x4) for 8 of the 9 distributions, DFMA for the rest; it shares the "
+                 "DFMA pipe and its peak (measured: 36.8 vs 37.1 TFLOP/s) and holds the scheduler's issue port while it runs, so the "
+                 "denominator is the same fp64 peak; tcgen05 has no fp64 kind")
+    kernel_text = work.ens.describe(args.steps)
+    is_quad = kernel_text.startswith("ensemble_quad_kernel")
+    roofline = roofline_of(kernel_text + "; one persistent launch of %d steps" % args.steps,
+                           s_ms * 1e-3, s_flops, s_bytes, args.workload + ("_sampler_quad" if is_quad else "_sampler"),
+                           "not used by this kernel: (L+1)(L+2)/2 DFMA per evaluation from the triangular factor; the DMMA steppers "
+                           "(direct_evaluation below) remain selectable with MDA_ENS_IMPL=direct" if is_quad else dmma_note,
+                           executed_flops=((n_l + 1) * (n_l + 2) + 5.0 * n_l) * bins * cfg["walkers"] * args.steps if is_quad else None)
+    direct = None
+    if is_quad:
+        # the same steps on the angle-by-angle stepper (chi^2 as C/ChiSquare.c:188-210 sums it, on the fp64 tensor path)
+        os.environ["MDA_ENS_IMPL"] = "direct"
+        try:
+            work.store.synchronize()
+            dist.barrier()
+            d_ms, _ = work.sampler_resident(args.steps, max(args.warmup, 3))
+            dist.barrier()
+            d_ms = dist.max(d_ms)
+            d_text = work.ens.describe(args.steps)
+        finally:
+            os.environ.pop("MDA_ENS_IMPL", None)
+        direct = {"value": evals_step * args.steps / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms / args.steps,
+                  "roofline": roofline_of(d_text + "; one persistent launch of %d steps" % args.steps, d_ms * 1e-3, s_flops, s_bytes,
+                                          args.workload + "_sampler", dmma_note)}
     dur_s = ms * 1e-3 / timed_launches
     b_kernel = ("lnpost_tile_kernel<L=%d,WPT=%d> %d threads x %d CTAs" % (n_l, tile[1], tile[0], tile[2]) if tile[1] > 0 else
                 "lnpost_mma_kernel<L=%d> (fp64 DMMA) %d threads x %d CTAs" % (n_l, tile[0], tile[2]))
@@ -669,7 +701,7 @@ def main():
             "gpu_launches": 1,
             "gpu_launches_total_in_run": int(total_launches),
             "ensemble_steps_per_s": args.steps / (s_ms * 1e-3),
-            "roofline": roofline, "batched_half_step": batched, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "direct_evaluation": direct, "batched_half_step": batched, "cpu_baseline": cpu, "clocks": clocks,
             "parity_max_rel_err": worst,
             "device": {"name": name.value.decode(), "sms": sms.value, "cc": cc.value},
         }

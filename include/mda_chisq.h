@@ -192,10 +192,15 @@ MDA_API unsigned long long mdaKernelLaunchCount(void);
  *
  * One persistent launch advances every bin's ensemble of nWalkers walkers by
  * nSteps stretch-move steps (two half-ensemble updates per step, emcee 2.x
- * semantics); positions, log-probabilities and the bin's constants stay in
- * shared memory, chi^2 runs on the fp64 tensor path (DMMA.8x8x4; two schedules
- * of the same arithmetic, picked by bins per SM; ensembles of
- * more than 512 walkers or numL < 4 use the DFMA stepper), random numbers come
+ * semantics); positions and log-probabilities stay in shared memory.  Default
+ * stepper: chi^2(a) = |T [a; -1]|^2 from the triangular factor T of the bin's
+ * [distributions | data] matrix (QR in long double when the store is uploaded):
+ * (L+1)(L+2)/2 multiply-adds per evaluation whatever the number of angles, same
+ * decisions and chains as the angle-by-angle steppers, lnL within ~1e-14 of
+ * C/ChiSquare.c:176-213.  MDA_ENS_IMPL=direct selects those: chi^2 angle by angle
+ * on the fp64 tensor path (DMMA.8x8x4; two schedules picked by bins per SM,
+ * DESIGN.md 4.2; ensembles of more than 512 walkers or numL < 4 on the DFMA
+ * stepper).  Random numbers come
  * from Philox4x32-10 with counter
  * (walker, bin id, 2*step+half, draw) and key = seed, so a chain depends only
  * on (seed, bin id, start positions) -- not on launch shape or GPU count.

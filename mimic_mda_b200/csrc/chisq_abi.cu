@@ -486,14 +486,16 @@ struct MdaEnsemble {
 // Which stepper runs an ensemble.  DMMA wherever it can: with two or more bins per SM the homogeneous 8-warp kernel
 // (ensemble_mma_kernel, two CTAs -- two bins -- per SM), below that the warp-specialised 16-warp kernel
 // (ensemble_ws_kernel, one bin per SM at a time).  The register-tiled DFMA stepper carries numL < 4, ensembles of
-// more than 512 walkers and ensembles larger than shared memory.  MDA_ENS_IMPL = mma | ws | dfma forces one.
+// more than 512 walkers and ensembles larger than shared memory.  MDA_ENS_IMPL = quad | mma | ws | dfma forces one,
+// direct = the angle-by-angle steppers picked by shape as described.
 EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
     const bool want_dfma = impl && strcmp(impl, "dfma") == 0, want_ws = impl && strcmp(impl, "ws") == 0,
-               want_mma = impl && strcmp(impl, "mma") == 0, want_quad = impl && strcmp(impl, "quad") == 0;
+               want_mma = impl && strcmp(impl, "mma") == 0, want_quad = impl && strcmp(impl, "quad") == 0,
+               want_direct = impl && strcmp(impl, "direct") == 0;       // angle-by-angle evaluation, stepper picked by shape
     EnsembleShape shape{};
     // default: the triangular-factor stepper (fewest operations per evaluation, same chains); the others on request
-    if ((want_quad || !(want_dfma || want_ws || want_mma)) && choose_ensemble_quad_shape(walkers, s->n_l, g_rt.smem_optin, &shape)) return shape;
+    if ((want_quad || !(want_dfma || want_ws || want_mma || want_direct)) && choose_ensemble_quad_shape(walkers, s->n_l, g_rt.smem_optin, &shape)) return shape;
     if (!want_dfma) {
         const bool prefer_mma = want_mma || (!want_ws && s->bins >= 2 * g_rt.sm_count);
         const int wt = env_int("MDA_ENS_WT", 0);

@@ -30,6 +30,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace mda {
 
@@ -79,8 +80,10 @@ __device__ __forceinline__ double chi_from_factor(const double *__restrict__ tri
     return chi;
 }
 
-template <int L>
-__global__ void __launch_bounds__(kQuadMaxThreads) ensemble_quad_kernel(const EnsembleArgs args) {
+// PRE: the Philox draw of the next half-step is made ahead of the evaluation of this one (shorter half-steps, 72
+// registers: three CTAs per SM) -- for up to three bins per SM; without it 64 registers, four CTAs per SM.
+template <int L, bool PRE>
+__global__ void __launch_bounds__(kQuadMaxThreads, PRE ? 3 : 4) ensemble_quad_kernel(const EnsembleArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int W = args.walkers, H = W >> 1;
@@ -114,12 +117,17 @@ __global__ void __launch_bounds__(kQuadMaxThreads) ensemble_quad_kernel(const En
         long long slot = args.keep0;
         const uint32_t t_begin = 2u * (uint32_t)args.step0, t_end = t_begin + 2u * (uint32_t)args.n_steps;
 
+        auto draw = [&](uint32_t tt, int i) {
+            return philox4x32_10(Philox4{(uint32_t)(((tt & 1u) ? H : 0) + i), bin_id, tt, 0u}, seed0, seed1);
+        };
+        const bool one_each = PRE && H <= T;                   // one walker per thread (every BASELINE.json shape)
+        const int my_i = min(tid, H - 1);
+        Philox4 r_cur = draw(t_begin, my_i);
         for (uint32_t t = t_begin; t < t_end; ++t) {
             const uint32_t half = t & 1u;
             const int s_base = half ? H : 0, c_base = half ? 0 : H;            // updated half; partners come from the other one
-            for (int i = tid; i < H; i += T) {
+            auto update = [&](int i, const Philox4 &r) {
                 const int gw = s_base + i;
-                const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
                 // numpy arithmetic is one rounding per operation: no FMA contraction in the proposal
                 const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
                 const double z2 = __dmul_rn(zr, zr);
@@ -155,6 +163,14 @@ __global__ void __launch_bounds__(kQuadMaxThreads) ensemble_quad_kernel(const En
                     sLnp[gw] = newlnp;
                     sAcc[gw] += 1u;
                 }
+            };
+            if (one_each) {
+                // the draw of the next half-step does not depend on the state: issued here, it overlaps the evaluation below
+                const Philox4 r_next = t + 1 < t_end ? draw(t + 1, my_i) : r_cur;
+                if (tid < H) update(tid, r_cur);
+                r_cur = r_next;
+            } else {
+                for (int i = tid; i < H; i += T) update(i, draw(t, i));
             }
             const bool kept_step = keeping && until_keep == 1 && slot < args.keep_cap;
             if (kept_step) fence_proxy_async_smem();           // my rows before the bulk store reads them
@@ -195,24 +211,24 @@ __global__ void __launch_bounds__(kQuadMaxThreads) ensemble_quad_kernel(const En
 
 using EnsKernel = void (*)(const EnsembleArgs);
 
-EnsKernel pick_quad_kernel(int n_l) {
+EnsKernel pick_quad_kernel(int n_l, bool pre) {
     switch (n_l) {
-        case 1: return ensemble_quad_kernel<1>;
-        case 2: return ensemble_quad_kernel<2>;
-        case 3: return ensemble_quad_kernel<3>;
-        case 4: return ensemble_quad_kernel<4>;
-        case 5: return ensemble_quad_kernel<5>;
-        case 6: return ensemble_quad_kernel<6>;
-        case 7: return ensemble_quad_kernel<7>;
-        case 8: return ensemble_quad_kernel<8>;
-        case 9: return ensemble_quad_kernel<9>;
-        case 10: return ensemble_quad_kernel<10>;
-        case 11: return ensemble_quad_kernel<11>;
-        case 12: return ensemble_quad_kernel<12>;
-        case 13: return ensemble_quad_kernel<13>;
-        case 14: return ensemble_quad_kernel<14>;
-        case 15: return ensemble_quad_kernel<15>;
-        case 16: return ensemble_quad_kernel<16>;
+        case 1: return pre ? ensemble_quad_kernel<1, true> : ensemble_quad_kernel<1, false>;
+        case 2: return pre ? ensemble_quad_kernel<2, true> : ensemble_quad_kernel<2, false>;
+        case 3: return pre ? ensemble_quad_kernel<3, true> : ensemble_quad_kernel<3, false>;
+        case 4: return pre ? ensemble_quad_kernel<4, true> : ensemble_quad_kernel<4, false>;
+        case 5: return pre ? ensemble_quad_kernel<5, true> : ensemble_quad_kernel<5, false>;
+        case 6: return pre ? ensemble_quad_kernel<6, true> : ensemble_quad_kernel<6, false>;
+        case 7: return pre ? ensemble_quad_kernel<7, true> : ensemble_quad_kernel<7, false>;
+        case 8: return pre ? ensemble_quad_kernel<8, true> : ensemble_quad_kernel<8, false>;
+        case 9: return pre ? ensemble_quad_kernel<9, true> : ensemble_quad_kernel<9, false>;
+        case 10: return pre ? ensemble_quad_kernel<10, true> : ensemble_quad_kernel<10, false>;
+        case 11: return pre ? ensemble_quad_kernel<11, true> : ensemble_quad_kernel<11, false>;
+        case 12: return pre ? ensemble_quad_kernel<12, true> : ensemble_quad_kernel<12, false>;
+        case 13: return pre ? ensemble_quad_kernel<13, true> : ensemble_quad_kernel<13, false>;
+        case 14: return pre ? ensemble_quad_kernel<14, true> : ensemble_quad_kernel<14, false>;
+        case 15: return pre ? ensemble_quad_kernel<15, true> : ensemble_quad_kernel<15, false>;
+        case 16: return pre ? ensemble_quad_kernel<16, true> : ensemble_quad_kernel<16, false>;
         default: return nullptr;
     }
 }
@@ -235,21 +251,23 @@ bool choose_ensemble_quad_shape(int walkers, int n_l, size_t smem_optin, Ensembl
 }
 
 cudaError_t configure_ensemble_quad_kernels(size_t smem_optin) {
-    for (int l = 1; l <= kMaxRegL; ++l) {
-        const void *k = reinterpret_cast<const void *>(pick_quad_kernel(l));
-        cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, k);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
-        if (e != cudaSuccess) return e;
-    }
+    for (int l = 1; l <= kMaxRegL; ++l)
+        for (int pre = 0; pre < 2; ++pre) {
+            const void *k = reinterpret_cast<const void *>(pick_quad_kernel(l, pre != 0));
+            cudaFuncAttributes fa;
+            cudaError_t e = cudaFuncGetAttributes(&fa, k);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
+            if (e != cudaSuccess) return e;
+        }
     return cudaSuccess;
 }
 
 cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int sm_count, cudaStream_t stream) {
-    (void)sm_count;
     if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
-    EnsKernel k = pick_quad_kernel(args.n_l);
+    const char *force = getenv("MDA_ENS_QUAD_PRE");                          // experiments: 0 | 1
+    const bool pre = force ? force[0] == '1' : args.bins <= 3 * sm_count;
+    EnsKernel k = pick_quad_kernel(args.n_l, pre);
     if (!k || !shape.fits || !shape.quad || !args.quad) return cudaErrorInvalidValue;
     k<<<args.bins, shape.threads, shape.smem_bytes, stream>>>(args);
     return cudaGetLastError();
