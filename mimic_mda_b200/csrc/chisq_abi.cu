@@ -369,6 +369,13 @@ int enqueue_eval(MdaStore *s, int walkers, const double *d_params, double *d_out
     args.mode = mode;
     if (s->n_l <= kMaxRegL)
         for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
+    const char *batch_impl = getenv("MDA_BATCH_IMPL");
+    if (batch_impl && strcmp(batch_impl, "quad") == 0 && lnpost_quad_supported(s->n_l) && s->force_threads == 0 && s->force_wpt == 0) {
+        args.quad = s->d_quad;
+        MDA_CUDA(launch_batch_quad(args, s->stream), "batched likelihood launch (triangular factor)");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return MDA_OK;
+    }
     if (use_batch_mma(s)) {
         args.consts_mma = s->d_consts_mma;
         args.n_tiles = s->n_tiles;

@@ -24,8 +24,8 @@
 // read of shared memory never delays anyone.  Several CTAs -- bins -- share an SM (41 KB of shared memory at
 // 512 walkers x 9 parameters) and hide each other's latencies; what bounds the run is the chain: W (L+1) 8 bytes
 // per bin and kept step to HBM.
-#include "mda_kernels.cuh"
 #include "philox.cuh"
+#include "quad_chi.cuh"
 
 #include <math_constants.h>
 
@@ -45,7 +45,7 @@ struct QuadSmem {
         size_t off = 0;
         pos = off; off += (size_t)walkers * (size_t)n_l * 8;                  // [W][L] dense, updated in place; bulk-stored as is
         lnp = off; off += (size_t)walkers * 8;                                // [W]
-        tri = off; off += (((size_t)quad_doubles(n_l) + 1) & ~(size_t)1) * 8; // packed T, rows T[i][i..L]
+        tri = off; off += (size_t)quad_padded_doubles(n_l) * 8;               // T, rows T[i][i..L] padded to 16 bytes
         acc = off; off += (size_t)walkers * 4;                                // [W] accepted proposals
         total = (off + 15) & ~(size_t)15;
     }
@@ -62,22 +62,6 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uint32_t y) {
     return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
-}
-
-// chi^2 = |T [a; -1]|^2, T packed by rows in shared memory (every lane reads the same address: broadcasts).
-template <int L>
-__device__ __forceinline__ double chi_from_factor(const double *__restrict__ tri, const double (&a)[L]) {
-    double chi = 0.0;
-    int o = 0;
-#pragma unroll
-    for (int i = 0; i <= L; ++i) {
-        double u = -tri[o + (L - i)];                                         // T[i][L], the transformed data
-#pragma unroll
-        for (int l = i; l < L; ++l) u = fma(tri[o + (l - i)], a[l], u);
-        chi = fma(u, u, chi);
-        o += L + 1 - i;
-    }
-    return chi;
 }
 
 // PRE: the Philox draw of the next half-step is made ahead of the evaluation of this one (shorter half-steps, 72
@@ -108,7 +92,7 @@ __global__ void __launch_bounds__(kQuadMaxThreads, PRE ? 3 : 4) ensemble_quad_ke
         unsigned int *gAcc = args.nacc + (size_t)bin * W;
         for (int i = tid; i < W * L; i += T) sPos[i] = gPos[i];
         for (int w = tid; w < W; w += T) { sLnp[w] = gLnp[w]; sAcc[w] = gAcc[w]; }
-        for (int i = tid; i < quad_doubles(L); i += T) sTri[i] = args.quad[(size_t)bin * quad_doubles(L) + i];
+        load_factor<L>(sTri, args.quad + (size_t)bin * quad_doubles(L), tid, T);
         fence_proxy_async_smem();
         __syncthreads();
 

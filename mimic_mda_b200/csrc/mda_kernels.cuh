@@ -32,6 +32,7 @@ struct BatchArgs {
     double hi[kMaxRegL];
     const double *consts_mma;   // DMMA kernel: fragment-major constants [bins][n_tiles][8 (1+L)] (see mma_chi.cuh)
     int n_tiles;                // DMMA kernel: angle tiles of 8
+    const double *quad;         // triangular-factor kernel: [bins][quad_doubles(L)] packed T (see quad_chi.cuh)
 };
 
 struct TileShape {
@@ -59,6 +60,10 @@ cudaError_t configure_kernels(size_t smem_optin);
 bool lnpost_mma_supported(int n_l, int n_tiles, size_t smem_optin);
 cudaError_t configure_lnpost_mma_kernels(size_t smem_optin);
 cudaError_t launch_batch_mma(BatchArgs &args, int sm_count, cudaStream_t stream, int *grid_out, int *threads_out);
+
+// The same evaluation from the bins' triangular factors (lnpost_quad_kernel.cu), numL <= kMaxRegL, args.quad set.
+bool lnpost_quad_supported(int n_l);
+cudaError_t launch_batch_quad(const BatchArgs &args, cudaStream_t stream);
 
 // ---- device-resident ensemble stepping (ensemble_kernel.cu) -----------------------------
 struct EnsembleArgs {

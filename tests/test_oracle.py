@@ -125,3 +125,24 @@ def test_reference_tester_prints_known_answer():
         pytest.skip("reference build does not run on this CPU")
     out = subprocess.run([reflib.REF_TESTER], capture_output=True, text=True, timeout=60).stdout
     assert "the chi was: 0.456000" in out and out.count("the chi was: -0.228000") == 2
+
+
+def test_triangular_factor_evaluation_reproduces_reference_outputs(golden):
+    """chi^2(a) = |T [a; -1]|^2 with [D^T | d] = Q T (oracle/quad_oracle.py, the restatement of the device's default
+    sampler arithmetic) against the golden outputs of the unmodified reference library: 1e-12 relative, the
+    tolerance north_star states."""
+    from oracle import quad_oracle
+    worst = 0.0
+    for name in golden.cases:
+        g = golden.case(name)
+        n_l = g["params"].shape[2]
+        for b in range(g["consts"].shape[0]):
+            n = int(g["n_pts"][b])
+            t = quad_oracle.factor(g["consts"][b, 0, :n], g["consts"][b, 1:1 + n_l, :n])
+            params = g["params"][b]
+            ok = np.all(np.isfinite(params), axis=1)
+            got = quad_oracle.chi(t, params[ok])
+            want = g["chi"][b][ok]
+            scale = np.maximum(np.abs(want), 1e-300)
+            worst = max(worst, float(np.max(np.abs(got - want) / scale))) if want.size else worst
+    assert worst <= 1e-12, worst
