@@ -29,9 +29,10 @@ stretch move, mda.py:1128-1131), i.e. bins x 512 likelihood evaluations.
                  microbenchmark) and against HBM (MEASURED_PEAKS.json); the kernel and its
                  schedule are named by the library (mdaEnsembleDescribe).  The default stepper
                  takes chi^2 from the bin's triangular factor (55 instead of 600 multiply-adds
-                 at C4): its ALGORITHMIC flop rate is reported next to the
-                 flops it executes; direct_evaluation is the same run on the angle-by-angle
-                 DMMA stepper (MDA_ENS_IMPL=direct).
+                 at C4): its headline fraction is the HBM one (the chain going out); the
+                 ALGORITHMIC flop rate of SURVEY.md 8d and the flops it executes are sub-objects.
+                 direct_evaluation is the same run on the angle-by-angle DMMA stepper
+                 (MDA_ENS_IMPL=direct), whose roofline is the fp64 pipe.
   cpu_baseline   the unmodified reference library (oracle/_ref) through the Python
                  ctypes path of mda.py:1540-1578 on all host cores (N = 1, rank 0).
 """
@@ -600,16 +601,20 @@ def main():
         if executed_flops is not None:
             etf = executed_flops / seconds_per_launch / 1e12
             extra = {"fp64_executed": {"achieved_tflops": etf, "frac": etf / peak_tf.value, "flops_per_launch": executed_flops},
-                     "note": "achieved/frac use the ALGORITHMIC flops of SURVEY.md 8d (2 N (L+1) per evaluation); this kernel obtains "
-                             "the same chi^2 from the bin's triangular factor with (L+1)(L+2) + 5 L flops per evaluation "
-                             "(fp64_executed), so the algorithmic rate is not capped by the pipe peak; what limits it is "
-                             "instruction issue and latency per half-step (1.35 bins per SM at C4) and then the chain's HBM writes (hbm)"}
+                     "note": "this kernel obtains chi^2 from the bin's triangular factor with (L+1)(L+2) + 5 L flops per evaluation "
+                             "(fp64_executed) instead of the 2 N (L+1) of SURVEY.md 8d (fp64: the ALGORITHMIC rate, which the pipe peak "
+                             "does not cap), so the roofline that can bind it is HBM: the chain, 8 (L+1) bytes per evaluation, going "
+                             "out (achieved / frac).  At C4 (1.35 bins per SM) it is limited by latency and instruction issue per "
+                             "half-step before that; with four bins per SM the chain reaches 56 % of the HBM rate"}
+        # the triangular-factor kernel executes a tenth of the algorithmic flops: the roofline that can bind it is HBM
+        # (the chain going out); its algorithmic flop rate is reported in "fp64" below, not as the headline fraction
+        by_flops = f64 >= fhbm and executed_flops is None
         return {**extra, **{
-            "bound": "fp64" if f64 >= fhbm else "hbm",
-            "achieved": tf if f64 >= fhbm else gbs,
-            "peak": peak_tf.value if f64 >= fhbm else hbm_peak,
-            "unit": "TFLOP/s" if f64 >= fhbm else "GB/s",
-            "frac": max(f64, fhbm), "traffic": traffic_of(traffic_key),
+            "bound": "fp64" if by_flops else "hbm",
+            "achieved": tf if by_flops else gbs,
+            "peak": peak_tf.value if by_flops else hbm_peak,
+            "unit": "TFLOP/s" if by_flops else "GB/s",
+            "frac": f64 if by_flops else fhbm, "traffic": traffic_of(traffic_key),
             "kernel": kernel, "launch_us": seconds_per_launch * 1e6,
             "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
             "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf.value, "frac": f64,
