@@ -480,6 +480,7 @@ struct MdaEnsemble {
     unsigned long long launches = 0;            // stepping launches so far (the words' high half)
     double *d_chain = nullptr, *d_lnp_chain = nullptr;
     long long keep_cap = 0, kept = 0, steps = 0;
+    long long alloc_cap = 0;         // kept samples the chain allocations can hold (>= keep_cap: a smaller reservation reuses them)
     bool has_state = false;
     long long *d_prof = nullptr;     // [bins][8] section cycle counters of the last launch (debug)
     void *scratch = nullptr;         // device scratch of the posterior reductions, grown on demand
@@ -1041,16 +1042,22 @@ int mdaEnsembleReserveChain(void *ens, long long capacity) {
     if (rc) return rc;
     MdaStore *s = e->store;
     MDA_CUDA(cudaStreamSynchronize(s->stream), "mdaEnsembleReserveChain");
+    e->kept = 0;
+    if (capacity > 0 && capacity <= e->alloc_cap && e->d_chain && e->d_lnp_chain) {
+        e->keep_cap = capacity;                            // the chain is step-major: a shorter one is a prefix of the allocation
+        return MDA_OK;                                     // (gigabytes of cudaFree + cudaMalloc cost tens of milliseconds)
+    }
     if (e->d_chain) cudaFree(e->d_chain);
     if (e->d_lnp_chain) cudaFree(e->d_lnp_chain);
     e->d_chain = e->d_lnp_chain = nullptr;
     e->keep_cap = 0;
-    e->kept = 0;
+    e->alloc_cap = 0;
     if (capacity == 0) return MDA_OK;
     const size_t per_keep = (size_t)s->bins * (size_t)e->walkers;
     MDA_CUDA(cudaMalloc((void **)&e->d_chain, sizeof(double) * per_keep * (size_t)s->n_l * (size_t)capacity), "chain allocation");
     MDA_CUDA(cudaMalloc((void **)&e->d_lnp_chain, sizeof(double) * per_keep * (size_t)capacity), "lnprob chain allocation");
     e->keep_cap = capacity;
+    e->alloc_cap = capacity;
     return MDA_OK;
 }
 
