@@ -519,6 +519,7 @@ EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
 // walk the list, so that every SM carries the same share of the run (C4: 200 bins on 148 SMs; from two bins per
 // SM on, the 8-warp kernel keeps two CTAs per SM).  MDA_ENS_GRID / MDA_ENS_CHUNK override, for experiments and tests.
 struct SteppingPlan { int grid, chunk_steps, n_chunks; };
+constexpr int kQuadWalkPerSm = 1;      // CTAs per SM when the triangular-factor stepper walks units
 SteppingPlan plan_stepping(const MdaStore *s, const EnsembleShape &shape, int nSteps) {
     SteppingPlan p{0, nSteps, 1};
     const int capacity = shape.ws ? ensemble_ws_capacity(s->n_l, shape, g_rt.sm_count) : ensemble_mma_capacity(s->n_l, shape, g_rt.sm_count);
@@ -541,6 +542,45 @@ SteppingPlan plan_stepping(const MdaStore *s, const EnsembleShape &shape, int nS
             const int cs = (nSteps + n - 1) / n, real_n = (nSteps + cs - 1) / cs;
             const long long units = (long long)real_n * s->bins, rounds = (units + grid - 1) / grid;
             const double waste = (double)(rounds * grid) / (double)units + 0.0005 * real_n;   // each hand-over costs ~0.05 % of a chunk
+            if (waste < best_waste - 1e-12) { best_waste = waste; best = real_n; }
+        }
+        chunk_steps = (nSteps + best - 1) / best;
+    }
+    const int force_chunk = env_int("MDA_ENS_CHUNK", 0);
+    if (force_chunk > 0) chunk_steps = std::min(force_chunk, nSteps);
+    p.grid = grid;
+    p.chunk_steps = std::max(1, chunk_steps);
+    p.n_chunks = (nSteps + p.chunk_steps - 1) / p.chunk_steps;
+    return p;
+}
+
+// Schedule of the triangular-factor stepper: a CTA per bin for the whole launch, unless a grid smaller than the number of
+// bins pays (just above one bin per SM a few SMs would carry two bins for the whole run and set its length): then one CTA
+// per SM walks (chunk, bin) units as above.  MDA_ENS_GRID / MDA_ENS_CHUNK / MDA_ENS_QUAD_WALK override.
+SteppingPlan plan_quad_stepping(const MdaStore *s, const EnsembleShape &shape, int nSteps) {
+    SteppingPlan p{s->bins, nSteps, 1};
+    int grid = s->bins;
+    const int forced_walk = env_int("MDA_ENS_QUAD_WALK", -1);                // experiments: CTAs per SM of the walk (0: off)
+    const int walk_per_sm = forced_walk >= 0 ? forced_walk : kQuadWalkPerSm;
+    // measured at 512 x 9: one bin per SM 2.57 us per step, two bins per SM 3.83 -- a CTA per bin costs the two-bin time as soon
+    // as one SM carries two, walking with one CTA per SM costs bins / SMs x 2.6: it pays up to 1.4 bins per SM (C4: 3.83 -> 3.57)
+    const bool walk_pays = forced_walk >= 0 ? s->bins < 3 * g_rt.sm_count : 10LL * s->bins <= 14LL * g_rt.sm_count;
+    if (walk_per_sm > 0 && s->bins > g_rt.sm_count && walk_pays) grid = walk_per_sm * g_rt.sm_count;
+    const int force_grid = env_int("MDA_ENS_GRID", 0);
+    if (force_grid > 0) grid = force_grid;
+    if (grid >= s->bins && env_int("MDA_ENS_CHUNK", 0) <= 0) return p;       // every bin has its own CTA
+    const int capacity = ensemble_quad_capacity(s->n_l, shape, grid, g_rt.sm_count);
+    if (capacity < 1) { p.grid = 0; return p; }
+    grid = std::max(1, std::min(std::min(grid, capacity), s->bins));
+    int chunk_steps = nSteps;
+    if (grid < s->bins) {
+        const int min_chunk = 8, max_chunks = std::max(1, std::min(96, nSteps / min_chunk));
+        double best_waste = 1e30;
+        int best = 1;
+        for (int n = std::min(4, max_chunks); n <= max_chunks; ++n) {
+            const int cs = (nSteps + n - 1) / n, real_n = (nSteps + cs - 1) / cs;
+            const long long units = (long long)real_n * s->bins, rounds = (units + grid - 1) / grid;
+            const double waste = (double)(rounds * grid) / (double)units + 0.0005 * real_n;
             if (waste < best_waste - 1e-12) { best_waste = waste; best = real_n; }
         }
         chunk_steps = (nSteps + best - 1) / best;
@@ -1101,7 +1141,13 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.quad = s->d_quad;
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
     if (shape.quad) {
-        MDA_CUDA(launch_ensemble_quad(args, shape, g_rt.sm_count, s->stream), "ensemble stepping launch (triangular factor)");
+        const SteppingPlan plan = plan_quad_stepping(s, shape, nSteps);
+        if (plan.grid < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
+        args.chunk_steps = plan.chunk_steps;
+        args.n_chunks = plan.n_chunks;
+        args.progress = e->d_progress;
+        args.launch_serial = (++e->launches) << 32;
+        MDA_CUDA(launch_ensemble_quad(args, shape, plan.grid, g_rt.sm_count, s->stream), "ensemble stepping launch (triangular factor)");
     } else if (shape.mma) {
         const SteppingPlan plan = plan_stepping(s, shape, nSteps);
         if (plan.grid < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
@@ -1132,8 +1178,9 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
     if (shape.quad) {
         snprintf(text, (size_t)textLen,
                  "ensemble_quad_kernel<L=%d>: chi^2 = |T [a; -1]|^2 from the bin's triangular factor (%d multiply-adds per evaluation), %d threads x %d walkers, "
-                 "one barrier per half-step, bulk-TMA chain stores, %zu B shared memory; one CTA per bin (%d)",
-                 s->n_l, quad_doubles(s->n_l), shape.threads, shape.wpt, shape.smem_bytes, s->bins);
+                 "one barrier per half-step, bulk-TMA chain stores, %zu B shared memory; %d CTAs, %d bins x %d chunks of %d steps",
+                 s->n_l, quad_doubles(s->n_l), shape.threads, shape.wpt, shape.smem_bytes, plan_quad_stepping(s, shape, nSteps).grid, s->bins,
+                 plan_quad_stepping(s, shape, nSteps).n_chunks, plan_quad_stepping(s, shape, nSteps).chunk_steps);
     } else if (shape.mma) {
         const SteppingPlan plan = plan_stepping(s, shape, nSteps);
         if (shape.ws)

@@ -37,6 +37,7 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
+constexpr int kStatusStalled = 4;        // a unit waited ~3 s for its predecessor: the launch gave up (a guard against a hung GPU)
 constexpr int kQuadMaxThreads = 256;
 
 struct QuadSmem {
@@ -59,6 +60,15 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uint32_t y) {
     return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
@@ -86,20 +96,44 @@ __global__ void __launch_bounds__(kQuadMaxThreads, PRE ? 3 : 4) ensemble_quad_ke
     const bool split = ((H * L) & 1) == 0 && (H & 1) == 0;
     bool saw_nan = false;
 
-    for (int bin = blockIdx.x; bin < args.bins; bin += gridDim.x) {
+    // Units of work are (chunk of steps, bin), chunk-major, unit u on CTA u mod grid (one chunk, grid = bins: a CTA keeps its
+    // bin for the whole launch).  With fewer CTAs than bins every SM carries the same share of the run; a unit takes the
+    // bin's state over from HBM/L2 behind a release/acquire progress word per bin, as in the DMMA steppers.
+    __shared__ int s_abort;
+    if (tid == 0) s_abort = 0;
+    __syncthreads();
+    const long long n_units = (long long)args.n_chunks * args.bins;
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int chunk = (int)(unit / args.bins);
+        const int bin = (int)(unit - (long long)chunk * args.bins);
+        const long long step_first = args.step0 + (long long)chunk * args.chunk_steps;
+        const int steps_here = min(args.chunk_steps, args.n_steps - chunk * args.chunk_steps);
         double *gPos = args.pos + (size_t)bin * W * L;
         double *gLnp = args.lnp + (size_t)bin * W;
         unsigned int *gAcc = args.nacc + (size_t)bin * W;
-        for (int i = tid; i < W * L; i += T) sPos[i] = gPos[i];
-        for (int w = tid; w < W; w += T) { sLnp[w] = gLnp[w]; sAcc[w] = gAcc[w]; }
+        if (tid == 0 && chunk > 0) {
+            const unsigned long long want = args.launch_serial + (unsigned long long)chunk;
+            unsigned int spins = 0;
+            while (ld_acquire_u64(args.progress + bin) != want) {
+                __nanosleep(64);
+                if (++spins > (1u << 25)) { s_abort = 1; break; }             // ~3 s: the predecessor is not coming
+            }
+        }
+        __syncthreads();
+        if (s_abort) {                                         // every CTA that depends on this bin gives up the same way
+            if (tid == 0) atomicOr(args.status, kStatusStalled);
+            break;
+        }
+        for (int i = tid; i < W * L; i += T) sPos[i] = __ldcg(gPos + i);
+        for (int w = tid; w < W; w += T) { sLnp[w] = __ldcg(gLnp + w); sAcc[w] = __ldcg(gAcc + w); }
         load_factor<L>(sTri, args.quad + (size_t)bin * quad_doubles(L), tid, T);
         fence_proxy_async_smem();
         __syncthreads();
 
         const uint32_t bin_id = (uint32_t)args.bin_ids[bin];
-        int until_keep = args.thin - (int)((uint64_t)args.step0 % (uint64_t)args.thin);
-        long long slot = args.keep0;
-        const uint32_t t_begin = 2u * (uint32_t)args.step0, t_end = t_begin + 2u * (uint32_t)args.n_steps;
+        int until_keep = args.thin - (int)((uint64_t)step_first % (uint64_t)args.thin);
+        long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
+        const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = t_begin + 2u * (uint32_t)steps_here;
 
         auto draw = [&](uint32_t tt, int i) {
             return philox4x32_10(Philox4{(uint32_t)(((tt & 1u) ? H : 0) + i), bin_id, tt, 0u}, seed0, seed1);
@@ -188,6 +222,10 @@ __global__ void __launch_bounds__(kQuadMaxThreads, PRE ? 3 : 4) ensemble_quad_ke
         for (int i = tid; i < W * L; i += T) gPos[i] = sPos[i];
         for (int w = tid; w < W; w += T) { gLnp[w] = sLnp[w]; gAcc[w] = sAcc[w]; }
         __syncthreads();
+        if (tid == 0 && args.n_chunks > 1) {
+            __threadfence();
+            st_release_u64(args.progress + bin, args.launch_serial + (unsigned long long)(chunk + 1));
+        }
     }
     if (tid == 0) bulk_wait_all();
     if (saw_nan) atomicOr(args.status, kStatusNaN);
@@ -247,13 +285,28 @@ cudaError_t configure_ensemble_quad_kernels(size_t smem_optin) {
     return cudaSuccess;
 }
 
-cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int sm_count, cudaStream_t stream) {
-    if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
+// The build for `grid` CTAs: with the draw made ahead up to three CTAs per SM.
+static bool quad_pre_for(int grid, int sm_count) {
     const char *force = getenv("MDA_ENS_QUAD_PRE");                          // experiments: 0 | 1
-    const bool pre = force ? force[0] == '1' : args.bins <= 3 * sm_count;
-    EnsKernel k = pick_quad_kernel(args.n_l, pre);
-    if (!k || !shape.fits || !shape.quad || !args.quad) return cudaErrorInvalidValue;
-    k<<<args.bins, shape.threads, shape.smem_bytes, stream>>>(args);
+    return force ? force[0] == '1' : grid <= 3 * sm_count;
+}
+
+// Co-resident CTAs on the whole device (a walked unit list needs every CTA of the grid resident).
+int ensemble_quad_capacity(int n_l, const EnsembleShape &shape, int grid, int sm_count) {
+    EnsKernel k = pick_quad_kernel(n_l, quad_pre_for(grid, sm_count));
+    int per_sm = 0;
+    if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(k), shape.threads, shape.smem_bytes) != cudaSuccess)
+        return 0;
+    return per_sm * sm_count;
+}
+
+cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int grid, int sm_count, cudaStream_t stream) {
+    if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
+    EnsKernel k = pick_quad_kernel(args.n_l, quad_pre_for(grid, sm_count));
+    if (!k || !shape.fits || !shape.quad || !args.quad || grid < 1 || args.chunk_steps < 1 || args.n_chunks < 1 ||
+        (args.n_chunks > 1 && !args.progress))
+        return cudaErrorInvalidValue;
+    k<<<grid, shape.threads, shape.smem_bytes, stream>>>(args);
     return cudaGetLastError();
 }
 

@@ -133,7 +133,8 @@ cudaError_t launch_ensemble_ws(const EnsembleArgs &args, const EnsembleShape &sh
 // ensemble_quad_kernel.cu: one CTA per bin at a time, one thread per walker of the half being updated.
 bool choose_ensemble_quad_shape(int walkers, int n_l, size_t smem_optin, EnsembleShape *out);
 cudaError_t configure_ensemble_quad_kernels(size_t smem_optin);
-cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int sm_count, cudaStream_t stream);
+int ensemble_quad_capacity(int n_l, const EnsembleShape &shape, int grid, int sm_count);
+cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int grid, int sm_count, cudaStream_t stream);
 
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
 // gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.

@@ -94,7 +94,9 @@ def test_split_runs_thinning_and_partition_invariance(cs_lib):
                                  {"MDA_ENS_IMPL": "mma"}, {"MDA_ENS_IMPL": "mma", "MDA_ENS_WT": "4"},
                                  {"MDA_ENS_IMPL": "mma", "MDA_ENS_DRAWW": "2"}, {"MDA_ENS_IMPL": "mma", "MDA_ENS_DRAWW": "2", "MDA_ENS_WT": "2"},
                                  {"MDA_ENS_IMPL": "mma", "MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "5"},
-                                 {"MDA_ENS_IMPL": "dfma"}, {"MDA_ENS_IMPL": "quad"}])
+                                 {"MDA_ENS_IMPL": "dfma"}, {"MDA_ENS_IMPL": "quad"},
+                                 {"MDA_ENS_IMPL": "quad", "MDA_ENS_GRID": "2", "MDA_ENS_CHUNK": "7"},    # units handed over through HBM
+                                 {"MDA_ENS_IMPL": "quad", "MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "1"}])
 def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
     """Units of (chunk of steps, bin) walked by fewer CTAs than bins, other tilings of the chi^2 work and the
     DFMA stepper: the chains are the same (identical for every schedule of the same kernel; the DFMA
