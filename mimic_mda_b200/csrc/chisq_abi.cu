@@ -568,12 +568,13 @@ SteppingPlan plan_quad_stepping(const MdaStore *s, const EnsembleShape &shape, i
     if (walk_per_sm > 0 && s->bins > g_rt.sm_count && walk_pays) grid = walk_per_sm * g_rt.sm_count;
     const int force_grid = env_int("MDA_ENS_GRID", 0);
     if (force_grid > 0) grid = force_grid;
-    if (grid >= s->bins && env_int("MDA_ENS_CHUNK", 0) <= 0) return p;       // every bin has its own CTA
+    if ((grid == s->bins || (grid > s->bins && force_grid <= 0)) && env_int("MDA_ENS_CHUNK", 0) <= 0) return p;   // every bin has its own CTA
     const int capacity = ensemble_quad_capacity(s->n_l, shape, grid, g_rt.sm_count);
     if (capacity < 1) { p.grid = 0; return p; }
-    grid = std::max(1, std::min(std::min(grid, capacity), s->bins));
+    grid = std::max(1, std::min(grid, capacity));          // (a forced grid may exceed the bins: more CTAs than active units)
+    if (force_grid <= 0) grid = std::min(grid, s->bins);
     int chunk_steps = nSteps;
-    if (grid < s->bins) {
+    if (grid != s->bins) {
         const int min_chunk = 8, max_chunks = std::max(1, std::min(96, nSteps / min_chunk));
         double best_waste = 1e30;
         int best = 1;
