@@ -74,10 +74,11 @@ __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uint32_t y) 
     return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
 }
 
-// PRE: the Philox draw of the next half-step is made ahead of the evaluation of this one (shorter half-steps, 72
-// registers: three CTAs per SM) -- for up to three bins per SM; without it 64 registers, four CTAs per SM.
-template <int L, bool PRE>
-__global__ void __launch_bounds__(kQuadMaxThreads, PRE ? 3 : 4) ensemble_quad_kernel(const EnsembleArgs args) {
+// OCC: CTAs per SM the build is made for.  4: 64 registers.  3 and 1: the Philox draw of the next half-step is made ahead of
+// the evaluation of this one (shorter half-steps; 78 registers) -- for up to three bins per SM; 1: no register cap at all
+// (158 registers) for a CTA that has its SM to itself (up to one bin per SM, and the walking schedule).
+template <int L, int OCC>
+__global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(const EnsembleArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int W = args.walkers, H = W >> 1;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(kQuadMaxThreads, PRE ? 3 : 4) ensemble_quad_ke
         auto draw = [&](uint32_t tt, int i) {
             return philox4x32_10(Philox4{(uint32_t)(((tt & 1u) ? H : 0) + i), bin_id, tt, 0u}, seed0, seed1);
         };
-        const bool one_each = PRE && H <= T;                   // one walker per thread (every BASELINE.json shape)
+        const bool one_each = OCC != 4 && H <= T;                   // one walker per thread (every BASELINE.json shape)
         const int my_i = min(tid, H - 1);
         Philox4 r_cur = draw(t_begin, my_i);
         for (uint32_t t = t_begin; t < t_end; ++t) {
@@ -233,24 +234,24 @@ __global__ void __launch_bounds__(kQuadMaxThreads, PRE ? 3 : 4) ensemble_quad_ke
 
 using EnsKernel = void (*)(const EnsembleArgs);
 
-EnsKernel pick_quad_kernel(int n_l, bool pre) {
+EnsKernel pick_quad_kernel(int n_l, int occ) {
     switch (n_l) {
-        case 1: return pre ? ensemble_quad_kernel<1, true> : ensemble_quad_kernel<1, false>;
-        case 2: return pre ? ensemble_quad_kernel<2, true> : ensemble_quad_kernel<2, false>;
-        case 3: return pre ? ensemble_quad_kernel<3, true> : ensemble_quad_kernel<3, false>;
-        case 4: return pre ? ensemble_quad_kernel<4, true> : ensemble_quad_kernel<4, false>;
-        case 5: return pre ? ensemble_quad_kernel<5, true> : ensemble_quad_kernel<5, false>;
-        case 6: return pre ? ensemble_quad_kernel<6, true> : ensemble_quad_kernel<6, false>;
-        case 7: return pre ? ensemble_quad_kernel<7, true> : ensemble_quad_kernel<7, false>;
-        case 8: return pre ? ensemble_quad_kernel<8, true> : ensemble_quad_kernel<8, false>;
-        case 9: return pre ? ensemble_quad_kernel<9, true> : ensemble_quad_kernel<9, false>;
-        case 10: return pre ? ensemble_quad_kernel<10, true> : ensemble_quad_kernel<10, false>;
-        case 11: return pre ? ensemble_quad_kernel<11, true> : ensemble_quad_kernel<11, false>;
-        case 12: return pre ? ensemble_quad_kernel<12, true> : ensemble_quad_kernel<12, false>;
-        case 13: return pre ? ensemble_quad_kernel<13, true> : ensemble_quad_kernel<13, false>;
-        case 14: return pre ? ensemble_quad_kernel<14, true> : ensemble_quad_kernel<14, false>;
-        case 15: return pre ? ensemble_quad_kernel<15, true> : ensemble_quad_kernel<15, false>;
-        case 16: return pre ? ensemble_quad_kernel<16, true> : ensemble_quad_kernel<16, false>;
+        case 1: return occ == 1 ? ensemble_quad_kernel<1, 1> : (occ == 3 ? ensemble_quad_kernel<1, 3> : ensemble_quad_kernel<1, 4>);
+        case 2: return occ == 1 ? ensemble_quad_kernel<2, 1> : (occ == 3 ? ensemble_quad_kernel<2, 3> : ensemble_quad_kernel<2, 4>);
+        case 3: return occ == 1 ? ensemble_quad_kernel<3, 1> : (occ == 3 ? ensemble_quad_kernel<3, 3> : ensemble_quad_kernel<3, 4>);
+        case 4: return occ == 1 ? ensemble_quad_kernel<4, 1> : (occ == 3 ? ensemble_quad_kernel<4, 3> : ensemble_quad_kernel<4, 4>);
+        case 5: return occ == 1 ? ensemble_quad_kernel<5, 1> : (occ == 3 ? ensemble_quad_kernel<5, 3> : ensemble_quad_kernel<5, 4>);
+        case 6: return occ == 1 ? ensemble_quad_kernel<6, 1> : (occ == 3 ? ensemble_quad_kernel<6, 3> : ensemble_quad_kernel<6, 4>);
+        case 7: return occ == 1 ? ensemble_quad_kernel<7, 1> : (occ == 3 ? ensemble_quad_kernel<7, 3> : ensemble_quad_kernel<7, 4>);
+        case 8: return occ == 1 ? ensemble_quad_kernel<8, 1> : (occ == 3 ? ensemble_quad_kernel<8, 3> : ensemble_quad_kernel<8, 4>);
+        case 9: return occ == 1 ? ensemble_quad_kernel<9, 1> : (occ == 3 ? ensemble_quad_kernel<9, 3> : ensemble_quad_kernel<9, 4>);
+        case 10: return occ == 1 ? ensemble_quad_kernel<10, 1> : (occ == 3 ? ensemble_quad_kernel<10, 3> : ensemble_quad_kernel<10, 4>);
+        case 11: return occ == 1 ? ensemble_quad_kernel<11, 1> : (occ == 3 ? ensemble_quad_kernel<11, 3> : ensemble_quad_kernel<11, 4>);
+        case 12: return occ == 1 ? ensemble_quad_kernel<12, 1> : (occ == 3 ? ensemble_quad_kernel<12, 3> : ensemble_quad_kernel<12, 4>);
+        case 13: return occ == 1 ? ensemble_quad_kernel<13, 1> : (occ == 3 ? ensemble_quad_kernel<13, 3> : ensemble_quad_kernel<13, 4>);
+        case 14: return occ == 1 ? ensemble_quad_kernel<14, 1> : (occ == 3 ? ensemble_quad_kernel<14, 3> : ensemble_quad_kernel<14, 4>);
+        case 15: return occ == 1 ? ensemble_quad_kernel<15, 1> : (occ == 3 ? ensemble_quad_kernel<15, 3> : ensemble_quad_kernel<15, 4>);
+        case 16: return occ == 1 ? ensemble_quad_kernel<16, 1> : (occ == 3 ? ensemble_quad_kernel<16, 3> : ensemble_quad_kernel<16, 4>);
         default: return nullptr;
     }
 }
@@ -274,8 +275,8 @@ bool choose_ensemble_quad_shape(int walkers, int n_l, size_t smem_optin, Ensembl
 
 cudaError_t configure_ensemble_quad_kernels(size_t smem_optin) {
     for (int l = 1; l <= kMaxRegL; ++l)
-        for (int pre = 0; pre < 2; ++pre) {
-            const void *k = reinterpret_cast<const void *>(pick_quad_kernel(l, pre != 0));
+        for (int occ : {1, 3, 4}) {
+            const void *k = reinterpret_cast<const void *>(pick_quad_kernel(l, occ));
             cudaFuncAttributes fa;
             cudaError_t e = cudaFuncGetAttributes(&fa, k);
             if (e != cudaSuccess) return e;
@@ -285,15 +286,16 @@ cudaError_t configure_ensemble_quad_kernels(size_t smem_optin) {
     return cudaSuccess;
 }
 
-// The build for `grid` CTAs: with the draw made ahead up to three CTAs per SM.
-static bool quad_pre_for(int grid, int sm_count) {
-    const char *force = getenv("MDA_ENS_QUAD_PRE");                          // experiments: 0 | 1
-    return force ? force[0] == '1' : grid <= 3 * sm_count;
+// The build for `grid` CTAs.
+static int quad_occ_for(int grid, int sm_count) {
+    const char *force = getenv("MDA_ENS_QUAD_OCC");                          // experiments: 1 | 3 | 4
+    if (force && (force[0] == '1' || force[0] == '3' || force[0] == '4')) return force[0] - '0';
+    return grid <= sm_count ? 1 : (grid <= 3 * sm_count ? 3 : 4);
 }
 
 // Co-resident CTAs on the whole device (a walked unit list needs every CTA of the grid resident).
 int ensemble_quad_capacity(int n_l, const EnsembleShape &shape, int grid, int sm_count) {
-    EnsKernel k = pick_quad_kernel(n_l, quad_pre_for(grid, sm_count));
+    EnsKernel k = pick_quad_kernel(n_l, quad_occ_for(grid, sm_count));
     int per_sm = 0;
     if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(k), shape.threads, shape.smem_bytes) != cudaSuccess)
         return 0;
@@ -302,7 +304,7 @@ int ensemble_quad_capacity(int n_l, const EnsembleShape &shape, int grid, int sm
 
 cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int grid, int sm_count, cudaStream_t stream) {
     if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
-    EnsKernel k = pick_quad_kernel(args.n_l, quad_pre_for(grid, sm_count));
+    EnsKernel k = pick_quad_kernel(args.n_l, quad_occ_for(grid, sm_count));
     if (!k || !shape.fits || !shape.quad || !args.quad || grid < 1 || args.chunk_steps < 1 || args.n_chunks < 1 ||
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;
