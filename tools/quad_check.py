@@ -1,4 +1,4 @@
-"""The triangular-factor stepper against the default stepper on the same seeds: positions identical, log-probabilities
+"""The triangular-factor stepper (the default) against the angle-by-angle steppers (MDA_ENS_IMPL=direct) on the same seeds: positions identical, log-probabilities
 to 1e-12 relative (and against the numpy oracle on the final state)."""
 import os, sys; sys.path.insert(0, '/root/repo')
 import numpy as np
@@ -22,7 +22,7 @@ for (bins, n_l, n_pts, walkers, steps, thin, ragged) in [(5, 4, 30, 64, 200, 1, 
                                                          (2, 8, 41, 2500, 40, 1, False), (3, 12, 256, 96, 100, 2, False), (2, 3, 16, 10, 300, 1, False),
                                                          (2, 1, 20, 32, 100, 1, False), (2, 6, 4, 40, 100, 1, False)]:
     a = run("quad", bins, n_l, n_pts, walkers, steps, thin, ragged)
-    b = run("", bins, n_l, n_pts, walkers, steps, thin, ragged)
+    b = run("direct", bins, n_l, n_pts, walkers, steps, thin, ragged)
     same_pos = np.array_equal(a[0], b[0])
     fin = np.isfinite(b[1])
     rel = np.max(np.abs(a[1][fin] - b[1][fin]) / np.abs(b[1][fin]))
