@@ -258,3 +258,30 @@ def test_run_to_host_streams_the_same_chain(cs_lib):
         ens.close()
     ref.close()
     store.close()
+
+
+def test_walking_schedule_of_the_default_stepper_with_thinning_and_split_runs(cs_lib, monkeypatch):
+    """Just above one bin per SM the default stepper lets one CTA per SM walk (chunk, bin) units: the chain, thinned and
+    advanced in two calls, equals the one a CTA per bin produces (MDA_ENS_QUAD_WALK=0)."""
+    n_bins = 200
+    consts, counts, lo, hi, p0, _ = _problem(n_bins, 4, 16, 32)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    monkeypatch.setenv("MDA_ENS_QUAD_WALK", "0")
+    ref = DeviceEnsemble(store, 32, seed=31)
+    assert "200 CTAs" in ref.describe(90)
+    ref.run_mcmc(p0, 90, thin=3)
+    want, want_state = ref.chain.copy(), ref.state()
+    monkeypatch.delenv("MDA_ENS_QUAD_WALK")
+    ens = DeviceEnsemble(store, 32, seed=31)
+    if n_bins <= 1.4 * 148:
+        assert "chunks" in ens.describe(90) and "200 CTAs" not in ens.describe(90)
+    ens.set_state(p0)
+    ens.reserve_chain(30)
+    ens.advance(40, thin=3)
+    ens.advance(50, thin=3)
+    np.testing.assert_array_equal(ens.chain, want)
+    for a, b in zip(ens.state(), want_state):
+        np.testing.assert_array_equal(a, b)
+    ens.close()
+    ref.close()
+    store.close()
