@@ -564,7 +564,9 @@ SteppingPlan plan_quad_stepping(const MdaStore *s, const EnsembleShape &shape, i
     const int walk_per_sm = forced_walk >= 0 ? forced_walk : kQuadWalkPerSm;
     // measured at 512 x 9: one bin per SM 2.57 us per step, two bins per SM 3.83 -- a CTA per bin costs the two-bin time as soon
     // as one SM carries two, walking with one CTA per SM costs bins / SMs x 2.6: it pays up to 1.4 bins per SM (C4: 3.83 -> 3.57)
-    const bool walk_pays = forced_walk >= 0 ? s->bins < 3 * g_rt.sm_count : 10LL * s->bins <= 14LL * g_rt.sm_count;
+    // ... for launches long enough that a unit is ~100 steps (a hand-over moves 40 KB of state and the constants; with 8-step
+    // units a 100-step launch ran at 4.5 us per step under ncu)
+    const bool walk_pays = forced_walk >= 0 ? s->bins < 3 * g_rt.sm_count : (10LL * s->bins <= 14LL * g_rt.sm_count && nSteps >= 512);
     if (walk_per_sm > 0 && s->bins > g_rt.sm_count && walk_pays) grid = walk_per_sm * g_rt.sm_count;
     const int force_grid = env_int("MDA_ENS_GRID", 0);
     if (force_grid > 0) grid = force_grid;
