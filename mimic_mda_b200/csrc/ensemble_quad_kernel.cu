@@ -79,6 +79,7 @@ __device__ __forceinline__ double uniform43(uint32_t w, uint32_t x, uint32_t y) 
 // (158 registers) for a CTA that has its SM to itself (up to one bin per SM, and the walking schedule).
 template <int L, int OCC>
 __global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(const EnsembleArgs args) {
+    constexpr bool kTriInRegs = OCC == 1 && quad_padded_doubles(L) <= 60;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int W = args.walkers, H = W >> 1;
@@ -131,6 +132,12 @@ __global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(con
         fence_proxy_async_smem();
         __syncthreads();
 
+        // the lone-CTA build keeps T in registers for the unit (up to 60 doubles): no shared-memory reads in the contraction
+        double tri_regs[kTriInRegs ? quad_padded_doubles(L) : 1];
+        if constexpr (kTriInRegs) {
+#pragma unroll
+            for (int k = 0; k < quad_padded_doubles(L); ++k) tri_regs[k] = sTri[k];
+        }
         const uint32_t bin_id = (uint32_t)args.bin_ids[bin];
         int until_keep = args.thin - (int)((uint64_t)step_first % (uint64_t)args.thin);
         long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
@@ -162,7 +169,9 @@ __global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(con
                     q[l] = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, xrow[l])));
                     outside = outside | (q[l] < args.lo[l]) | (q[l] > args.hi[l]);   // mda.py:1575; a NaN compares false, as there
                 }
-                const double chi = outside ? CUDART_INF : chi_from_factor<L>(sTri, q);
+                double chi;
+                if constexpr (kTriInRegs) chi = outside ? CUDART_INF : chi_from_factor_regs<L>(tri_regs, q);
+                else chi = outside ? CUDART_INF : chi_from_factor<L>(sTri, q);
                 const double newlnp = chi * -0.5;                              // C/ChiSquare.c:212; outside the box: -inf (mda.py:1576)
                 saw_nan = saw_nan || (newlnp != newlnp);
                 const double oldlnp = sLnp[gw];

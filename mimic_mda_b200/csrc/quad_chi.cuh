@@ -53,4 +53,21 @@ __device__ __forceinline__ double chi_from_factor(const double *__restrict__ tri
     return chi;
 }
 
+// The same with T held in registers (indices are compile-time constants after unrolling): for the build that has an SM's
+// register file to itself.  t[] in the padded layout of load_factor.
+template <int L>
+__device__ __forceinline__ double chi_from_factor_regs(const double (&t)[quad_padded_doubles(L)], const double (&a)[L]) {
+    double chi = 0.0;
+#pragma unroll
+    for (int i = 0; i <= L; ++i) {
+        const int len = L + 1 - i, o = quad_padded_offset(L, i);
+        double u = 0.0;
+#pragma unroll
+        for (int k = 0; k < len - 1; ++k) u = fma(t[o + k], a[i + k], u);
+        u -= t[o + len - 1];
+        chi = fma(u, u, chi);
+    }
+    return chi;
+}
+
 }  // namespace mda
