@@ -634,7 +634,7 @@ def main():
                  "DFMA pipe and its peak (measured: 36.8 vs 37.1 TFLOP/s) and holds the scheduler's issue port while it runs, so the "
                  "denominator is the same fp64 peak; tcgen05 has no fp64 kind")
     kernel_text = work.ens.describe(args.steps)
-    is_quad = kernel_text.startswith("ensemble_quad_kernel")
+    is_quad = kernel_text.startswith(("ensemble_quad_kernel", "ensemble_qws_kernel"))
     roofline = roofline_of(kernel_text + "; one persistent launch of %d steps" % args.steps,
                            s_ms * 1e-3, s_flops, s_bytes, args.workload + ("_sampler_quad" if is_quad else "_sampler"),
                            "not used by this kernel: (L+1)(L+2)/2 DFMA per evaluation from the triangular factor; the DMMA steppers "

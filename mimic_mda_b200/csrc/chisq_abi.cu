@@ -117,6 +117,7 @@ int ensure_runtime() {
     MDA_CUDA(configure_ensemble_mma_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, DMMA ensemble)");
     MDA_CUDA(configure_ensemble_ws_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, warp-specialised DMMA ensemble)");
     MDA_CUDA(configure_ensemble_quad_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, triangular-factor ensemble)");
+    MDA_CUDA(configure_ensemble_qws_kernels(g_rt.smem_optin), "cudaFuncSetAttribute(max dynamic smem, warp-specialised triangular-factor ensemble)");
     g_rt.ready = true;
     return MDA_OK;
 }
@@ -194,7 +195,7 @@ struct MdaStore {
     std::vector<double> host;        // [bins][n_pad/2][1+L][2]  (the HBM layout)
     std::vector<double> host_mma;    // [bins][n_tiles][8 (1+L)]  fragment-major copy for the DMMA stepper
     int n_tiles = 0;                 // angle tiles of 8
-    std::vector<double> host_quad;   // [bins][(L+1)(L+2)/2]  packed triangular factor of [D^T | d] (see factor_bin)
+    std::vector<double> host_quad;   // [bins][quad_stride(L)]  packed triangular factor of [D^T | d] (see factor_bin)
     double *d_quad = nullptr;
     std::vector<int> n_pts;          // [bins]
     std::vector<double> lo, hi;      // [L]
@@ -297,7 +298,7 @@ void factor_bin(const MdaStore *s, int bin, double *packed) {
 
 int upload_store(MdaStore *s) {
     if (!s->dirty) return MDA_OK;
-    for (int b = 0; b < s->bins; ++b) factor_bin(s, b, s->host_quad.data() + (size_t)b * (size_t)quad_doubles(s->n_l));
+    for (int b = 0; b < s->bins; ++b) factor_bin(s, b, s->host_quad.data() + (size_t)b * (size_t)quad_stride(s->n_l));
     MDA_CUDA(cudaMemcpyAsync(s->d_quad, s->host_quad.data(), sizeof(double) * s->host_quad.size(), cudaMemcpyHostToDevice,
                              s->stream), "store upload (triangular factors)");
     MDA_CUDA(cudaMemcpyAsync(s->d_consts, s->host.data(), sizeof(double) * s->host.size(), cudaMemcpyHostToDevice,
@@ -500,10 +501,14 @@ EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
     const bool want_dfma = impl && strcmp(impl, "dfma") == 0, want_ws = impl && strcmp(impl, "ws") == 0,
                want_mma = impl && strcmp(impl, "mma") == 0, want_quad = impl && strcmp(impl, "quad") == 0,
-               want_direct = impl && strcmp(impl, "direct") == 0;       // angle-by-angle evaluation, stepper picked by shape
+               want_direct = impl && strcmp(impl, "direct") == 0,       // angle-by-angle evaluation, stepper picked by shape
+               want_qws = impl && strcmp(impl, "qws") == 0;
     EnsembleShape shape{};
-    // default: the triangular-factor stepper (fewest operations per evaluation, same chains); the others on request
-    if ((want_quad || !(want_dfma || want_ws || want_mma || want_direct)) && choose_ensemble_quad_shape(walkers, s->n_l, g_rt.smem_optin, &shape)) return shape;
+    // default: the triangular-factor stepper (fewest operations per evaluation, same chains); the others on request.
+    // Warp-specialised (ensemble_qws_kernel) below two bins per SM, a plain CTA per bin and several per SM from there on.
+    if ((want_qws || (!impl && s->bins < 2 * g_rt.sm_count)) &&
+        choose_ensemble_qws_shape(s->bins, walkers, s->n_l, g_rt.sm_count, g_rt.smem_optin, &shape)) return shape;
+    if ((want_quad || want_qws || !(want_dfma || want_ws || want_mma || want_direct)) && choose_ensemble_quad_shape(walkers, s->n_l, g_rt.smem_optin, &shape)) return shape;
     if (!want_dfma) {
         const bool prefer_mma = want_mma || (!want_ws && s->bins >= 2 * g_rt.sm_count);
         const int wt = env_int("MDA_ENS_WT", 0);
@@ -594,6 +599,17 @@ SteppingPlan plan_quad_stepping(const MdaStore *s, const EnsembleShape &shape, i
     p.chunk_steps = std::max(1, chunk_steps);
     p.n_chunks = (nSteps + p.chunk_steps - 1) / p.chunk_steps;
     return p;
+}
+
+// Grid of the warp-specialised triangular-factor stepper: a CTA per bin while they are all resident at once, else as many
+// CTAs as are resident, each carrying an equal share of the bins' steps (see qws_next_unit).  MDA_ENS_GRID overrides (tests).
+int qws_grid(const MdaStore *s, const EnsembleShape &shape) {
+    const int capacity = ensemble_qws_capacity(s->n_l, shape, g_rt.sm_count);
+    if (capacity < 1) return 0;
+    int grid = std::min(s->bins, capacity);
+    const int force_grid = env_int("MDA_ENS_GRID", 0);
+    if (force_grid > 0) grid = std::max(1, std::min(force_grid, grid));
+    return grid;
 }
 
 MdaEnsemble *as_ensemble(void *p, const char *fn) {
@@ -751,7 +767,7 @@ void *mdaStoreCreate(int numBins, int numL, int maxPts) {
     s->host.assign((size_t)numBins * bin_stride(s), 0.0);
     s->n_tiles = (s->n_pad + 7) / 8;
     s->host_mma.assign((size_t)numBins * (size_t)s->n_tiles * 8 * (size_t)(numL + 1), 0.0);
-    s->host_quad.assign((size_t)numBins * (size_t)quad_doubles(numL), 0.0);
+    s->host_quad.assign((size_t)numBins * (size_t)quad_stride(numL), 0.0);
     s->n_pts.assign((size_t)numBins, 0);
     s->lo.assign((size_t)numL, 0.0);
     s->hi.assign((size_t)numL, 1.0);
@@ -1143,7 +1159,15 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.n_tiles = s->n_tiles;
     args.quad = s->d_quad;
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
-    if (shape.quad) {
+    if (shape.qws) {
+        const int grid = qws_grid(s, shape);
+        if (grid < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
+        args.chunk_steps = nSteps;
+        args.n_chunks = 1;
+        args.progress = e->d_progress;
+        args.launch_serial = (++e->launches) << 32;
+        MDA_CUDA(launch_ensemble_qws(args, shape, grid, s->stream), "ensemble stepping launch (triangular factor, warp-specialised)");
+    } else if (shape.quad) {
         const SteppingPlan plan = plan_quad_stepping(s, shape, nSteps);
         if (plan.grid < 1) return set_error(MDA_ERR_CUDA, "mdaEnsembleAdvance: the stepping kernel cannot be resident");
         args.chunk_steps = plan.chunk_steps;
@@ -1178,7 +1202,14 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
     if (rc) return rc;
     MdaStore *s = e->store;
     const EnsembleShape shape = ensemble_shape_for(s, e->walkers);
-    if (shape.quad) {
+    if (shape.qws) {
+        snprintf(text, (size_t)textLen,
+                 "ensemble_qws_kernel<L=%d,%s>: chi^2 = |T [a; -1]|^2 from the bin's triangular factor (%d multiply-adds per evaluation), 8 walker warps "
+                 "(a thread per walker of the active half) + 4 draw warps (Philox draws of the next half-step, chain stores), one barrier per half-step, "
+                 "bulk-TMA state load and chain stores, %zu B shared memory; %d CTAs for %d bins%s",
+                 s->n_l, shape.treg ? "T in registers via setmaxnreg 208/56/40" : "T in shared memory", quad_doubles(s->n_l), shape.smem_bytes,
+                 qws_grid(s, shape), s->bins, qws_grid(s, shape) < s->bins ? " (every CTA carries the same number of bin-steps; cooperative launch)" : "");
+    } else if (shape.quad) {
         snprintf(text, (size_t)textLen,
                  "ensemble_quad_kernel<L=%d>: chi^2 = |T [a; -1]|^2 from the bin's triangular factor (%d multiply-adds per evaluation), %d threads x %d walkers, "
                  "one barrier per half-step, bulk-TMA chain stores, %zu B shared memory; %d CTAs, %d bins x %d chunks of %d steps",
@@ -1213,7 +1244,14 @@ int mdaEnsembleSynchronize(void *ens) {
     int status = 0;
     MDA_CUDA(cudaMemcpyAsync(&status, e->d_status, sizeof(int), cudaMemcpyDeviceToHost, e->store->stream), "ensemble status read");
     MDA_CUDA(cudaStreamSynchronize(e->store->stream), "mdaEnsembleSynchronize");
-    if (status & 4) return set_error(MDA_ERR_CUDA, "ensemble stepping gave up: a unit of work waited ~3 s for its predecessor (is another kernel holding SMs of this device?)");
+    if (status & 4) {
+        // bins were stopped at different steps: the ensemble is torn, nobody may continue from it
+        e->has_state = false;
+        e->kept = 0;
+        cudaMemsetAsync(e->d_status, 0, sizeof(int), e->store->stream);
+        return set_error(MDA_ERR_CUDA, "ensemble stepping gave up: a piece of work waited seconds for its predecessor (is another kernel holding SMs of "
+                                       "this device?); the ensemble state is invalid, call mdaEnsembleSetState again");
+    }
     if (status & 1) return set_error(MDA_ERR_BAD_STATE, "lnprob returned NaN during ensemble stepping");
     return MDA_OK;
 }

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(con
         }
         for (int i = tid; i < W * L; i += T) sPos[i] = __ldcg(gPos + i);
         for (int w = tid; w < W; w += T) { sLnp[w] = __ldcg(gLnp + w); sAcc[w] = __ldcg(gAcc + w); }
-        load_factor<L>(sTri, args.quad + (size_t)bin * quad_doubles(L), tid, T);
+        load_factor<L>(sTri, args.quad + (size_t)bin * quad_stride(L), tid, T);
         fence_proxy_async_smem();
         __syncthreads();
 

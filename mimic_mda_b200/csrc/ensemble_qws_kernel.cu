@@ -1,0 +1,621 @@
+// ensemble_qws_kernel.cu -- the triangular-factor stepper, warp-specialised: walker warps and draw warps.
+//
+// Same job, same random streams, same arithmetic and therefore the same chains as ensemble_quad_kernel.cu (the
+// reference's host loop emcee.EnsembleSampler.run_mcmc -> ln_post_prob per walker, mda.py:1128-1131, 1540-1578, with
+// chi^2(a) = |T [a; -1]|^2 from the bin's triangular factor, quad_chi.cuh).  What changes is who does what, and when.
+//
+// A half-step of the plain kernel is ~400 instructions per walker thread of which only ~170 depend on the ensemble's
+// state; the rest -- the Philox4x32-10 draw, the stretch factor z = ((a-1) u + 1)^2 / a, the partner index, the
+// single-precision estimate of (L-1) ln z - ln u' -- depends on the counter alone.  With one bin per SM (the shapes
+// BASELINE.json names: 100 bins, or 25 per GPU when C4 is spread over 8 GPUs) there are two walker warps per scheduler and
+// every half-step is a chain of exposed latencies (ncu: a warp issues in 15 % of its cycles).  Here
+//
+//   * 8 WALKER warps (thread i = walker i of the half being updated) take what the draw warps left for this half-step,
+//     gather the partner row, propose, test the box prior (mda.py:1574-1576), evaluate chi^2, decide, overwrite their row.
+//     The accept test is two thresholds on chi^2 prepared while chi^2 is being summed;
+//   * 4 DRAW warps stay two half-steps ahead with the draws (a ring of three slots in shared memory) -- work that is
+//     independent of the walker warps' chain and fills their stall slots.  One of their threads owns every bulk copy: the
+//     chain stores (issued after the half-step's barrier, waited for before the next one), the state of the next piece of
+//     work coming in and the state of the last one going back;
+//   * one __syncthreads per half-step, as before.
+//
+// A CTA that has its SM to itself (TREG build) moves registers from the draw warps to the walker warps with setmaxnreg
+// (208 for a walker thread, 56 for a draw thread, 40 for the copy warpgroup): T (55 doubles at L = 9) and the thread's own two rows stay in registers.  The other build keeps T in
+// shared memory and fits two CTAs per SM.
+//
+// Schedule: see qws_next_unit.  With more bins than resident CTAs (C4: 200 bins on 148 SMs) every CTA carries the same
+// number of bin-steps whatever the length of the launch; a CTA's pieces of work are double-buffered in shared memory, the
+// next one's state (positions, log-probabilities, factor) arriving by bulk copy while the current one steps, and the draw
+// pipeline runs across the boundary: a switch costs two barriers.
+#include "philox.cuh"
+#include "quad_chi.cuh"
+
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
+
+namespace mda {
+
+namespace {
+
+constexpr int kStatusNaN = 1;
+constexpr int kStatusStalled = 4;             // a piece of work waited 4 s for the other piece of its bin: the launch gave up
+constexpr int kWalkerThreads = 256;           // 8 walker warps: one walker of the active half each
+constexpr int kDrawThreads = 128;             // 4 draw warps (one warpgroup: setmaxnreg works on warpgroups)
+constexpr int kThreads = kWalkerThreads + kDrawThreads;          // two CTAs per SM: a draw thread also copies
+constexpr int kThreadsLone = kThreads + 128;                      // a CTA with its SM to itself: plus a copy warpgroup (see qws_service)
+
+struct QwsSmem {
+    size_t lnp, fac, buf_bytes, z, ua, pf, tri, total;       // a piece's buffer: positions at 0, then lnp, then fac; buffer b at b * buf_bytes
+    __host__ __device__ QwsSmem(int walkers, int n_l, bool tri_in_smem) {
+        const size_t h = (size_t)walkers / 2;
+        size_t off = 0;
+        off += (size_t)walkers * (size_t)n_l * 8;                             // [W][L] dense, updated in place; bulk-stored as is
+        lnp = off; off += (size_t)walkers * 8;                                // [W]
+        fac = off; off += (size_t)quad_stride(n_l) * 8;                       // the bin's packed factor as it lies in the store
+        buf_bytes = off;
+        off *= 2;                                                             // two pieces of work: the current one and the next one coming in
+        z = off; off += 3 * h * 8;                                            // [3][H] stretch factor of the half-step's draw (ring: t, t+1, t+2)
+        ua = off; off += 3 * h * 8;                                           // [3][H] acceptance uniform
+        pf = off; off += 3 * h * 8;                                           // [3][H] {partner index, float (L-1) ln z - ln u'}
+        off = (off + 15) & ~(size_t)15;
+        tri = off; if (tri_in_smem) off += (size_t)quad_padded_doubles(n_l) * 8;
+        total = (off + 15) & ~(size_t)15;
+    }
+};
+
+__device__ __forceinline__ uint32_t q_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void q_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void q_bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(q_smem_addr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void q_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void q_bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void q_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void q_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(q_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void q_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(q_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void q_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(q_smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(q_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void q_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QWS_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QWS_DONE;\n"
+        "bra QWS_WAIT;\n"
+        "QWS_DONE:\n"
+        "}\n" ::"r"(q_smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long q_ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void q_st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long q_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ double q_uniform43(uint32_t w, uint32_t x, uint32_t y) {
+    return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
+}
+
+// One piece of work of a CTA: steps [s0, s1) of the launch for bin `bin`.
+struct QwsUnit {
+    int bin, s0, s1;
+    bool waits;        // the bin's earlier steps run on the next CTA: take the state over behind its progress word
+    bool signals;      // the bin's later steps run on the previous CTA: publish the state when done
+};
+
+// The schedule.  Up to one bin per CTA every CTA simply owns a bin.  With more bins than CTAs (grid = SMs: C4's 200 bins on
+// 148 SMs) the bins' step ranges are laid end to end on a ribbon of bins x n_steps bin-steps and the ribbon is cut into
+// gridDim.x equal segments, one per CTA (McNaughton's wrap-around rule): every CTA carries the same number of bin-steps
+// whatever the launch length, a bin is cut at most once, and its two pieces never overlap in time -- the piece at the START of
+// CTA j+1's segment takes the bin's FIRST steps, the piece at the END of CTA j's segment the rest, which (a segment being at
+// least n_steps long) begins after the other has ended.  The later piece still waits for the earlier one's progress word; the
+// grid is launched cooperatively, so the CTA it waits for is resident by construction.
+__device__ __forceinline__ bool qws_next_unit(const EnsembleArgs &args, long long &p, long long r1, QwsUnit &u) {
+    if (p >= r1) return false;
+    const long long K = args.n_steps;
+    const long long b = p / K, o = p - b * K;
+    const long long len = min(K - o, r1 - p);
+    u.bin = (int)b;
+    if (o == 0 && len == K) { u.s0 = 0; u.s1 = (int)K; u.waits = u.signals = false; }
+    else if (o == 0) { u.s0 = (int)(K - len); u.s1 = (int)K; u.waits = true; u.signals = false; }     // the end of my segment: the bin's last steps
+    else { u.s0 = 0; u.s1 = (int)len; u.waits = false; u.signals = true; }                              // the start of my segment: its first steps
+    p += len;
+    return true;
+}
+
+struct QwsCtx {
+    unsigned char *smem_raw;
+    uint64_t *s_bar;
+    int *s_abort;
+    int W, H;
+    long long total, ribbon_end;
+    uint32_t seed0, seed1;
+    bool keeping, split;
+    QwsSmem lay{2, 1, false};
+};
+
+// What the non-walker threads do.  DRAWS: this thread (d of 128) makes the draws, two half-steps ahead of the walkers.
+// COPIES: thread d == 0 owns every bulk copy and the progress words.  One warpgroup does both (two CTAs per SM), or -- in the
+// build whose CTA has its SM to itself -- the draw warps only draw and one thread of a fourth warpgroup only copies: issuing
+// two bulk stores and computing their addresses cost the draw warp that did it ~500 cycles per half-step, and the draw warps
+// are the last to arrive at the half-step's barrier as it is.
+template <int L, bool DRAWS, bool COPIES, bool PROF>
+__device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsCtx &cx, QwsUnit unit, long long ribbon, const int d) {
+    unsigned char *smem_raw = cx.smem_raw;
+    uint64_t *s_bar = cx.s_bar;
+    int &s_abort = *cx.s_abort;
+    const int W = cx.W, H = cx.H;
+    const long long total = cx.total, ribbon_end = cx.ribbon_end;
+    const uint32_t seed0 = cx.seed0, seed1 = cx.seed1;
+    const bool keeping = cx.keeping, split = cx.split;
+    const QwsSmem &lay = cx.lay;
+    double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
+    double *sUa = reinterpret_cast<double *>(smem_raw + lay.ua);
+    uint2 *sPF = reinterpret_cast<uint2 *>(smem_raw + lay.pf);
+    auto pos_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes); };
+    auto lnp_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes + lay.lnp); };
+    auto fac_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes + lay.fac); };
+    const bool copier = COPIES && d == 0;
+    QwsUnit next;
+    const double a_scale = args.a;
+    const float dim_m1f = (float)(L - 1);
+    const uint32_t state_bytes = (uint32_t)W * (L + 1) * 8u + (uint32_t)quad_stride(L) * 8u;
+    auto load_state = [&](int bin, int b) {              // (thread d == 0) positions, log-probabilities and factor of `bin` into buffer b
+        q_mbar_expect_tx(&s_bar[b], state_bytes);
+        q_bulk_g2s(pos_of(b), args.pos + (size_t)bin * W * L, (uint32_t)W * L * 8u, &s_bar[b]);
+        q_bulk_g2s(lnp_of(b), args.lnp + (size_t)bin * W, (uint32_t)W * 8u, &s_bar[b]);
+        q_bulk_g2s(fac_of(b), args.quad + (size_t)bin * quad_stride(L), (uint32_t)quad_stride(L) * 8u, &s_bar[b]);
+    };
+    auto make_draws = [&](uint32_t bin_id, uint32_t tt, int ring) {   // the draws of half-step tt into slot `ring` of the ring of three
+        const int buf = ring * H;
+        const uint32_t w_base = (tt & 1u) ? (uint32_t)H : 0u;
+        // a thread's two walkers (d and d + 128) in one straight-line block: two independent Philox chains interleave
+        const int i0 = d, i1 = min(d + kDrawThreads, H - 1);
+        const Philox4 r0 = philox4x32_10(Philox4{w_base + (uint32_t)min(i0, H - 1), bin_id, tt, 0u}, seed0, seed1);
+        Philox4 r1 = r0;
+    if (H > kDrawThreads) r1 = philox4x32_10(Philox4{w_base + (uint32_t)i1, bin_id, tt, 0u}, seed0, seed1);
+        auto finish = [&](const Philox4 &r, int i, bool valid) {
+            // numpy arithmetic is one rounding per operation: no FMA contraction
+            const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
+            const double z2 = __dmul_rn(zr, zr);
+            const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;   // ((a-1) u + 1)^2 / a
+            const double ua = q_uniform43(r.w, r.x, r.y);
+            const float fast = dim_m1f * __logf((float)z) - __logf((float)ua);   // decides all but near-ties
+            if (valid) {
+                sZ[buf + i] = z;
+                sUa[buf + i] = ua;
+                sPF[buf + i] = make_uint2(__umulhi(r.z, (uint32_t)H), __float_as_uint(fast));
+            }
+        };
+        finish(r0, i0, i0 < H);
+        if (H > kDrawThreads) finish(r1, i1, d + kDrawThreads < H);
+    };
+    // the draw cursor runs over the CTA's whole sequence of half-steps, across its pieces of work
+    long long d_ribbon = (long long)blockIdx.x * total / gridDim.x;
+    QwsUnit d_unit;
+    bool d_valid = qws_next_unit(args, d_ribbon, ribbon_end, d_unit);
+    uint32_t d_bin_id = 0, d_t = 0, d_t_end = 0;
+    auto cursor_open = [&]() {
+        d_bin_id = (uint32_t)args.bin_ids[d_unit.bin];
+        d_t = 2u * (uint32_t)(args.step0 + d_unit.s0);
+        d_t_end = 2u * (uint32_t)(args.step0 + d_unit.s1);
+    };
+    int d_ring = 0;
+    auto draw_one = [&]() {                              // the next half-step of the sequence, if there is one
+        if (!d_valid) return;
+        make_draws(d_bin_id, d_t, d_ring);
+        d_ring = d_ring == 2 ? 0 : d_ring + 1;
+        if (++d_t == d_t_end) { d_valid = qws_next_unit(args, d_ribbon, ribbon_end, d_unit); if (d_valid) cursor_open(); }
+    };
+    cursor_open();
+    int buf = 0;
+    bool next_loaded = false;
+    long long p_d[5] = {0, 0, 0, 0, 0};
+    int pending_release = -1;                            // bin whose state store must complete before its progress word is set
+    if (copier && !unit.waits) load_state(unit.bin, 0);
+    if (copier && unit.waits) {                          // (a one-unit segment that is the tail of a bin)
+        const unsigned long long want = args.launch_serial + 1ull, t_start = q_globaltimer_ns();
+        while (q_ld_acquire_u64(args.progress + unit.bin) != want) {
+            __nanosleep(100);
+            if (q_globaltimer_ns() - t_start > 4000000000ull) { s_abort = 1; break; }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (!s_abort) load_state(unit.bin, 0);
+    }
+    if constexpr (DRAWS) { draw_one(); draw_one(); }
+    __syncthreads();                                     // (A) the first draws are in place
+    while (true) {
+        const bool has_next = qws_next_unit(args, ribbon, ribbon_end, next);
+        const int bin = unit.bin;
+        if (s_abort) break;
+        const long long step_first = args.step0 + unit.s0;
+        const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = 2u * (uint32_t)(args.step0 + unit.s1);
+        int until_keep = args.thin - (int)((uint64_t)step_first % (uint64_t)args.thin);
+        long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
+        double *sPos = pos_of(buf), *sLnp = lnp_of(buf);
+        for (uint32_t t = t_begin; t < t_end; ++t) {
+            const uint32_t half = t & 1u;
+            const int s_base = half ? H : 0;
+            const bool kept_step = keeping && until_keep == 1 && slot < args.keep_cap;
+            long long c0 = 0;
+            if constexpr (PROF) c0 = clock64();
+            if constexpr (DRAWS) draw_one();
+            if constexpr (PROF) { const long long c1 = clock64(); p_d[0] += c1 - c0; c0 = c1; }
+            // the last store read the half that is written next, a whole half-step after it was issued: no wait in practice
+            if (keeping && copier) q_bulk_wait_read_all();
+            if constexpr (PROF) { const long long c1 = clock64(); p_d[1] += c1 - c0; c0 = c1; }
+            __syncthreads();                             // (B) the half is complete
+            if constexpr (PROF) { const long long c1 = clock64(); p_d[2] += c1 - c0; c0 = c1; }
+            if (copier) {
+                if (pending_release >= 0) {              // the previous piece's state is on its way out since the switch
+                    q_bulk_wait_all();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    q_st_release_u64(args.progress + pending_release, args.launch_serial + 1ull);
+                    pending_release = -1;
+                }
+                if (kept_step) {
+                    double *dst = args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L;
+                    double *ldst = args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W;
+                    if (split) {                         // the half just updated is final for this step
+                        q_bulk_s2g(dst + (size_t)s_base * L, sPos + (size_t)s_base * L, (uint32_t)H * L * 8u);
+                        q_bulk_s2g(ldst + s_base, sLnp + s_base, (uint32_t)H * 8u);
+                        q_bulk_commit();
+                    } else if (half) {
+                        q_bulk_s2g(dst, sPos, (uint32_t)W * L * 8u);
+                        q_bulk_s2g(ldst, sLnp, (uint32_t)W * 8u);
+                        q_bulk_commit();
+                    }
+                }
+                // the next piece's state comes in behind this one's steps (its buffer was last read by the store of the piece
+                // before this one); a piece that continues another CTA's bin only once that CTA has published it
+                if (has_next && !next_loaded && t > t_begin) {
+                    bool ready = !next.waits;
+                    if (!ready && q_ld_acquire_u64(args.progress + next.bin) == args.launch_serial + 1ull) {
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        ready = true;
+                    }
+                    if (ready) {
+                        q_bulk_wait_read_all();
+                        load_state(next.bin, buf ^ 1);
+                        next_loaded = true;
+                    }
+                }
+            }
+            if (kept_step && !split && half) {           // whole-state store: nobody may write until it has been read
+                if (copier) q_bulk_wait_read_all();
+                __syncthreads();                         // (C)
+            }
+            if (half) {
+                if (--until_keep == 0) { until_keep = args.thin; if (keeping) ++slot; }
+            }
+            if constexpr (PROF) { const long long c1 = clock64(); p_d[3] += c1 - c0; p_d[4] += 1; }
+        }
+        // ---- switch: this piece's state goes back, the next one's must be on its way
+        if (copier && has_next && !next_loaded) {
+            const unsigned long long want = args.launch_serial + 1ull, t_start = q_globaltimer_ns();
+            while (next.waits && q_ld_acquire_u64(args.progress + next.bin) != want) {
+                __nanosleep(100);
+                if (q_globaltimer_ns() - t_start > 4000000000ull) { s_abort = 1; break; }     // 4 s: it is not coming
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+            if (!s_abort) { q_bulk_wait_read_all(); load_state(next.bin, buf ^ 1); }
+        }
+        __syncthreads();                                 // (D) every walker thread has fenced its last writes; abort flag settled
+        if (copier) {
+            q_bulk_s2g(args.pos + (size_t)bin * W * L, sPos, (uint32_t)W * L * 8u);
+            q_bulk_s2g(args.lnp + (size_t)bin * W, sLnp, (uint32_t)W * 8u);
+            q_bulk_commit();
+            if (unit.signals) pending_release = bin;     // the rest of this bin's steps is waiting on another CTA
+        }
+        if (!has_next) break;
+        unit = next;
+        buf ^= 1;
+        next_loaded = false;
+    }
+    if constexpr (PROF) if (d == 0 && args.prof) for (int k = 0; k < 5; ++k) args.prof[(size_t)blockIdx.x * 128 + (DRAWS ? 112 : 120) + k] = p_d[k];
+    if (copier) {
+        q_bulk_wait_all();
+        if (pending_release >= 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            q_st_release_u64(args.progress + pending_release, args.launch_serial + 1ull);
+        }
+    }
+}
+
+// PROF: thread 0 stamps the phases of every piece of work into args.prof[cta][...] (debug build, selected when
+// mdaEnsembleProfile switched the counters on).
+template <int L, bool TREG, bool PROF = false>
+__global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) ensemble_qws_kernel(const EnsembleArgs args) {
+    constexpr bool COPYWG = TREG;                            // a fourth warpgroup whose first thread does nothing but the bulk copies
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_abort;
+    const int tid = threadIdx.x;
+    const bool is_walker = tid < kWalkerThreads;
+    const int W = args.walkers, H = W >> 1;
+    const QwsSmem lay(W, L, !TREG);
+    double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
+    double *sUa = reinterpret_cast<double *>(smem_raw + lay.ua);
+    uint2 *sPF = reinterpret_cast<uint2 *>(smem_raw + lay.pf);
+    double *sTri = reinterpret_cast<double *>(smem_raw + lay.tri);
+    auto pos_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes); };
+    auto lnp_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes + lay.lnp); };
+    auto fac_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes + lay.fac); };
+
+    if (tid == 0) {
+        q_mbar_init(&s_bar[0], 1);
+        q_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_abort = 0;
+    }
+    const uint32_t seed0 = args.seed_lo, seed1 = args.seed_hi;
+    const bool keeping = args.chain != nullptr;
+    // a half can be stored on its own if its rows and log-probabilities are 16-byte multiples (bulk-copy granularity)
+    const bool split = ((H * L) & 1) == 0 && (H & 1) == 0;
+    // my segment of the ribbon of bins x n_steps bin-steps (a bin per CTA when the grid is the number of bins)
+    const long long total = (long long)args.bins * args.n_steps;
+    long long ribbon = (long long)blockIdx.x * total / gridDim.x;
+    const long long ribbon_end = (long long)(blockIdx.x + 1) * total / gridDim.x;
+    QwsUnit unit, next;
+    bool has_unit = qws_next_unit(args, ribbon, ribbon_end, unit);
+    __syncthreads();                                         // (I) the mbarriers are initialised
+    if (!has_unit) return;
+
+    if (!is_walker) {
+        // =========================================================== draw warps and the copy thread
+        QwsCtx cx;
+        cx.smem_raw = smem_raw; cx.s_bar = s_bar; cx.s_abort = &s_abort; cx.W = W; cx.H = H; cx.total = total; cx.ribbon_end = ribbon_end;
+        cx.seed0 = seed0; cx.seed1 = seed1; cx.keeping = keeping; cx.split = split; cx.lay = lay;
+        if constexpr (COPYWG) {
+            if (tid < kWalkerThreads + kDrawThreads) {
+                asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+                qws_service<L, true, false, PROF>(args, cx, unit, ribbon, tid - kWalkerThreads);
+            } else {
+                asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+                qws_service<L, false, true, PROF>(args, cx, unit, ribbon, tid - kWalkerThreads - kDrawThreads);
+            }
+        } else {
+            qws_service<L, true, true, PROF>(args, cx, unit, ribbon, tid - kWalkerThreads);
+        }
+        return;
+    }
+
+    // =============================================================== walker warps
+    if constexpr (TREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    constexpr bool XREG = TREG;                              // with 224 registers the thread's own two rows live in registers too
+    const bool owner = tid < H;
+    const int me = min(tid, H - 1);
+    const double dim_m1 = (double)(L - 1);
+    bool saw_nan = false;
+    int buf = 0, ring = 0, unit_index = 0;
+    uint32_t load_parity[2] = {0u, 0u};
+    double z = 0.0;
+    uint2 pf = make_uint2(0u, 0u);
+    __syncthreads();                                         // (A)
+    if (owner) { z = sZ[me]; pf = sPF[me]; }                 // the first half-step's draw; from then on fetched one half-step ahead
+    while (true) {
+        const bool has_next = qws_next_unit(args, ribbon, ribbon_end, next);
+        const int bin = unit.bin;
+        if (s_abort) {
+            if (tid == 0) atomicOr(args.status, kStatusStalled);
+            break;
+        }
+        long long *ustamp = (PROF && tid == 0 && args.prof && unit_index < 12) ? args.prof + (size_t)blockIdx.x * 128 + 16 + 8 * unit_index : nullptr;
+        ++unit_index;
+        if (ustamp) { ustamp[0] = clock64(); ustamp[6] = unit.s1 - unit.s0; }
+        double *sPos = pos_of(buf), *sLnp = lnp_of(buf);
+        q_mbar_wait(&s_bar[buf], buf ? load_parity[1] : load_parity[0]);      // the piece's state has arrived
+        if (buf) load_parity[1] ^= 1u; else load_parity[0] ^= 1u;
+        if (ustamp) ustamp[1] = clock64();
+        double tri_regs[TREG ? quad_padded_doubles(L) : 1];
+        {
+            const double *packed = fac_of(buf);
+            if constexpr (TREG) {
+#pragma unroll
+                for (int k = 0; k < quad_padded_doubles(L); ++k) tri_regs[k] = 0.0;
+#pragma unroll
+                for (int i = 0; i <= L; ++i)
+#pragma unroll
+                    for (int k = 0; k < L + 1 - i; ++k) tri_regs[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
+            } else {
+                // rows padded for 16-byte broadcast reads (walker warps only: named barrier 1, 256 threads; the previous piece's
+                // last read of sTri lies before its barrier (D))
+                for (int k = tid; k < quad_padded_doubles(L); k += kWalkerThreads) sTri[k] = 0.0;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i <= L; ++i)
+                    for (int k = tid; k < L + 1 - i; k += kWalkerThreads) sTri[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        }
+        const long long step_first = args.step0 + unit.s0;
+        const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = 2u * (uint32_t)(args.step0 + unit.s1);
+        int until_keep = args.thin - (int)((uint64_t)step_first % (uint64_t)args.thin);
+        long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
+        // my two walkers: row and log-probability (registers in the XREG build, else re-read from shared memory)
+        double x0[XREG ? L : 1], x1[XREG ? L : 1], lnp0 = 0.0, lnp1 = 0.0;
+        if constexpr (XREG) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) { x0[l] = sPos[(size_t)me * L + l]; x1[l] = sPos[(size_t)(H + me) * L + l]; }
+            lnp0 = sLnp[me];
+            lnp1 = sLnp[H + me];
+        }
+        unsigned int acc0 = 0u, acc1 = 0u;                   // proposals accepted in this piece, per walker of either half
+        if (ustamp) ustamp[2] = clock64();
+
+        auto half_step = [&](const int half, uint32_t t, double (&x)[XREG ? L : 1], double &lnp_reg, unsigned int &acc) {   // half: a literal at both call sites
+            const int s_base = half ? H : 0, c_base = half ? 0 : H;           // updated half; partners come from the other one
+            const bool kept_step = keeping && until_keep == 1 && slot < args.keep_cap;
+            if (owner) {
+                const double *crow = sPos + (size_t)(c_base + (int)pf.x) * L;
+                double *xrow = sPos + (size_t)(s_base + me) * L;
+                const double oldlnp = XREG ? lnp_reg : sLnp[s_base + me];
+                // accept for sure if lnp(q) - lnp(x) + fast > 1e-4, reject for sure if < -1e-4 (fast: the float estimate of
+                // (L-1) ln z - ln u', error < 2e-5); with lnp = -chi^2 / 2 both are thresholds on chi^2, ready before it is
+                const double fast_d = (double)__uint_as_float(pf.y);
+                const double chi_accept = -2.0 * ((oldlnp - fast_d) + 1e-4), chi_reject = -2.0 * ((oldlnp - fast_d) - 1e-4);
+                double q[L];
+                bool outside = false;
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    const double c = crow[l];
+                    const double xl = XREG ? x[XREG ? l : 0] : xrow[l];
+                    q[l] = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, xl)));       // numpy rounding: no FMA contraction
+                    outside = outside | (q[l] < args.lo[l]) | (q[l] > args.hi[l]);   // mda.py:1575; a NaN compares false, as there
+                }
+                double chi;
+                if constexpr (TREG) chi = outside ? CUDART_INF : chi_from_factor_regs<L>(tri_regs, q);
+                else chi = outside ? CUDART_INF : chi_from_factor<L>(sTri, q);
+                saw_nan = saw_nan || (chi != chi);
+                bool accept = chi < chi_accept;
+                if (!accept && !(chi > chi_reject)) {        // near a tie (or NaN): emcee's test in full precision
+                    const double newlnp = chi * -0.5;
+                    const double zlog = __dmul_rn(dim_m1, log(z));
+                    accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(sUa[ring * H + me]);
+                }
+                if (accept) {
+                    const double newlnp = chi * -0.5;                          // C/ChiSquare.c:212; outside the box: -inf (mda.py:1576), never accepted
+#pragma unroll
+                    for (int l = 0; l < L; ++l) { xrow[l] = q[l]; if constexpr (XREG) x[XREG ? l : 0] = q[l]; }
+                    sLnp[s_base + me] = newlnp;
+                    if constexpr (XREG) lnp_reg = newlnp;
+                    acc += 1u;
+                }
+            }
+            // the draws of the next half-step (of this piece or of the next one) are in place since the last barrier
+            const int next_ring = ring == 2 ? 0 : ring + 1;
+            if (owner && (t + 1 < t_end || has_next)) { z = sZ[next_ring * H + me]; pf = sPF[next_ring * H + me]; }
+            ring = next_ring;
+            if (kept_step) q_fence_proxy_async();            // my rows before the bulk store reads them
+            __syncthreads();                                 // (B)
+            if (kept_step && !split && half) __syncthreads();   // (C)
+            if (half) {
+                if (--until_keep == 0) { until_keep = args.thin; if (keeping) ++slot; }
+            }
+        };
+        for (uint32_t t = t_begin; t < t_end; t += 2) {      // t_begin is even: a step is the update of half 0, then of half 1
+            half_step(0, t, x0, lnp0, acc0);
+            half_step(1, t + 1, x1, lnp1, acc1);
+        }
+        if (ustamp) ustamp[3] = clock64();
+        q_fence_proxy_async();
+        __syncthreads();                                     // (D)
+        if (owner) {                                         // the bin is mine alone: plain adds; issued after the barrier, so that no fence
+            unsigned int *gAcc = args.nacc + (size_t)bin * W;   // of this piece waits for them (the next barrier orders them before a release)
+            if (acc0) atomicAdd(gAcc + tid, acc0);
+            if (acc1) atomicAdd(gAcc + H + tid, acc1);
+        }
+        if (ustamp) ustamp[4] = clock64();
+        if (!has_next) break;
+        unit = next;
+        buf ^= 1;
+    }
+    if (saw_nan) atomicOr(args.status, kStatusNaN);
+}
+
+using EnsKernel = void (*)(const EnsembleArgs);
+
+template <int L>
+EnsKernel pick_for_l(bool treg) {
+    if constexpr (quad_padded_doubles(L) <= 60) return treg ? ensemble_qws_kernel<L, true> : ensemble_qws_kernel<L, false>;
+    else return ensemble_qws_kernel<L, false>;
+}
+
+template <int... Ls>
+EnsKernel pick_from(int n_l, bool treg, std::integer_sequence<int, Ls...>) {
+    EnsKernel k = nullptr;
+    ((n_l == Ls + 1 ? (k = pick_for_l<Ls + 1>(treg), 0) : 0), ...);
+    return k;
+}
+
+EnsKernel pick_qws_kernel(int n_l, bool treg) { return pick_from(n_l, treg, std::make_integer_sequence<int, kMaxRegL>{}); }
+
+}  // namespace
+
+bool choose_ensemble_qws_shape(int bins, int walkers, int n_l, int sm_count, size_t smem_optin, EnsembleShape *out) {
+    if (n_l < 1 || n_l > kMaxRegL || walkers < 2 || (walkers & 1) || walkers / 2 > kWalkerThreads || bins < 1) return false;
+    EnsembleShape s{};
+    s.threads = kThreads;                                   // (kThreadsLone with T in registers, set below)
+    s.wpt = 1;
+    s.groups = 1;
+    s.qws = true;
+    s.quad = true;
+    // T in registers for a CTA that has its SM to itself (setmaxnreg gives the walker warps 224 registers): one CTA per SM
+    // carrying bins / SMs bins' worth of steps at 1.99 us per bin-step (512 x 9) beats two CTAs per SM (3.61 us per pair) up
+    // to 1.8 bins per SM
+    s.treg = quad_padded_doubles(n_l) <= 60 && 10LL * bins <= 18LL * sm_count;
+    const char *force_treg = getenv("MDA_ENS_TREG");
+    if (force_treg && (force_treg[0] == '0' || force_treg[0] == '1')) s.treg = quad_padded_doubles(n_l) <= 60 && force_treg[0] == '1';
+    if (s.treg) s.threads = kThreadsLone;
+    s.smem_bytes = QwsSmem(walkers, n_l, !s.treg).total;
+    if (s.smem_bytes > smem_optin) return false;
+    s.fits = true;
+    *out = s;
+    return true;
+}
+
+cudaError_t configure_ensemble_qws_kernels(size_t smem_optin) {
+    for (int l = 1; l <= kMaxRegL; ++l)
+        for (int treg = 0; treg < 2; ++treg) {
+            const void *k = reinterpret_cast<const void *>(pick_qws_kernel(l, treg != 0));
+            cudaFuncAttributes fa;
+            cudaError_t e = cudaFuncGetAttributes(&fa, k);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - fa.sharedSizeBytes));
+            if (e != cudaSuccess) return e;
+        }
+    for (const void *k : {reinterpret_cast<const void *>(ensemble_qws_kernel<9, true, true>), reinterpret_cast<const void *>(ensemble_qws_kernel<9, false, true>)}) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_optin - 64));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// Co-resident CTAs on the whole device (a grid smaller than the number of bins is launched cooperatively).
+int ensemble_qws_capacity(int n_l, const EnsembleShape &shape, int sm_count) {
+    EnsKernel k = pick_qws_kernel(n_l, shape.treg);
+    int per_sm = 0;
+    if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(k), shape.threads, shape.smem_bytes) != cudaSuccess)
+        return 0;
+    return per_sm * sm_count;
+}
+
+cudaError_t launch_ensemble_qws(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream) {
+    if (args.bins <= 0 || args.n_steps <= 0) return cudaSuccess;
+    EnsKernel k = pick_qws_kernel(args.n_l, shape.treg);
+    if (args.prof && args.n_l == 9) k = shape.treg ? ensemble_qws_kernel<9, true, true> : ensemble_qws_kernel<9, false, true>;
+    if (!k || !shape.fits || !shape.qws || !args.quad || grid < 1 || grid > args.bins || (grid < args.bins && !args.progress)) return cudaErrorInvalidValue;
+    if (grid == args.bins) {                                 // a bin per CTA: no CTA waits for another
+        k<<<grid, shape.threads, shape.smem_bytes, stream>>>(args);
+        return cudaGetLastError();
+    }
+    // bins cut across CTAs: the piece that waits needs the other one resident -- a cooperative launch fails instead of hanging
+    EnsembleArgs copy = args;
+    void *params[] = {&copy};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k), dim3((unsigned)grid), dim3((unsigned)shape.threads), params, shape.smem_bytes, stream);
+}
+
+}  // namespace mda

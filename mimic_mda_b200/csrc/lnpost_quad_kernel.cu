@@ -20,7 +20,7 @@ template <int L>
 __global__ void __launch_bounds__(kThreads) lnpost_quad_kernel(const BatchArgs a) {
     __shared__ __align__(16) double sTri[quad_padded_doubles(L)];
     const int bin = blockIdx.y;
-    load_factor<L>(sTri, a.quad + (size_t)bin * quad_doubles(L), threadIdx.x, kThreads);
+    load_factor<L>(sTri, a.quad + (size_t)bin * quad_stride(L), threadIdx.x, kThreads);
     __syncthreads();
     const int w = blockIdx.x * kThreads + threadIdx.x;
     if (w >= a.walkers) return;

@@ -32,7 +32,7 @@ struct BatchArgs {
     double hi[kMaxRegL];
     const double *consts_mma;   // DMMA kernel: fragment-major constants [bins][n_tiles][8 (1+L)] (see mma_chi.cuh)
     int n_tiles;                // DMMA kernel: angle tiles of 8
-    const double *quad;         // triangular-factor kernel: [bins][quad_doubles(L)] packed T (see quad_chi.cuh)
+    const double *quad;         // triangular-factor kernel: [bins][quad_stride(L)] packed T (see quad_chi.cuh)
 };
 
 struct TileShape {
@@ -69,7 +69,7 @@ cudaError_t launch_batch_quad(const BatchArgs &args, cudaStream_t stream);
 struct EnsembleArgs {
     const double *consts;      // store layout [bins][n_pad/2][1+L][2]
     const double *consts_mma;  // fragment-major copy [bins][n_tiles][8 (1+L)] (see mma_tile_doubles), or null
-    const double *quad;        // [bins][quad_doubles(L)] packed triangular factor T of [D^T | d]: chi^2(a) = |T [a; -1]|^2, or null
+    const double *quad;        // [bins][quad_stride(L)] packed triangular factor T of [D^T | d]: chi^2(a) = |T [a; -1]|^2, or null
     const int *n_pts;          // [bins]
     const int *bin_ids;        // [bins] global bin index (Philox counter word; partition invariant)
     double *pos;               // [bins][W][L]   ensemble state, updated in place
@@ -103,9 +103,13 @@ struct EnsembleShape {
     bool mma;                  // a DMMA stepper (wpt = tiles of 8 walkers per item)
     bool ws;                   // the warp-specialised one, ensemble_ws_kernel (groups = walker warps); else ensemble_mma_kernel
     bool quad;                 // ensemble_quad_kernel: chi^2 from the bin's triangular factor, one thread per walker
+    bool qws;                  // ensemble_qws_kernel: the same, warp-specialised (walker warps + draw warps); quad is set too
+    bool treg;                 // ensemble_qws_kernel: the factor T in registers (else in shared memory)
 };
 
 __host__ __device__ constexpr int quad_doubles(int n_l) { return (n_l + 1) * (n_l + 2) / 2; }
+// doubles between two bins' packed factors in the store: rounded up to a 16-byte multiple, so that a factor is a bulk-copy source
+__host__ __device__ constexpr int quad_stride(int n_l) { return (quad_doubles(n_l) + 1) & ~1; }
 
 EnsembleShape choose_ensemble_shape(int bins, int walkers, int n_l, int n_pad, int sm_count, size_t smem_optin,
                                     int force_groups, int force_wpt);
@@ -135,6 +139,13 @@ bool choose_ensemble_quad_shape(int walkers, int n_l, size_t smem_optin, Ensembl
 cudaError_t configure_ensemble_quad_kernels(size_t smem_optin);
 int ensemble_quad_capacity(int n_l, const EnsembleShape &shape, int grid, int sm_count);
 cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &shape, int grid, int sm_count, cudaStream_t stream);
+
+// ensemble_qws_kernel.cu: the same stepper warp-specialised -- 8 walker warps + 4 draw warps per bin (walkers / 2 <= 256).
+bool choose_ensemble_qws_shape(int bins, int walkers, int n_l, int sm_count, size_t smem_optin, EnsembleShape *out);
+cudaError_t configure_ensemble_qws_kernels(size_t smem_optin);
+int ensemble_qws_capacity(int n_l, const EnsembleShape &shape, int sm_count);   // co-resident CTAs on the device
+// grid == bins: a CTA per bin; grid < bins: the bins' step ranges cut evenly over `grid` CTAs (cooperative launch, args.progress set)
+cudaError_t launch_ensemble_qws(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);
 
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
 // gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.

@@ -26,9 +26,12 @@ def _problem(n_bins, n_l, n_pts, walkers, ragged=True, seed=17):
                                    # 2500 walkers x 8 parameters (mda_config0.py:93,105), and a wider one
                                    (1, 8, 41, 2500, 12), (2, 9, 60, 3000, 6)])
 # the triangular-factor stepper (the default) and the DMMA steppers (shapes none of those takes run on the DFMA stepper)
-@pytest.mark.parametrize("impl", ["quad", "ws", "mma", "mma-2cta"])
+# "qws": the triangular-factor stepper warp-specialised (the default below two bins per SM), T in registers or in shared memory
+@pytest.mark.parametrize("impl", ["quad", "ws", "mma", "mma-2cta", "qws-treg1", "qws-treg0"])
 def test_device_chain_equals_cpu_restatement(cs_lib, oracle_lib, monkeypatch, shape, impl):
     monkeypatch.setenv("MDA_ENS_IMPL", impl.split("-")[0])
+    if "-treg" in impl:
+        monkeypatch.setenv("MDA_ENS_TREG", impl[-1])
     monkeypatch.setenv("MDA_ENS_DRAWW", "2" if impl.endswith("2cta") else "0")     # 2: without draw warps (two CTAs per SM)
     n_bins, n_l, n_pts, walkers, steps = shape
     consts, counts, lo, hi, p0, _ = _problem(n_bins, n_l, n_pts, walkers)
@@ -96,7 +99,11 @@ def test_split_runs_thinning_and_partition_invariance(cs_lib):
                                  {"MDA_ENS_IMPL": "mma", "MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "5"},
                                  {"MDA_ENS_IMPL": "dfma"}, {"MDA_ENS_IMPL": "quad"},
                                  {"MDA_ENS_IMPL": "quad", "MDA_ENS_GRID": "2", "MDA_ENS_CHUNK": "7"},    # units handed over through HBM
-                                 {"MDA_ENS_IMPL": "quad", "MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "1"}])
+                                 {"MDA_ENS_IMPL": "quad", "MDA_ENS_GRID": "3", "MDA_ENS_CHUNK": "1"},
+                                 # the warp-specialised stepper: a CTA per bin, and 5 bins' steps cut evenly over 2 / 3 / 4 CTAs
+                                 {"MDA_ENS_IMPL": "qws"}, {"MDA_ENS_IMPL": "qws", "MDA_ENS_TREG": "0"},
+                                 {"MDA_ENS_IMPL": "qws", "MDA_ENS_GRID": "2"}, {"MDA_ENS_IMPL": "qws", "MDA_ENS_GRID": "3", "MDA_ENS_TREG": "0"},
+                                 {"MDA_ENS_IMPL": "qws", "MDA_ENS_GRID": "4"}])
 def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
     """Units of (chunk of steps, bin) walked by fewer CTAs than bins, other tilings of the chi^2 work and the
     DFMA stepper: the chains are the same (identical for every schedule of the same kernel; the DFMA
@@ -118,7 +125,7 @@ def test_chain_does_not_depend_on_the_schedule(cs_lib, monkeypatch, env):
         same = np.all(ens.chain == want, axis=(1, 3))
         assert same.mean() > 0.999
         np.testing.assert_allclose(ens.chain[:, :, :3], want[:, :, :3], rtol=1e-13)
-    elif env.get("MDA_ENS_IMPL") == "quad":
+    elif env.get("MDA_ENS_IMPL") in ("quad", "qws"):
         # chi^2 from the triangular factor: log-probabilities agree to rounding, positions and decisions exactly
         np.testing.assert_array_equal(ens.chain, want)
         np.testing.assert_array_equal(ens.state()[0], want_state[0])
@@ -173,6 +180,13 @@ def test_full_size_steppers_agree_and_follow_the_restatement(cs_lib, oracle_lib,
     if np.array_equal(got[0], ref[0]):
         np.testing.assert_allclose(got[1], ref[1], rtol=1e-12)
         np.testing.assert_array_equal(got[2], ref[2])
+    # the warp-specialised build of the same stepper (the default at these shapes: the library's own schedule -- C4: 148 CTAs
+    # carry 200 bins' steps, some bins stepped by two CTAs in turn), and a coarser cut over 37 CTAs: identical to the plain one
+    for grid in ("", "37"):
+        qws = run("qws", "0", grid=grid)
+        for a, b in zip(qws, got):
+            np.testing.assert_array_equal(a, b, err_msg="qws grid=" + grid)
+        del qws
     del got
     got = run("dfma", "0")                 # another summation order: may differ in a measure-zero set of near ties
     assert np.all(got[0] == ref[0], axis=(1, 3)).mean() > 0.999
@@ -260,20 +274,23 @@ def test_run_to_host_streams_the_same_chain(cs_lib):
     store.close()
 
 
-def test_walking_schedule_of_the_default_stepper_with_thinning_and_split_runs(cs_lib, monkeypatch):
-    """Just above one bin per SM the default stepper lets one CTA per SM walk (chunk, bin) units: the chain, thinned and
-    advanced in two calls, equals the one a CTA per bin produces (MDA_ENS_QUAD_WALK=0)."""
+def test_balanced_schedule_of_the_default_stepper_with_thinning_and_split_runs(cs_lib, monkeypatch):
+    """Just above one bin per SM the default stepper cuts the bins' step ranges evenly over one CTA per SM (some bins are
+    stepped by two CTAs, one after the other): the chain, thinned and advanced in two calls, equals the one a CTA per bin
+    produces (the plain triangular-factor kernel, MDA_ENS_IMPL=quad with its own walk switched off)."""
     n_bins = 200
     consts, counts, lo, hi, p0, _ = _problem(n_bins, 4, 16, 32)
     store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    monkeypatch.setenv("MDA_ENS_IMPL", "quad")
     monkeypatch.setenv("MDA_ENS_QUAD_WALK", "0")
     ref = DeviceEnsemble(store, 32, seed=31)
     assert "200 CTAs" in ref.describe(90)
     ref.run_mcmc(p0, 90, thin=3)
     want, want_state = ref.chain.copy(), ref.state()
-    monkeypatch.setenv("MDA_ENS_QUAD_WALK", "1")          # (the library's own rule walks from 512 steps per launch on)
+    monkeypatch.delenv("MDA_ENS_IMPL")
     ens = DeviceEnsemble(store, 32, seed=31)
-    assert "200 CTAs" not in ens.describe(90)
+    text = ens.describe(90)
+    assert text.startswith("ensemble_qws_kernel") and "CTAs for 200 bins" in text and "200 CTAs for" not in text, text
     ens.set_state(p0)
     ens.reserve_chain(30)
     ens.advance(40, thin=3)

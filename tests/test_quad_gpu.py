@@ -86,7 +86,7 @@ def test_sampler_log_probabilities_equal_the_oracle_on_the_visited_positions(cs_
     lo, hi = synth.default_bounds(9)
     store = chisq.DeviceStore(consts, n_pts, (lo, hi), cs_lib=cs_lib)
     ens = DeviceEnsemble(store, 512, seed=77)
-    assert ens.describe(40).startswith("ensemble_quad_kernel")
+    assert ens.describe(40).startswith(("ensemble_qws_kernel", "ensemble_quad_kernel"))      # the triangular-factor steppers
     ens.run_mcmc(synth.make_walkers(a_true, 512, seed=1, oob_frac=0.0), 40, thin=4)
     chain, lnp = ens.chain, ens.lnprobability                                  # [B, W, kept, L], [B, W, kept]
     for k in range(chain.shape[2]):

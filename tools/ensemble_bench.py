@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--chain", type=int, default=1)
     ap.add_argument("--profile", type=int, default=0)
+    ap.add_argument("--spacer", type=int, default=100, help="untimed steps enqueued right before the timed launch (0: none)")
     args = ap.parse_args()
     lib = chisq.prepare_shared_object()
     peak = ct.c_double()
@@ -43,6 +44,8 @@ def main():
     ev0, ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
     if args.chain:
         ens.reserve_chain(args.steps)
+    if args.spacer:                                   # keeps the GPU busy while the host enqueues the timed launch
+        ens.advance(args.spacer, thin=10 ** 6, wait=False)
     lib.mdaEventRecord(ev0, store.handle)
     ens.advance(args.steps, wait=False)
     lib.mdaEventRecord(ev1, store.handle)
@@ -61,7 +64,21 @@ def main():
            "fp64_peak": peak.value, "acceptance": float(acc)}
     if args.profile:
         cyc = ens.profile().astype(float)
-        if os.environ.get("MDA_ENS_IMPL") == "dfma" or args.n_l < 4:
+        if ens.describe(args.steps).startswith("ensemble_qws"):
+            per_half = cyc[:, :8].mean(axis=0) / (2 * args.steps)
+            u = cyc[:, 16:112].reshape(args.bins, 12, 8)      # per CTA and unit: stamps start, (U), before wait, after wait, (A), loop end, steps, (D)
+            rows = []
+            for cta in (0, 1, 2, 147):
+                if cta < args.bins:
+                    t0 = u[cta, 0, 0]
+                    rows.append([[int(v - t0) for v in u[cta, k, [0, 1, 2, 3, 4, 5, 7]]] + [int(u[cta, k, 6])] for k in range(4) if u[cta, k, 0] > 0])
+            out["unit_timeline_cycles"] = rows
+            for name, o in (("draw0", 112), ("draw1", 120)):
+                v = cyc[:, o:o + 5].mean(axis=0)
+                out[name + "_cycles_per_half_step"] = dict(zip(["draws", "wait_read", "barrier", "post"], [round(x / max(v[4], 1), 1) for x in v[:4]]))
+            out["cycles_per_half_step"] = dict(zip(["walker:gather+propose", "walker:chi2", "walker:accept+store", "walker:fence", "walker:barrier",
+                                                     "-", "draw:draws", "draw:wait+barrier"], [round(x, 1) for x in per_half]))
+        elif os.environ.get("MDA_ENS_IMPL") == "dfma" or args.n_l < 4:
             per_half = cyc[:, :8].mean(axis=0) / (2 * args.steps)
             out["cycles_per_half_step"] = dict(zip(["propose+bar", "bar_after_A", "accept+bar", "chi_loop", "draw"], [round(x, 1) for x in per_half[:5]]))
         else:                                           # timeline of one half-step: [bin, warp, stamp], relative to the CTA's first stamp
