@@ -1,177 +1,157 @@
 """Store builder: from the reference's input files to the device-resident store
 (SURVEY.md 8f-3).
 
-Python-3 mirror of the reference's one-off preprocessing, same names and argument
-meaning, with the CONFIG keys it reads passed explicitly:
+What the store must hold is fixed by the reference (mda.py:173-176, 2069):
 
-    read_row_cs_data_file       mda.py:2331-2401   exp data rows "Ex, (theta, sigma, dsigma) x N",
-                                                   Start/Final Energy window, per-row Max Theta cut
-    read_dist                   mda.py:2072-2113   DWBA csv  A%d_Ex%4.2f_L%02d_T0_F%03d.csv
-    read_ivgdr_dists            mda.py:2211-2245   IVGDR csv A%d_Ex%4.2f_L01_T1_F100.csv
-    IVGDRFraction               mda.py:2249-2328   Lorentzian EWSR fraction
-    interpolate_and_scale_ivgdr mda.py:2180-2208
-    handle_ivgdr                mda.py:2116-2177   IVGDR subtracted from the data (not fitted)
-    interpolate_dist            mda.py:2040-2069   interp1d(kind="cubic") at exp angles / error
-    interp_all_dists            mda.py:1989-2037
-    build_store                 mda.py:160-183     the sequence initialize_mda runs, ending in a
-                                                   DeviceStore instead of per-bin tuples
+    dists[l][j] = cubic_l(theta_j) / dsigma_j          cubic_l: scipy interp1d(kind="cubic") through the
+                                                       DWBA table of multipole l at this bin's energy
+    data[j]     = (sigma_j - ivgdr_j) / dsigma_j       ivgdr_j: the isovector dipole's table, interpolated
+                                                       the same way and scaled by its Lorentzian
+                                                       sum-rule fraction (only if "Subtract IVGDR")
 
-The interpolation is scipy's (the reference's own third-party dependency): the store
-contents are defined as ``dists[l][j] = cubic_l(theta_j) / dsigma_j`` and
-``data[j] = (sigma_j - ivgdr_j) / dsigma_j`` (mda.py:176, 2069).
+and so are the on-disk formats it is computed from (README.md:11-17):
+
+    experimental data     one row per Ex bin: "Ex, theta, sigma, dsigma, theta, sigma, dsigma, ..."
+                          (mda.py:2331-2401: bins strictly inside (Start Energy, Final Energy), angles
+                          up to Max Theta are fitted, every angle is kept for plots)
+    DWBA tables           A<A>_Ex<E>_L<LL>_T0_F<FFF>.csv, rows "theta, sigma"  (mda.py:2072-2113)
+    IVGDR tables          A<A>_Ex<E>_L01_T1_F100.csv                            (mda.py:2211-2245)
+
+How it is computed here is this module's own: a row of the data file is parsed into one array
+and split by slicing, tables are parsed whole, the Lorentzian is one vectorised expression over
+the spectrum's energies, and bins are packed straight into the store's [B, 1+L, n_pad] block.
+The arithmetic per value -- one interpolation, one multiply, one subtract, one divide -- is the
+reference's, so the results are bit-identical to its preprocessing
+(tests/golden/golden_builder.npz holds the outputs of the reference's own functions).
 """
-import copy
-import math
 import os
+from dataclasses import dataclass
 
 import numpy as np
-from scipy import interpolate
+from scipy.interpolate import interp1d
+
+DWBA_NAME = "A{a:d}_Ex{e:4.2f}_L{l:02d}_T0_F{f:03d}.csv"
+IVGDR_NAME = "A{a:d}_Ex{e:4.2f}_L01_T1_F100.csv"
 
 
-def read_row_cs_data_file(path, start_energy, final_energy, max_theta):
-    """Returns (fit_output, plot_output): lists of [energy, array(N, 3)] with columns
-    (angle, cross-section, error); fit_output keeps only angles <= max_theta."""
-    fit_output, plot_output = [], []
-    with open(path, "r") as input_file:
-        for line in input_file:
-            data_list = line.split(",")
-            energy = float(data_list[0].strip())
-            if energy < final_energy and energy > start_energy:
-                distribution_data = [float(x.strip()) for x in data_list[1:]]
-                fit_distribution, plot_distribution = [], []
-                for i in range(0, len(distribution_data), 3):
-                    point = (distribution_data[i], distribution_data[i + 1], distribution_data[i + 2])
-                    if distribution_data[i] <= max_theta:
-                        fit_distribution.append(point)
-                    plot_distribution.append(point)
-                fit_output.append([energy, np.array(fit_distribution, dtype=np.float64)])
-                plot_output.append([energy, np.array(plot_distribution, dtype=np.float64)])
-    return fit_output, plot_output
+@dataclass
+class ExBin:
+    """One excitation-energy bin of the measured spectrum."""
+    energy: float
+    points: np.ndarray        # [n, 3] every (theta, sigma, dsigma) of the row, in file order
+    fitted: np.ndarray        # [n] bool: theta <= Max Theta
+
+    @property
+    def theta(self):
+        return self.points[self.fitted, 0]
+
+    @property
+    def sigma(self):
+        return self.points[self.fitted, 1]
+
+    @property
+    def dsigma(self):
+        return self.points[self.fitted, 2]
 
 
-def dist_file_name(directory, target_a, energy, l_value, ewsr_fraction):
-    fmt_str = "A{0:d}_Ex{1:4.2f}_L{2:02d}_T0_F{3:03d}.csv"
-    return os.path.join(directory, fmt_str.format(target_a, energy, l_value, int(100.0 * ewsr_fraction)))
+def _numbers(text):
+    """Comma-separated decimal numbers -> float64 (Python's correctly rounded parser)."""
+    return np.array(text.split(","), dtype=np.float64)
 
 
-def read_dist(directory, target_a, energy, l_value, ewsr_fractions):
-    """DWBA angular distribution (angle, cross-section) of multipole l_value at this energy."""
-    output = []
-    with open(dist_file_name(directory, target_a, energy, l_value, ewsr_fractions[l_value]), "r") as dist_file:
-        for line in dist_file:
-            vals = [float(x.strip()) for x in line.strip().split(",")]
-            output.append((vals[0], vals[1]))
-    return np.array(output, dtype=np.float64)
+def load_table(path):
+    """A two-column csv table (theta, sigma) as [n, 2]."""
+    with open(path, "r") as fh:
+        rows = [ln for ln in fh.read().splitlines() if ln.strip()]
+    return _numbers(",".join(rows)).reshape(len(rows), -1)[:, :2]
 
 
-def read_ivgdr_dists(directory, target_a, en_list):
-    fmt_str = "A{0:d}_Ex{1:4.2f}_L01_T1_F100.csv"
-    dists_list = []
-    for energy in en_list:
-        with open(os.path.join(directory, fmt_str.format(target_a, energy)), "r") as dist_file:
-            dist = [[float(elem) for elem in line.strip().split(",")] for line in dist_file]
-        dists_list.append(np.array(dist, dtype=np.float64))
-    return dists_list
+def load_spectrum(path, start_energy, final_energy, max_theta):
+    """The experimental data file -> [ExBin] for the rows with start < Ex < final."""
+    bins = []
+    with open(path, "r") as fh:
+        for row in fh:
+            if not row.strip():
+                continue
+            values = _numbers(row)
+            energy = float(values[0])
+            if not (start_energy < energy < final_energy):
+                continue
+            points = values[1:].reshape(-1, 3)
+            bins.append(ExBin(energy, points, points[:, 0] <= max_theta))
+    return bins
 
 
-class IVGDRFraction(object):
-    """Lorentzian normalised by its integral (mda.py:2249-2328)."""
-
-    def __init__(self, max_sigma, centroid, width, total_sigma):
-        self.sig_ratio = (max_sigma / total_sigma)
-        self.total = total_sigma
-        self.denom_const = (1.0 - 2.0 * math.pow(centroid / width, 2.0))
-        self.width_sq = math.pow(width, 2.0)
-        self.denom_inv = math.pow(centroid, 4.0) / self.width_sq
-
-    def get_ivgdr_fraction(self, excitation_energy):
-        en_sq = math.pow(excitation_energy, 2.0)
-        denom = self.denom_const + self.denom_inv / en_sq + en_sq / self.width_sq
-        return self.sig_ratio / denom
-
-    def get_ivgdr_cs(self, excitation_energy):
-        en_sq = math.pow(excitation_energy, 2.0)
-        denom = self.denom_const + self.denom_inv / en_sq + en_sq / self.width_sq
-        return (self.total * self.sig_ratio) / denom
+def dwba_table_path(directory, target_a, energy, l_value, ewsr_fraction):
+    return os.path.join(directory, DWBA_NAME.format(a=target_a, e=energy, l=l_value, f=int(100.0 * ewsr_fraction)))
 
 
-def interpolate_and_scale_ivgdr(dist, ewsr, angle_list):
-    interp = interpolate.interp1d(dist[:, 0], dist[:, 1], kind="cubic")
-    return ewsr * interp(angle_list)
+def ivgdr_table_path(directory, target_a, energy):
+    return os.path.join(directory, IVGDR_NAME.format(a=target_a, e=energy))
 
 
-def handle_ivgdr(data, subtract, directory=None, target_a=None, height=None, center=None, width=None, cs_integral=None):
-    """Returns (dists, ewsrs, sub_data) exactly as mda.py:2116-2177."""
-    if not subtract:
-        return None, None, copy.deepcopy(data)
-    frac = IVGDRFraction(height, center, width, cs_integral)
-    ewsrs = [frac.get_ivgdr_fraction(elem[0]) for elem in data]
-    dists = read_ivgdr_dists(directory, target_a, [elem[0] for elem in data])
-    angle_lists = [en_set[1][:, 0] for en_set in data]
-    ivgdr_values = [interpolate_and_scale_ivgdr(dist, ewsr, angle_list)
-                    for (dist, ewsr, angle_list) in zip(dists, ewsrs, angle_lists)]
-    sub_data = copy.deepcopy(data)
-    for i, sub_set in enumerate(sub_data):
-        sub_set[1][:, 1] = sub_set[1][:, 1] - ivgdr_values[i]
-    return dists, ewsrs, sub_data
+def lorentzian_cross_section(energies, height, centroid, width):
+    """The IVGDR photo-absorption Lorentzian  s(E) = h / (1 + (E^2 - c^2)^2 / (E^2 w^2))  at ``energies``, written as
+    the reference evaluates it (mda.py:2249-2328): h / ((1 - 2 c^2/w^2) + (c^4/w^2)/E^2 + E^2/w^2)."""
+    e_sq = np.square(np.asarray(energies, dtype=np.float64))
+    w_sq = width * width
+    ratio = centroid / width
+    return height / ((1.0 - 2.0 * (ratio * ratio)) + (centroid ** 4.0 / w_sq) / e_sq + e_sq / w_sq)
 
 
-def interpolate_dist(dist, angles, errors):
-    interp = interpolate.interp1d(dist[:, 0], dist[:, 1], kind="cubic")
-    return (interp(angles) / errors).astype(np.float64)
+def ivgdr_sum_rule_fraction(energies, height, centroid, width, cs_integral):
+    """Fraction of the IVGDR sum rule per MeV at each energy: Lorentzian / its integral (the peak-to-integral ratio is
+    formed first, as the reference does, so the values agree bit for bit)."""
+    return lorentzian_cross_section(energies, height / cs_integral, centroid, width)
 
 
-def interp_all_dists(dists, data):
-    output = []
-    for i, dis_set in enumerate(dists):
-        angle_list = data[i][1][:, 0]
-        error_list = data[i][1][:, 2]
-        output.append([interpolate_dist(dist, angle_list, error_list).astype(np.float64) for dist in dis_set])
-    return output
+def spline_at(table, theta):
+    """scipy's cubic interpolant (the reference's own third-party dependency) through a table, at ``theta``."""
+    return interp1d(table[:, 0], table[:, 1], kind="cubic")(theta)
 
 
-def pack_bins(fit_data, interp_dists):
-    """Per-bin arrays of initialize_mda (mda.py:173-176) -> ``consts [B, 1+L, n_pad]``
-    (row 0 data/error, rows 1..L distributions/error, zero padded) and ``n_pts [B]``."""
-    n_bins = len(fit_data)
-    n_l = len(interp_dists[0]) if n_bins else 0
-    n_max = max((len(d) for d in fit_data), default=0)
-    n_pad = n_max + (n_max & 1)
-    consts = np.zeros((n_bins, 1 + n_l, max(n_pad, 2)), dtype=np.float64)
-    n_pts = np.zeros(n_bins, dtype=np.int32)
-    for b in range(n_bins):
-        n = len(fit_data[b])
-        n_pts[b] = n
-        consts[b, 0, :n] = fit_data[b]
+def store_block(bins, dwba_tables, ivgdr=None):
+    """``consts [B, 1+L, n_pad]`` (row 0: data / error, rows 1..L: distributions / error, zero padded to an even
+    n_pad) and ``n_pts [B]`` for bins of ragged length.  ``dwba_tables[b][l]`` is the [n, 2] table of multipole l at
+    bin b's energy; ``ivgdr`` = (tables, fractions) to subtract the dipole from the data first."""
+    n_bins = len(bins)
+    n_l = len(dwba_tables[0]) if n_bins else 0
+    n_pts = np.array([int(b.fitted.sum()) for b in bins], dtype=np.int32)
+    n_max = int(n_pts.max()) if n_bins else 0
+    consts = np.zeros((n_bins, 1 + n_l, max(n_max + (n_max & 1), 2)), dtype=np.float64)
+    for b, ex in enumerate(bins):
+        n, theta, err = n_pts[b], ex.theta, ex.dsigma
+        sigma = ex.sigma
+        if ivgdr is not None:
+            sigma = sigma - ivgdr[1][b] * spline_at(ivgdr[0][b], theta)
+        consts[b, 0, :n] = sigma / err
         for l in range(n_l):
-            consts[b, 1 + l, :n] = interp_dists[b][l]
+            consts[b, 1 + l, :n] = spline_at(dwba_tables[b][l], theta) / err
     return consts, n_pts
 
 
 def build_inputs(config):
-    """The sequence initialize_mda runs up to the per-bin tuples (mda.py:160-183), from a
-    CONFIG dictionary with the reference's keys.  Returns a dict with ``energies``,
-    ``consts``, ``n_pts``, ``bounds`` and the intermediate products."""
-    exp_data, plot_data = read_row_cs_data_file(config["Input File Path"], config["Start Energy"],
-                                                config["Final Energy"], config["Max Theta"])
-    ivgdr_info = handle_ivgdr(exp_data, config.get("Subtract IVGDR", False), config["Distribution Directory"],
-                              config["Target A"], config.get("IVGDR Height"), config.get("IVGDR Center"),
-                              config.get("IVGDR Width"), config.get("IVGDR CS Integral"))
+    """Everything ``initialize_mda`` prepares per bin (mda.py:160-183), from a CONFIG dictionary with the reference's
+    keys.  Returns a dict: ``bins`` ([ExBin]), ``energies``, ``consts``, ``n_pts``, ``bounds`` (0, 1/EWSR_l:
+    mda.py:1124) and ``ivgdr_fractions`` (None unless "Subtract IVGDR")."""
+    bins = load_spectrum(config["Input File Path"], config["Start Energy"], config["Final Energy"], config["Max Theta"])
+    directory, target_a, ewsr = config["Distribution Directory"], config["Target A"], config["EWSR Fractions"]
     n_l = config["Maximum L"] + 1
-    dists = [[read_dist(config["Distribution Directory"], config["Target A"], elem[0], i, config["EWSR Fractions"])
-              for i in range(n_l)] for elem in exp_data]
-    interp_dists = interp_all_dists(dists, exp_data)
-    fit_data = [(exp_en[1][:, 1] / exp_en[1][:, 2]) for exp_en in ivgdr_info[2]]
-    consts, n_pts = pack_bins(fit_data, interp_dists)
-    bounds = [(0.0, 1.0 / x) for x in config["EWSR Fractions"][:n_l]]              # mda.py:1124
-    return {"energies": [elem[0] for elem in exp_data], "consts": consts, "n_pts": n_pts, "bounds": bounds,
-            "exp_data": exp_data, "plot_data": plot_data, "ivgdr_info": ivgdr_info, "dists": dists,
-            "interp_dists": interp_dists, "fit_data": fit_data}
+    energies = [b.energy for b in bins]
+    dwba = [[load_table(dwba_table_path(directory, target_a, e, l, ewsr[l])) for l in range(n_l)] for e in energies]
+    ivgdr = fractions = None
+    if config.get("Subtract IVGDR", False):
+        fractions = ivgdr_sum_rule_fraction(energies, config["IVGDR Height"], config["IVGDR Center"], config["IVGDR Width"],
+                                            config["IVGDR CS Integral"])
+        ivgdr = ([load_table(ivgdr_table_path(directory, target_a, e)) for e in energies], fractions)
+    consts, n_pts = store_block(bins, dwba, ivgdr)
+    return {"bins": bins, "energies": energies, "consts": consts, "n_pts": n_pts, "bounds": [(0.0, 1.0 / x) for x in ewsr[:n_l]],
+            "ivgdr_fractions": fractions}
 
 
 def build_store(config, cs_lib=None, bins=None):
-    """Everything above, then the device-resident store.  ``bins`` selects a subset of the
-    spectrum (e.g. ``shard.bins_for_rank``) so every rank uploads only its own bins."""
+    """``build_inputs``, then the device-resident store.  ``bins`` selects a subset of the spectrum (e.g.
+    ``shard.bins_for_rank``) so every rank uploads only its own bins."""
     from . import chisq
     inputs = build_inputs(config)
     sel = np.arange(len(inputs["energies"])) if bins is None else np.asarray(bins, dtype=np.int64)

@@ -1154,6 +1154,13 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.seed_lo = (unsigned int)(e->seed & 0xFFFFFFFFull);
     args.seed_hi = (unsigned int)(e->seed >> 32);
     args.a = e->a;
+    {
+        uint32_t rk[20];
+        philox_round_keys(args.seed_lo, args.seed_hi, rk);
+        for (int r = 0; r < 20; ++r) args.round_keys[r] = rk[r];
+        int exponent = 0;
+        args.a_inv = (std::frexp(e->a, &exponent) == 0.5) ? 1.0 / e->a : 0.0;      // a power of two: the division is a multiplication
+    }
     for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
     args.consts_mma = s->d_consts_mma;
     args.n_tiles = s->n_tiles;

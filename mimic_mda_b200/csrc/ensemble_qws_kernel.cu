@@ -113,6 +113,19 @@ __device__ __forceinline__ unsigned long long q_globaltimer_ns() {
     return t;
 }
 
+// Shared-memory accesses by 32-bit address.  volatile + "memory": they keep their place among the barriers.
+__device__ __forceinline__ double q_lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 q_lds_u2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void q_sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
 __device__ __forceinline__ double q_uniform43(uint32_t w, uint32_t x, uint32_t y) {
     return ((double)w * 2048.0 + (double)(((x & 31u) << 6) | (y & 63u))) * (1.0 / 8796093022208.0);
 }
@@ -150,10 +163,97 @@ struct QwsCtx {
     int *s_abort;
     int W, H;
     long long total, ribbon_end;
-    uint32_t seed0, seed1;
     bool keeping, split;
     QwsSmem lay{2, 1, false};
 };
+
+// The barrier that only the walker warps and the thread that copies take part in (state of a piece complete / whole-state
+// chain store read).  In the build with a copy warpgroup the draw warps do not track pieces of work at all: they count
+// half-steps (qws_draw_loop), so these hand-offs are a named barrier of the other 384 threads.
+template <bool COPYWG>
+__device__ __forceinline__ void qws_piece_barrier() {
+    if constexpr (COPYWG) asm volatile("bar.sync 2, 384;" ::: "memory");
+    else __syncthreads();
+}
+
+__device__ __noinline__ double qws_divide(double x, double y) { return x / y; }
+
+// One walker's draw of half-step tt into slot `slot` (= ring position * H + walker): counter (walker, bin, half-step, 0),
+// round keys from the parameter block.  numpy arithmetic is one rounding per operation: no FMA contraction.
+template <int L>
+__device__ __forceinline__ void qws_draw(const EnsembleArgs &args, double *sZ, double *sUa, uint2 *sPF, uint32_t walker, uint32_t bin_id,
+                                         uint32_t tt, uint32_t H, int slot, bool valid) {
+    const Philox4 r = philox4x32_10_keys(Philox4{walker, bin_id, tt, 0u}, args.round_keys);
+    const double zr = __dadd_rn(__dmul_rn(args.a - 1.0, uniform53(r.x, r.y)), 1.0);
+    const double z2 = __dmul_rn(zr, zr);
+    double z;                                                                    // ((a-1) u + 1)^2 / a
+    if (args.a_inv != 0.0) z = z2 * args.a_inv; else z = qws_divide(z2, args.a);
+    const double ua = q_uniform43(r.w, r.x, r.y);
+    const float fast = (float)(L - 1) * __logf((float)z) - __logf((float)ua);   // decides all but near-ties
+    if (valid) {
+        sZ[slot] = z;
+        sUa[slot] = ua;
+        sPF[slot] = make_uint2(__umulhi(r.z, H), __float_as_uint(fast));
+    }
+}
+
+// The draw warps of the build with a copy warpgroup: NDRAW threads, thread d draws for walkers d, d + NDRAW, ... of the half,
+// two half-steps ahead of the walkers, over the CTA's whole sequence of half-steps (across its pieces of work).  Nothing
+// but the cursor, the draw and one barrier per half-step: these warps are the pacemaker of a CTA that has its SM to itself
+// (with the piece bookkeeping of qws_service in the same 56 registers a half-step's 256 draws took 1750 cycles).
+template <int L, int NDRAW, bool PROF>
+__device__ __forceinline__ void qws_draw_loop(const EnsembleArgs &args, unsigned char *smem_raw, const QwsSmem &lay, const int H,
+                                              const long long seg_begin, const long long seg_end, const int d) {
+    double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
+    double *sUa = reinterpret_cast<double *>(smem_raw + lay.ua);
+    uint2 *sPF = reinterpret_cast<uint2 *>(smem_raw + lay.pf);
+    long long cursor = seg_begin;
+    QwsUnit u;
+    bool valid = qws_next_unit(args, cursor, seg_end, u);
+    uint32_t bin_id = 0, t = 0, t_end = 0;
+    auto open = [&]() {
+        bin_id = (uint32_t)args.bin_ids[u.bin];
+        t = 2u * (uint32_t)(args.step0 + u.s0);
+        t_end = 2u * (uint32_t)(args.step0 + u.s1);
+    };
+    open();
+    int ring_base = 0;                                   // ring position * H
+    int made = 0;
+    auto draw_one = [&]() {
+        if (!valid) return;
+        if ((args.groups & 2) && ++made > 3) return;     // (debug bit 1: the first three draws are reused for ever)
+        const uint32_t w_base = (t & 1u) ? (uint32_t)H : 0u;
+        if (NDRAW >= kWalkerThreads) {
+            qws_draw<L>(args, sZ, sUa, sPF, w_base + (uint32_t)min(d, H - 1), bin_id, t, (uint32_t)H, ring_base + d, d < H);
+        } else {                                         // two independent Philox chains interleave
+            qws_draw<L>(args, sZ, sUa, sPF, w_base + (uint32_t)min(d, H - 1), bin_id, t, (uint32_t)H, ring_base + d, d < H);
+            if (H > NDRAW)
+                qws_draw<L>(args, sZ, sUa, sPF, w_base + (uint32_t)min(d + NDRAW, H - 1), bin_id, t, (uint32_t)H, ring_base + d + NDRAW, d + NDRAW < H);
+        }
+        ring_base = ring_base == 2 * H ? 0 : ring_base + H;
+        if (++t == t_end) {
+            valid = qws_next_unit(args, cursor, seg_end, u);
+            if (valid) open();
+        }
+    };
+    const int n_half = (int)(2 * (seg_end - seg_begin));
+    long long p_d[2] = {0, 0};
+    draw_one();
+    draw_one();
+    __syncthreads();                                     // (A) the first draws are in place
+    for (int h = 0; h < n_half; ++h) {
+        long long c0 = 0;
+        if constexpr (PROF) c0 = clock64();
+        draw_one();
+        if constexpr (PROF) { const long long c1 = clock64(); p_d[0] += c1 - c0; c0 = c1; }
+        __syncthreads();                                 // (B) the half is complete
+        if constexpr (PROF) p_d[1] += clock64() - c0;
+    }
+    if constexpr (PROF) if (d == 0 && args.prof) {
+        long long *o = args.prof + (size_t)blockIdx.x * 128 + 112;
+        o[0] = p_d[0]; o[1] = 0; o[2] = p_d[1]; o[3] = 0; o[4] = n_half;
+    }
+}
 
 // What the non-walker threads do.  DRAWS: this thread (d of 128) makes the draws, two half-steps ahead of the walkers.
 // COPIES: thread d == 0 owns every bulk copy and the progress words.  One warpgroup does both (two CTAs per SM), or -- in the
@@ -167,7 +267,6 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
     int &s_abort = *cx.s_abort;
     const int W = cx.W, H = cx.H;
     const long long total = cx.total, ribbon_end = cx.ribbon_end;
-    const uint32_t seed0 = cx.seed0, seed1 = cx.seed1;
     const bool keeping = cx.keeping, split = cx.split;
     const QwsSmem &lay = cx.lay;
     double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
@@ -178,8 +277,6 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
     auto fac_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes + lay.fac); };
     const bool copier = COPIES && d == 0;
     QwsUnit next;
-    const double a_scale = args.a;
-    const float dim_m1f = (float)(L - 1);
     const uint32_t state_bytes = (uint32_t)W * (L + 1) * 8u + (uint32_t)quad_stride(L) * 8u;
     auto load_state = [&](int bin, int b) {              // (thread d == 0) positions, log-probabilities and factor of `bin` into buffer b
         q_mbar_expect_tx(&s_bar[b], state_bytes);
@@ -191,25 +288,10 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
         const int buf = ring * H;
         const uint32_t w_base = (tt & 1u) ? (uint32_t)H : 0u;
         // a thread's two walkers (d and d + 128) in one straight-line block: two independent Philox chains interleave
-        const int i0 = d, i1 = min(d + kDrawThreads, H - 1);
-        const Philox4 r0 = philox4x32_10(Philox4{w_base + (uint32_t)min(i0, H - 1), bin_id, tt, 0u}, seed0, seed1);
-        Philox4 r1 = r0;
-    if (H > kDrawThreads) r1 = philox4x32_10(Philox4{w_base + (uint32_t)i1, bin_id, tt, 0u}, seed0, seed1);
-        auto finish = [&](const Philox4 &r, int i, bool valid) {
-            // numpy arithmetic is one rounding per operation: no FMA contraction
-            const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
-            const double z2 = __dmul_rn(zr, zr);
-            const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;   // ((a-1) u + 1)^2 / a
-            const double ua = q_uniform43(r.w, r.x, r.y);
-            const float fast = dim_m1f * __logf((float)z) - __logf((float)ua);   // decides all but near-ties
-            if (valid) {
-                sZ[buf + i] = z;
-                sUa[buf + i] = ua;
-                sPF[buf + i] = make_uint2(__umulhi(r.z, (uint32_t)H), __float_as_uint(fast));
-            }
-        };
-        finish(r0, i0, i0 < H);
-        if (H > kDrawThreads) finish(r1, i1, d + kDrawThreads < H);
+        qws_draw<L>(args, sZ, sUa, sPF, w_base + (uint32_t)min(d, H - 1), bin_id, tt, (uint32_t)H, buf + d, d < H);
+        if (H > kDrawThreads)
+            qws_draw<L>(args, sZ, sUa, sPF, w_base + (uint32_t)min(d + kDrawThreads, H - 1), bin_id, tt, (uint32_t)H, buf + d + kDrawThreads,
+                        d + kDrawThreads < H);
     };
     // the draw cursor runs over the CTA's whole sequence of half-steps, across its pieces of work
     long long d_ribbon = (long long)blockIdx.x * total / gridDim.x;
@@ -276,6 +358,10 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
                     pending_release = -1;
                 }
                 if (kept_step) {
+                    if (args.groups >> 2) {              // (debug bits 2..: the store is issued this many hundreds of cycles after the barrier)
+                        const long long until = clock64() + 100ll * (args.groups >> 2);
+                        while (clock64() < until) __nanosleep(20);
+                    }
                     double *dst = args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L;
                     double *ldst = args.lnp_chain + ((size_t)slot * args.bins + (size_t)bin) * W;
                     if (split) {                         // the half just updated is final for this step
@@ -305,7 +391,7 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
             }
             if (kept_step && !split && half) {           // whole-state store: nobody may write until it has been read
                 if (copier) q_bulk_wait_read_all();
-                __syncthreads();                         // (C)
+                qws_piece_barrier<!DRAWS>();             // (C)
             }
             if (half) {
                 if (--until_keep == 0) { until_keep = args.thin; if (keeping) ++slot; }
@@ -322,7 +408,7 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
             asm volatile("fence.proxy.async;" ::: "memory");
             if (!s_abort) { q_bulk_wait_read_all(); load_state(next.bin, buf ^ 1); }
         }
-        __syncthreads();                                 // (D) every walker thread has fenced its last writes; abort flag settled
+        qws_piece_barrier<!DRAWS>();                     // (D) every walker thread has fenced its last writes; abort flag settled
         if (copier) {
             q_bulk_s2g(args.pos + (size_t)bin * W * L, sPos, (uint32_t)W * L * 8u);
             q_bulk_s2g(args.lnp + (size_t)bin * W, sLnp, (uint32_t)W * 8u);
@@ -371,7 +457,6 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_abort = 0;
     }
-    const uint32_t seed0 = args.seed_lo, seed1 = args.seed_hi;
     const bool keeping = args.chain != nullptr;
     // a half can be stored on its own if its rows and log-probabilities are 16-byte multiples (bulk-copy granularity)
     const bool split = ((H * L) & 1) == 0 && (H & 1) == 0;
@@ -388,11 +473,11 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         // =========================================================== draw warps and the copy thread
         QwsCtx cx;
         cx.smem_raw = smem_raw; cx.s_bar = s_bar; cx.s_abort = &s_abort; cx.W = W; cx.H = H; cx.total = total; cx.ribbon_end = ribbon_end;
-        cx.seed0 = seed0; cx.seed1 = seed1; cx.keeping = keeping; cx.split = split; cx.lay = lay;
+        cx.keeping = keeping; cx.split = split; cx.lay = lay;
         if constexpr (COPYWG) {
             if (tid < kWalkerThreads + kDrawThreads) {
                 asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-                qws_service<L, true, false, PROF>(args, cx, unit, ribbon, tid - kWalkerThreads);
+                qws_draw_loop<L, kDrawThreads, PROF>(args, smem_raw, lay, H, (long long)blockIdx.x * total / gridDim.x, ribbon_end, tid - kWalkerThreads);
             } else {
                 asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
                 qws_service<L, false, true, PROF>(args, cx, unit, ribbon, tid - kWalkerThreads - kDrawThreads);
@@ -405,7 +490,6 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
 
     // =============================================================== walker warps
     if constexpr (TREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    constexpr bool XREG = TREG;                              // with 224 registers the thread's own two rows live in registers too
     const bool owner = tid < H;
     const int me = min(tid, H - 1);
     const double dim_m1 = (double)(L - 1);
@@ -455,24 +539,36 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = 2u * (uint32_t)(args.step0 + unit.s1);
         int until_keep = args.thin - (int)((uint64_t)step_first % (uint64_t)args.thin);
         long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
-        // my two walkers: row and log-probability (registers in the XREG build, else re-read from shared memory)
-        double x0[XREG ? L : 1], x1[XREG ? L : 1], lnp0 = 0.0, lnp1 = 0.0;
-        if constexpr (XREG) {
-#pragma unroll
-            for (int l = 0; l < L; ++l) { x0[l] = sPos[(size_t)me * L + l]; x1[l] = sPos[(size_t)(H + me) * L + l]; }
-            lnp0 = sLnp[me];
-            lnp1 = sLnp[H + me];
-        }
         unsigned int acc0 = 0u, acc1 = 0u;                   // proposals accepted in this piece, per walker of either half
+        long long p_w[PROF ? 5 : 1] = {};
         if (ustamp) ustamp[2] = clock64();
 
-        auto half_step = [&](const int half, uint32_t t, double (&x)[XREG ? L : 1], double &lnp_reg, unsigned int &acc) {   // half: a literal at both call sites
+        // 32-bit shared-memory addresses, formed once per piece: the partner row's is then one multiply-add from the draw
+        const uint32_t pos_a = q_smem_addr(sPos), lnp_a = q_smem_addr(sLnp);
+        const uint32_t draw_a = q_smem_addr(sZ) + (uint32_t)me * 8u;       // my slot of ring position 0; Ua and PF lie 3 H and 6 H doubles on
+        const uint32_t ring_bytes = (uint32_t)H * 8u, ring_span = 3u * ring_bytes;
+        uint32_t ring_off = (uint32_t)ring * ring_bytes;                   // ring position of this half-step's draw
+        // The row and log-probability of the walker I update next: fetched at the end of the half-step before (its half is
+        // not written meanwhile), so that after the barrier only the partner row is still to come.
+        double x[L], oldlnp = 0.0;
+        if (owner) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) x[l] = q_lds_f64(pos_a + (uint32_t)me * (uint32_t)(L * 8) + 8u * l);
+            oldlnp = q_lds_f64(lnp_a + (uint32_t)me * 8u);
+        }
+        auto half_step = [&](const int half, uint32_t t, unsigned int &acc) {   // half: a literal at both call sites
             const int s_base = half ? H : 0, c_base = half ? 0 : H;           // updated half; partners come from the other one
             const bool kept_step = keeping && until_keep == 1 && slot < args.keep_cap;
+            long long w0 = 0;
+            if constexpr (PROF) w0 = clock64();
+            const uint32_t next_off = ring_off + ring_bytes == ring_span ? 0u : ring_off + ring_bytes;
             if (owner) {
-                const double *crow = sPos + (size_t)(c_base + (int)pf.x) * L;
-                double *xrow = sPos + (size_t)(s_base + me) * L;
-                const double oldlnp = XREG ? lnp_reg : sLnp[s_base + me];
+                const uint32_t crow = pos_a + (uint32_t)(c_base + ((args.groups & 1) ? me : (int)pf.x)) * (uint32_t)(L * 8);   // (debug bit 0: no gather conflicts)
+                const uint32_t xrow = pos_a + (uint32_t)(s_base + me) * (uint32_t)(L * 8);
+                const uint32_t nrow = pos_a + (uint32_t)(c_base + me) * (uint32_t)(L * 8);      // my walker of the other half: the next one
+                double c[L];
+#pragma unroll
+                for (int l = 0; l < L; ++l) c[l] = q_lds_f64(crow + 8u * l);
                 // accept for sure if lnp(q) - lnp(x) + fast > 1e-4, reject for sure if < -1e-4 (fast: the float estimate of
                 // (L-1) ln z - ln u', error < 2e-5); with lnp = -chi^2 / 2 both are thresholds on chi^2, ready before it is
                 const double fast_d = (double)__uint_as_float(pf.y);
@@ -481,54 +577,61 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
                 bool outside = false;
 #pragma unroll
                 for (int l = 0; l < L; ++l) {
-                    const double c = crow[l];
-                    const double xl = XREG ? x[XREG ? l : 0] : xrow[l];
-                    q[l] = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, xl)));       // numpy rounding: no FMA contraction
+                    q[l] = __dsub_rn(c[l], __dmul_rn(z, __dsub_rn(c[l], x[l])));     // numpy rounding: no FMA contraction
                     outside = outside | (q[l] < args.lo[l]) | (q[l] > args.hi[l]);   // mda.py:1575; a NaN compares false, as there
                 }
+                if constexpr (PROF) { const long long w1 = clock64(); p_w[0] += w1 - w0; w0 = w1; }
                 double chi;
                 if constexpr (TREG) chi = outside ? CUDART_INF : chi_from_factor_regs<L>(tri_regs, q);
                 else chi = outside ? CUDART_INF : chi_from_factor<L>(sTri, q);
                 saw_nan = saw_nan || (chi != chi);
+                if constexpr (PROF) { const long long w1 = clock64() + (long long)(chi == -1.0); p_w[1] += w1 - w0; w0 = w1; }
                 bool accept = chi < chi_accept;
                 if (!accept && !(chi > chi_reject)) {        // near a tie (or NaN): emcee's test in full precision
                     const double newlnp = chi * -0.5;
                     const double zlog = __dmul_rn(dim_m1, log(z));
-                    accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(sUa[ring * H + me]);
+                    accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(q_lds_f64(draw_a + ring_span + ring_off));
                 }
-                if (accept) {
-                    const double newlnp = chi * -0.5;                          // C/ChiSquare.c:212; outside the box: -inf (mda.py:1576), never accepted
+                if (accept) {                                // C/ChiSquare.c:212; outside the box: -inf (mda.py:1576), never accepted
 #pragma unroll
-                    for (int l = 0; l < L; ++l) { xrow[l] = q[l]; if constexpr (XREG) x[XREG ? l : 0] = q[l]; }
-                    sLnp[s_base + me] = newlnp;
-                    if constexpr (XREG) lnp_reg = newlnp;
+                    for (int l = 0; l < L; ++l) q_sts_f64(xrow + 8u * l, q[l]);
+                    q_sts_f64(lnp_a + (uint32_t)(s_base + me) * 8u, chi * -0.5);
                     acc += 1u;
                 }
+                // the next half-step's operands: its draw (in place since the last barrier; of this piece or of the next one) and
+                // my walker of the other half -- not the next piece's, which is fetched when that piece starts
+                if (t + 1 < t_end || has_next) { z = q_lds_f64(draw_a + next_off); pf = q_lds_u2(draw_a + 2u * ring_span + next_off); }
+                if (t + 1 < t_end) {
+#pragma unroll
+                    for (int l = 0; l < L; ++l) x[l] = q_lds_f64(nrow + 8u * l);
+                    oldlnp = q_lds_f64(lnp_a + (uint32_t)(c_base + me) * 8u);
+                }
             }
-            // the draws of the next half-step (of this piece or of the next one) are in place since the last barrier
-            const int next_ring = ring == 2 ? 0 : ring + 1;
-            if (owner && (t + 1 < t_end || has_next)) { z = sZ[next_ring * H + me]; pf = sPF[next_ring * H + me]; }
-            ring = next_ring;
+            ring_off = next_off;
+            ring = ring == 2 ? 0 : ring + 1;
             if (kept_step) q_fence_proxy_async();            // my rows before the bulk store reads them
+            if constexpr (PROF) { const long long w1 = clock64(); p_w[2] += w1 - w0; w0 = w1; }
             __syncthreads();                                 // (B)
-            if (kept_step && !split && half) __syncthreads();   // (C)
+            if constexpr (PROF) { const long long w1 = clock64(); p_w[3] += w1 - w0; p_w[4] += 1; }
+            if (kept_step && !split && half) qws_piece_barrier<COPYWG>();   // (C)
             if (half) {
                 if (--until_keep == 0) { until_keep = args.thin; if (keeping) ++slot; }
             }
         };
         for (uint32_t t = t_begin; t < t_end; t += 2) {      // t_begin is even: a step is the update of half 0, then of half 1
-            half_step(0, t, x0, lnp0, acc0);
-            half_step(1, t + 1, x1, lnp1, acc1);
+            half_step(0, t, acc0);
+            half_step(1, t + 1, acc1);
         }
         if (ustamp) ustamp[3] = clock64();
         q_fence_proxy_async();
-        __syncthreads();                                     // (D)
+        qws_piece_barrier<COPYWG>();                         // (D)
         if (owner) {                                         // the bin is mine alone: plain adds; issued after the barrier, so that no fence
             unsigned int *gAcc = args.nacc + (size_t)bin * W;   // of this piece waits for them (the next barrier orders them before a release)
             if (acc0) atomicAdd(gAcc + tid, acc0);
             if (acc1) atomicAdd(gAcc + H + tid, acc1);
         }
         if (ustamp) ustamp[4] = clock64();
+        if constexpr (PROF) if ((tid == 0 || tid == 255) && args.prof) for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)args.prof + (size_t)blockIdx.x * 128 + (tid ? 8 : 0) + k, (unsigned long long)p_w[k]);
         if (!has_next) break;
         unit = next;
         buf ^= 1;
@@ -608,12 +711,14 @@ cudaError_t launch_ensemble_qws(const EnsembleArgs &args, const EnsembleShape &s
     EnsKernel k = pick_qws_kernel(args.n_l, shape.treg);
     if (args.prof && args.n_l == 9) k = shape.treg ? ensemble_qws_kernel<9, true, true> : ensemble_qws_kernel<9, false, true>;
     if (!k || !shape.fits || !shape.qws || !args.quad || grid < 1 || grid > args.bins || (grid < args.bins && !args.progress)) return cudaErrorInvalidValue;
+    EnsembleArgs copy = args;
+    copy.groups = 0;
+    if (const char *dbg = getenv("MDA_QWS_DEBUG")) copy.groups = atoi(dbg);   // timing experiments only (see the kernel): wrong chains
     if (grid == args.bins) {                                 // a bin per CTA: no CTA waits for another
-        k<<<grid, shape.threads, shape.smem_bytes, stream>>>(args);
+        k<<<grid, shape.threads, shape.smem_bytes, stream>>>(copy);
         return cudaGetLastError();
     }
     // bins cut across CTAs: the piece that waits needs the other one resident -- a cooperative launch fails instead of hanging
-    EnsembleArgs copy = args;
     void *params[] = {&copy};
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k), dim3((unsigned)grid), dim3((unsigned)shape.threads), params, shape.smem_bytes, stream);
 }

@@ -90,6 +90,8 @@ struct EnsembleArgs {
     long long keep0, keep_cap; // next free slot / capacity of the chain
     unsigned int seed_lo, seed_hi;
     double a;                  // stretch scale (emcee default 2)
+    unsigned int round_keys[20];       // Philox round keys of the seed (philox_round_keys), for the kernels that take them from here
+    double a_inv;              // 1 / a when a is a power of two (then z^2 / a == z^2 * a_inv exactly), else 0
     double lo[kMaxRegL];
     double hi[kMaxRegL];
 };

@@ -54,18 +54,33 @@ __device__ __forceinline__ double chi_from_factor(const double *__restrict__ tri
 }
 
 // The same with T held in registers (indices are compile-time constants after unrolling): for the build that has an SM's
-// register file to itself.  t[] in the padded layout of load_factor.
-template <int L>
+// register file to itself.  t[] in the padded layout of load_factor.  Rows are summed G at a time, column by column, so
+// that G independent multiply-add chains are in flight (a lone walker warp pair per scheduler cannot hide the latency of
+// one 55-long dependent chain); every row's sum still runs over ascending k and chi^2 over ascending i, so the result is
+// bit for bit the one of chi_from_factor.
+template <int L, int G = 5>
 __device__ __forceinline__ double chi_from_factor_regs(const double (&t)[quad_padded_doubles(L)], const double (&a)[L]) {
     double chi = 0.0;
 #pragma unroll
-    for (int i = 0; i <= L; ++i) {
-        const int len = L + 1 - i, o = quad_padded_offset(L, i);
-        double u = 0.0;
+    for (int i0 = 0; i0 <= L; i0 += G) {
+        double u[G];
 #pragma unroll
-        for (int k = 0; k < len - 1; ++k) u = fma(t[o + k], a[i + k], u);
-        u -= t[o + len - 1];
-        chi = fma(u, u, chi);
+        for (int g = 0; g < G; ++g) u[g] = 0.0;
+#pragma unroll
+        for (int k = i0; k < L; ++k)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int i = i0 + g;
+                if (i <= k) u[g] = fma(t[quad_padded_offset(L, i < L ? i : L) + (k - i)], a[k], u[g]);
+            }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int i = i0 + g;
+            if (i <= L) {
+                u[g] -= t[quad_padded_offset(L, i) + (L - i)];
+                chi = fma(u[g], u[g], chi);
+            }
+        }
     }
     return chi;
 }

@@ -32,27 +32,30 @@ def test_builder_reproduces_reference_preprocessing(case, tag):
     got = builder.build_inputs(config)
     np.testing.assert_array_equal(got["energies"], z[tag + "/energies"])           # Start/Final Energy window
     np.testing.assert_array_equal(got["n_pts"], z[tag + "/n_pts"])                 # per-row Max Theta cut
-    np.testing.assert_array_equal([len(p[1]) for p in got["plot_data"]], z[tag + "/n_plot"])
+    np.testing.assert_array_equal([len(b.points) for b in got["bins"]], z[tag + "/n_plot"])    # every angle is kept for plots
     assert len(set(got["n_pts"].tolist())) > 1                                      # ragged, as in real data
     for b in range(len(got["energies"])):
         n = int(got["n_pts"][b])
-        np.testing.assert_array_equal(got["fit_data"][b], z["%s/fit_data_%d" % (tag, b)])
-        np.testing.assert_array_equal(np.array(got["interp_dists"][b]), z["%s/interp_dists_%d" % (tag, b)])
-        # and the packed store layout holds exactly those values, zero padded
+        # the packed store block holds exactly the reference's values (bit for bit), zero padded
         np.testing.assert_array_equal(got["consts"][b, 0, :n], z["%s/fit_data_%d" % (tag, b)])
         np.testing.assert_array_equal(got["consts"][b, 1:, :n], z["%s/interp_dists_%d" % (tag, b)])
         assert np.all(got["consts"][b, :, n:] == 0.0)
     if tag == "ivgdr":
-        np.testing.assert_array_equal(got["ivgdr_info"][1], z["ivgdr/ewsrs"])
-        assert not np.array_equal(got["fit_data"][0], z["noivgdr/fit_data_0"])     # the subtraction happened
+        np.testing.assert_array_equal(got["ivgdr_fractions"], z["ivgdr/ewsrs"])
+        assert not np.array_equal(got["consts"][0, 0, :int(got["n_pts"][0])], z["noivgdr/fit_data_0"])     # the subtraction happened
+    else:
+        assert got["ivgdr_fractions"] is None
     assert got["bounds"] == [(0.0, 1.0), (0.0, 1.0), (0.0, 1.25), (0.0, 1.0)]       # (0, 1/EWSR), mda.py:1124
 
 
 def test_ivgdr_fraction_formula():
-    frac = builder.IVGDRFraction(280.0, 15.3, 4.9, 2100.0)
-    e = 15.3                                           # at the centroid the Lorentzian is at its height
-    assert abs(frac.get_ivgdr_cs(e) - 280.0) < 1e-9
-    assert abs(frac.get_ivgdr_fraction(e) - 280.0 / 2100.0) < 1e-12
+    e = np.array([15.3, 10.0, 20.0])                   # at the centroid the Lorentzian is at its height
+    cs = builder.lorentzian_cross_section(e, 280.0, 15.3, 4.9)
+    assert abs(cs[0] - 280.0) < 1e-9
+    want = 280.0 / (1.0 + (e ** 2 - 15.3 ** 2) ** 2 / (e ** 2 * 4.9 ** 2))      # the textbook form
+    np.testing.assert_allclose(cs, want, rtol=1e-13)
+    frac = builder.ivgdr_sum_rule_fraction(e, 280.0, 15.3, 4.9, 2100.0)
+    assert abs(frac[0] - 280.0 / 2100.0) < 1e-12
 
 
 @pytest.mark.gpu

@@ -65,6 +65,10 @@ def main():
     if args.profile:
         cyc = ens.profile().astype(float)
         if ens.describe(args.steps).startswith("ensemble_qws"):
+            ctas = min(args.bins, 148)
+            for name, o in (("walker_t0", 0), ("walker_t255", 8)):
+                v = cyc[:ctas, o:o + 5].sum(axis=0)
+                out[name + "_cycles_per_half_step"] = dict(zip(["gather+propose", "chi2", "accept+store+prefetch", "barrier"], [round(x / max(v[4], 1), 1) for x in v[:4]]))
             per_half = cyc[:, :8].mean(axis=0) / (2 * args.steps)
             u = cyc[:, 16:112].reshape(args.bins, 12, 8)      # per CTA and unit: stamps start, (U), before wait, after wait, (A), loop end, steps, (D)
             rows = []
@@ -76,8 +80,6 @@ def main():
             for name, o in (("draw0", 112), ("draw1", 120)):
                 v = cyc[:, o:o + 5].mean(axis=0)
                 out[name + "_cycles_per_half_step"] = dict(zip(["draws", "wait_read", "barrier", "post"], [round(x / max(v[4], 1), 1) for x in v[:4]]))
-            out["cycles_per_half_step"] = dict(zip(["walker:gather+propose", "walker:chi2", "walker:accept+store", "walker:fence", "walker:barrier",
-                                                     "-", "draw:draws", "draw:wait+barrier"], [round(x, 1) for x in per_half]))
         elif os.environ.get("MDA_ENS_IMPL") == "dfma" or args.n_l < 4:
             per_half = cyc[:, :8].mean(axis=0) / (2 * args.steps)
             out["cycles_per_half_step"] = dict(zip(["propose+bar", "bar_after_A", "accept+bar", "chi_loop", "draw"], [round(x, 1) for x in per_half[:5]]))
