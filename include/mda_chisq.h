@@ -131,6 +131,10 @@ MDA_API int   mdaStoreSetBinFromStruct(void *store, int bin, void *mdaStruct);
 MDA_API int   mdaStoreSetBounds(void *store, const double *lo, const double *hi);
 /* Push the host mirror to HBM (done lazily by the first evaluation too). */
 MDA_API int   mdaStoreUpload(void *store);
+/* Conditioning of the bins for the triangular-factor likelihood of section 6: kappa[bin] = |data| / sqrt(min chi^2)
+ * (numBins values, may be NULL), the limit it is compared with (4 eps kappa <= 1e-13) and whether every bin passes; a
+ * store with a bin that does not is sampled by the reference-order stepper instead.  Host arithmetic only. */
+MDA_API int   mdaStoreConditioning(void *store, double *kappa, double *kappaMax, int *quadSafe);
 MDA_API int   mdaStoreNumBins(void *store);
 MDA_API int   mdaStoreNumL(void *store);
 MDA_API int   mdaStoreMaxPts(void *store);

@@ -86,6 +86,7 @@ def prepare_shared_object(path=None):
         "mdaStoreSetBinFromStruct": (ct.c_int, [_VP, ct.c_int, _VP]),
         "mdaStoreSetBounds": (ct.c_int, [_VP, _DP, _DP]),
         "mdaStoreUpload": (ct.c_int, [_VP]),
+        "mdaStoreConditioning": (ct.c_int, [_VP, _DP, _DP, ct.POINTER(ct.c_int)]),
         "mdaStoreNumBins": (ct.c_int, [_VP]),
         "mdaStoreNumL": (ct.c_int, [_VP]),
         "mdaStoreMaxPts": (ct.c_int, [_VP]),
@@ -310,6 +311,17 @@ class DeviceStore:
 
     def synchronize(self):
         check(self.lib, self.lib.mdaStoreSynchronize(self.handle), "mdaStoreSynchronize")
+
+    def conditioning(self):
+        """``(kappa [B], limit, quad_safe)``: per bin |data| / sqrt(min chi^2), the limit the triangular-factor
+        likelihood of the sampler tolerates, and whether every bin is within it (else the ensemble is stepped in
+        the reference's operation order)."""
+        kappa = np.empty(self.n_bins, dtype=np.float64)
+        limit = ct.c_double()
+        safe = ct.c_int()
+        check(self.lib, self.lib.mdaStoreConditioning(self.handle, kappa.ctypes.data_as(_DP), ct.byref(limit), ct.byref(safe)),
+              "mdaStoreConditioning")
+        return kappa, limit.value, bool(safe.value)
 
     def close(self):
         if getattr(self, "handle", None):

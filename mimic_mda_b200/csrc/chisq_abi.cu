@@ -196,6 +196,11 @@ struct MdaStore {
     std::vector<double> host_mma;    // [bins][n_tiles][8 (1+L)]  fragment-major copy for the DMMA stepper
     int n_tiles = 0;                 // angle tiles of 8
     std::vector<double> host_quad;   // [bins][quad_stride(L)]  packed triangular factor of [D^T | d] (see factor_bin)
+    std::vector<double> kappa;       // [bins]  |d| / sqrt(min chi^2): how much rounding the triangular-factor chi^2 amplifies (see factor_bin)
+    bool factors_stale = true;       // host_quad / kappa do not reflect the host mirror yet
+    unsigned long long generation = 1;   // bumped by every change of a bin or of the bounds: ensembles remember the one their state belongs to
+    int live_ensembles = 0;          // ensembles created on this store and not yet freed
+    bool closing = false;            // mdaStoreFree was called while ensembles were alive: freed with the last of them
     double *d_quad = nullptr;
     std::vector<int> n_pts;          // [bins]
     std::vector<double> lo, hi;      // [L]
@@ -215,8 +220,8 @@ struct MdaStore {
 
 MdaStore *as_store(void *p, const char *fn) {
     MdaStore *s = static_cast<MdaStore *>(p);
-    if (!s || s->magic != kStoreMagic) {
-        set_error(MDA_ERR_BAD_ARGUMENT, "%s: not a handle from mdaStoreCreate", fn);
+    if (!s || s->magic != kStoreMagic || s->closing) {
+        set_error(MDA_ERR_BAD_ARGUMENT, "%s: not a (live) handle from mdaStoreCreate", fn);
         return nullptr;
     }
     return s;
@@ -255,6 +260,8 @@ void write_bin(MdaStore *s, int bin, int n, const double *data, const double *di
     }
     s->n_pts[bin] = n;
     s->dirty = true;
+    s->factors_stale = true;
+    ++s->generation;
 }
 
 // chi^2(a) = |d - D^T a|^2 (C/ChiSquare.c:188-210) is |M [a; -1]|^2 with M = [D^T | d] (N x (L+1)), and M = Q T with
@@ -262,7 +269,17 @@ void write_bin(MdaStore *s, int bin, int n, const double *data, const double *di
 // whatever N is.  No inverse is taken (rank-deficient bins are fine) and every term is a square, so there is no
 // cancellation beyond the one inside a row, which is that of the residuals themselves.  T comes from Householder
 // reflections in long double (64-bit mantissa) and is rounded to double once; packed by rows: T[i][i..L].
-void factor_bin(const MdaStore *s, int bin, double *packed) {
+//
+// What it costs in accuracy.  Both this form and the reference's angle-by-angle sum round every partial result of a
+// residual at the size of the DATA (eps |d_j|), while the residual that survives is smaller by the relative error of the
+// measurement; chi^2 computed either way is therefore only good to about eps * kappa relative, kappa = |d| / sqrt(chi^2),
+// and two different orders of the same arithmetic differ from each other by that much (measured against the unmodified
+// reference library: 1.0 eps_machine * kappa -- 5e-15 at 5 % errors, 2e-13 at 0.1 %, 2e-12 at 0.01 %).  The angle-by-angle
+// kernels in the reference's operation order reproduce its rounding itself and are immune.  Returned: kappa at the
+// unconstrained minimum, |d| / |T[L][L]| (the largest it gets; infinite when the bin can be fitted exactly).  Stores with
+// a bin beyond kQuadKappaMax are stepped by the reference-order stepper instead (ensemble_shape_for).
+constexpr double kQuadKappaMax = 1e-13 / (4.0 * 1.1102230246251565e-16);      // 4 eps kappa <= 1e-13: a tenth of north_star's 1e-12
+double factor_bin(const MdaStore *s, int bin, double *packed) {
     const int n = s->n_pts[bin], L = s->n_l, C = L + 1, row = L + 1;
     const double *blk = s->host.data() + (size_t)bin * bin_stride(s);
     const int rows = std::max(n, C);
@@ -294,11 +311,31 @@ void factor_bin(const MdaStore *s, int bin, double *packed) {
     size_t o = 0;
     for (int i = 0; i < C; ++i)
         for (int c = i; c < C; ++c) packed[o++] = (double)m[(size_t)i * C + c];
+    long double d2 = 0.0L;                                           // |Q^T d|^2 = |d|^2: the last column of T
+    for (int i = 0; i < C; ++i) d2 += m[(size_t)i * C + L] * m[(size_t)i * C + L];
+    const long double floor_chi = fabsl(m[(size_t)L * C + L]);       // sqrt of the unconstrained minimum of chi^2
+    if (d2 == 0.0L) return 1.0;                                      // an empty bin: chi^2 is exactly 0 everywhere
+    return floor_chi > 0.0L ? (double)(sqrtl(d2) / floor_chi) : std::numeric_limits<double>::infinity();
+}
+
+// host side of upload_store: triangular factors and their conditioning, from the host mirror
+void ensure_factors(MdaStore *s) {
+    if (!s->factors_stale) return;
+    s->kappa.assign((size_t)s->bins, 1.0);
+    for (int b = 0; b < s->bins; ++b) s->kappa[(size_t)b] = factor_bin(s, b, s->host_quad.data() + (size_t)b * (size_t)quad_stride(s->n_l));
+    s->factors_stale = false;
+}
+
+// every bin's chi^2 from the triangular factor stays within 4 eps kappa <= 1e-13 of the reference's arithmetic
+bool quad_is_safe(MdaStore *s) {
+    ensure_factors(s);
+    for (double k : s->kappa) if (!(k <= kQuadKappaMax)) return false;
+    return true;
 }
 
 int upload_store(MdaStore *s) {
     if (!s->dirty) return MDA_OK;
-    for (int b = 0; b < s->bins; ++b) factor_bin(s, b, s->host_quad.data() + (size_t)b * (size_t)quad_stride(s->n_l));
+    ensure_factors(s);
     MDA_CUDA(cudaMemcpyAsync(s->d_quad, s->host_quad.data(), sizeof(double) * s->host_quad.size(), cudaMemcpyHostToDevice,
                              s->stream), "store upload (triangular factors)");
     MDA_CUDA(cudaMemcpyAsync(s->d_consts, s->host.data(), sizeof(double) * s->host.size(), cudaMemcpyHostToDevice,
@@ -483,6 +520,9 @@ struct MdaEnsemble {
     long long keep_cap = 0, kept = 0, steps = 0;
     long long alloc_cap = 0;         // kept samples the chain allocations can hold (>= keep_cap: a smaller reservation reuses them)
     bool has_state = false;
+    unsigned long long state_generation = 0;   // the store's generation when the state (and its log-probabilities) was set
+    unsigned long long epoch = 0;    // mdaEnsembleSetState calls before the current one: folded into the Philox key, so that a run
+                                     // restarted on the same ensemble (burn-in, then production) does not replay the first run's draws
     long long *d_prof = nullptr;     // [bins][8] section cycle counters of the last launch (debug)
     void *scratch = nullptr;         // device scratch of the posterior reductions, grown on demand
     size_t scratch_bytes = 0;
@@ -497,8 +537,12 @@ struct MdaEnsemble {
 // (ensemble_ws_kernel, one bin per SM at a time).  The register-tiled DFMA stepper carries numL < 4, ensembles of
 // more than 512 walkers and ensembles larger than shared memory.  MDA_ENS_IMPL = quad | mma | ws | dfma forces one,
 // direct = the angle-by-angle steppers picked by shape as described.
-EnsembleShape ensemble_shape_for(const MdaStore *s, int walkers) {
+EnsembleShape ensemble_shape_for(MdaStore *s, int walkers) {
     const char *impl = getenv("MDA_ENS_IMPL");
+    // A store with an ill-conditioned bin (see factor_bin) is stepped in the reference's operation order, whatever it costs;
+    // an explicit MDA_ENS_IMPL is honoured (experiments).
+    if (!impl && !quad_is_safe(s))
+        return choose_ensemble_shape(s->bins, walkers, s->n_l, s->n_pad, g_rt.sm_count, g_rt.smem_optin, env_int("MDA_ENS_GROUPS", 0), env_int("MDA_ENS_WPT", 0));
     const bool want_dfma = impl && strcmp(impl, "dfma") == 0, want_ws = impl && strcmp(impl, "ws") == 0,
                want_mma = impl && strcmp(impl, "mma") == 0, want_quad = impl && strcmp(impl, "quad") == 0,
                want_direct = impl && strcmp(impl, "direct") == 0,       // angle-by-angle evaluation, stepper picked by shape
@@ -614,7 +658,7 @@ int qws_grid(const MdaStore *s, const EnsembleShape &shape) {
 
 MdaEnsemble *as_ensemble(void *p, const char *fn) {
     MdaEnsemble *e = static_cast<MdaEnsemble *>(p);
-    if (!e || e->magic != kEnsembleMagic || !e->store || e->store->magic != kStoreMagic) {
+    if (!e || e->magic != kEnsembleMagic || !e->store || e->store->magic != kStoreMagic) {      // (a store freed before its ensembles stays alive until the last of them goes)
         set_error(MDA_ERR_BAD_ARGUMENT, "%s: not a live handle from mdaEnsembleCreate", fn);
         return nullptr;
     }
@@ -782,9 +826,25 @@ void *mdaStoreCreate(int numBins, int numL, int maxPts) {
     return s;
 }
 
+}  // extern "C"
+
+namespace {
+void destroy_store(MdaStore *s);
+}
+
+extern "C" {
+
 void mdaStoreFree(void *store) {
     MdaStore *s = as_store(store, "mdaStoreFree");
     if (!s) return;
+    if (s->live_ensembles > 0) { s->closing = true; return; }      // its ensembles still point at it: freed with the last of them
+    destroy_store(s);
+}
+
+}  // extern "C"
+
+namespace {
+void destroy_store(MdaStore *s) {
     if (g_rt.ready) cudaSetDevice(g_rt.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     drop_graphs(s);
@@ -802,6 +862,9 @@ void mdaStoreFree(void *store) {
     s->magic = 0;
     delete s;
 }
+}  // namespace
+
+extern "C" {
 
 int mdaStoreSetBin(void *store, int bin, int numPts, const double *divData, const double *dists) {
     MdaStore *s = as_store(store, "mdaStoreSetBin");
@@ -832,6 +895,7 @@ int mdaStoreSetBounds(void *store, const double *lo, const double *hi) {
     s->lo.assign(lo, lo + s->n_l);
     s->hi.assign(hi, hi + s->n_l);
     s->dirty = true;
+    ++s->generation;
     if (s->stream) cudaStreamSynchronize(s->stream);
     drop_graphs(s);                                       // bounds are baked into captured launches
     return MDA_OK;
@@ -843,6 +907,16 @@ int mdaStoreUpload(void *store) {
     int rc = ensure_runtime();
     if (rc) return rc;
     return upload_store(s);
+}
+
+int mdaStoreConditioning(void *store, double *kappa, double *kappaMax, int *quadSafe) {
+    MdaStore *s = as_store(store, "mdaStoreConditioning");
+    if (!s) return MDA_ERR_BAD_ARGUMENT;
+    const bool safe = quad_is_safe(s);                   // (host arithmetic only: no device is touched)
+    if (kappa) for (int b = 0; b < s->bins; ++b) kappa[b] = s->kappa[(size_t)b];
+    if (kappaMax) *kappaMax = kQuadKappaMax;
+    if (quadSafe) *quadSafe = safe ? 1 : 0;
+    return MDA_OK;
 }
 
 int mdaStoreNumBins(void *store) { MdaStore *s = as_store(store, "mdaStoreNumBins"); return s ? s->bins : -1; }
@@ -1013,6 +1087,7 @@ void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, doub
     }
     MdaEnsemble *e = new MdaEnsemble();
     e->store = s;
+    ++s->live_ensembles;
     e->walkers = nWalkers;
     e->seed = seed;
     e->a = stretchA;
@@ -1038,7 +1113,8 @@ void mdaEnsembleFree(void *ens) {
     MdaEnsemble *e = static_cast<MdaEnsemble *>(ens);
     if (!e || e->magic != kEnsembleMagic) { set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleFree: not a handle from mdaEnsembleCreate"); return; }
     if (g_rt.ready) cudaSetDevice(g_rt.device);
-    if (e->store && e->store->magic == kStoreMagic && e->store->stream) cudaStreamSynchronize(e->store->stream);
+    MdaStore *owner = (e->store && e->store->magic == kStoreMagic) ? e->store : nullptr;
+    if (owner && owner->stream) cudaStreamSynchronize(owner->stream);
     if (e->d_pos) cudaFree(e->d_pos);
     if (e->d_lnp) cudaFree(e->d_lnp);
     if (e->d_nacc) cudaFree(e->d_nacc);
@@ -1057,6 +1133,7 @@ void mdaEnsembleFree(void *ens) {
     }
     e->magic = 0;
     delete e;
+    if (owner && --owner->live_ensembles == 0 && owner->closing) destroy_store(owner);   // mdaStoreFree came first
 }
 
 int mdaEnsembleSetBinIds(void *ens, const int *binIds) {
@@ -1087,6 +1164,8 @@ int mdaEnsembleSetState(void *ens, const double *p0) {
     MDA_CUDA(cudaMemsetAsync(e->d_status, 0, sizeof(int), s->stream), "ensemble status");
     if (n_eval && (rc = enqueue_eval(s, e->walkers, e->d_pos, e->d_lnp, kLnPost))) return rc;
     MDA_CUDA(cudaStreamSynchronize(s->stream), "mdaEnsembleSetState");
+    if (e->state_generation != 0) ++e->epoch;             // a restart on the same ensemble draws from a fresh stream
+    e->state_generation = s->generation;
     e->steps = 0;
     e->kept = 0;
     e->has_state = true;
@@ -1125,6 +1204,9 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     if (!e) return MDA_ERR_BAD_ARGUMENT;
     if (nSteps < 0 || thin < 1) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleAdvance: nSteps >= 0 and thin >= 1 required");
     if (!e->has_state) return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleAdvance: call mdaEnsembleSetState first");
+    if (e->state_generation != e->store->generation)
+        return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleAdvance: the store's bins or bounds changed after mdaEnsembleSetState: the stored "
+                                            "log-probabilities belong to the old ones, call mdaEnsembleSetState again");
     if ((unsigned long long)(e->steps + nSteps) >= (1ull << 31)) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleAdvance: step counter would exceed 2^31");
     int rc = ensure_runtime();
     if (rc) return rc;
@@ -1151,8 +1233,9 @@ int mdaEnsembleAdvance(void *ens, int nSteps, int thin) {
     args.step0 = e->steps;
     args.keep0 = e->kept;
     args.keep_cap = e->keep_cap;
-    args.seed_lo = (unsigned int)(e->seed & 0xFFFFFFFFull);
-    args.seed_hi = (unsigned int)(e->seed >> 32);
+    const unsigned long long key = e->seed + e->epoch * 0x9E3779B97F4A7C15ull;     // epoch 0 (a fresh ensemble): the seed itself
+    args.seed_lo = (unsigned int)(key & 0xFFFFFFFFull);
+    args.seed_hi = (unsigned int)(key >> 32);
     args.a = e->a;
     {
         uint32_t rk[20];
@@ -1240,6 +1323,17 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
         snprintf(text, (size_t)textLen, "ensemble_kernel<L=%d,WPT=%d,%s>: DFMA chi^2, %d threads x %d angle groups per CTA, %zu B shared memory; one CTA per bin (%d)",
                  s->n_l, shape.wpt, shape.global_state ? "state in HBM" : "state in shared memory", shape.threads, shape.groups, shape.smem_bytes, s->bins);
     }
+    // the conditioning decision (factor_bin): which bin, if any, ruled the triangular-factor stepper out
+    double worst = 0.0;
+    int worst_bin = -1;
+    ensure_factors(s);
+    for (int b = 0; b < s->bins; ++b) if (!(s->kappa[(size_t)b] <= worst)) { worst = s->kappa[(size_t)b]; worst_bin = b; }
+    const size_t used = strlen(text);
+    if (used + 1 < (size_t)textLen)
+        snprintf(text + used, (size_t)textLen - used, "; conditioning: max kappa = |d|/sqrt(min chi^2) = %.3g (bin %d), limit %.3g for the triangular factor -> %s",
+                 worst, worst_bin, kQuadKappaMax,
+                 shape.quad ? "chi^2 from the triangular factor (within 4 eps kappa of the reference's arithmetic)"
+                            : (worst <= kQuadKappaMax ? "angle-by-angle stepper on request" : "reference-order stepper (angle by angle, C/ChiSquare.c:188-210)"));
     return MDA_OK;
 }
 
@@ -1324,6 +1418,8 @@ int mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double
     if (!e) return MDA_ERR_BAD_ARGUMENT;
     if (nSteps < 0 || thin < 1) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleRunToHost: nSteps >= 0 and thin >= 1 required");
     if (!e->has_state) return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleRunToHost: call mdaEnsembleSetState first");
+    if (e->state_generation != e->store->generation)
+        return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleRunToHost: the store changed after mdaEnsembleSetState, call it again");
     if (e->steps % thin != 0) return set_error(MDA_ERR_BAD_STATE, "mdaEnsembleRunToHost: %lld steps already taken is not a multiple of thin = %d", e->steps, thin);
     int rc = ensure_runtime();
     if (rc) return rc;

@@ -46,7 +46,7 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
-constexpr int kStatusStalled = 4;        // a unit waited ~3 s for its predecessor: the launch gave up (never seen; a guard against a hung GPU)
+constexpr int kStatusStalled = 4;        // a unit waited 4 s (wall clock) for its predecessor: the launch gave up (never seen; a guard against a hung GPU)
 constexpr int kMaxWarps = 8;           // items (warps) per CTA
 constexpr int kDrawnBarrier = 1;       // named barrier: the draw of the next half-step is published (draw warps arrive, the others wait)
 constexpr size_t kStaticSmem = 64;     // the mbarriers (static __shared__), rounded up
@@ -211,10 +211,10 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
             bulk_g2s(smem_raw + lay.consts, args.consts_mma + (size_t)bin * NT * TS, cb, &mbar);
             if (chunk > 0) {
                 const unsigned long long want = args.launch_serial + (unsigned long long)chunk;
-                unsigned int spins = 0;
+                const unsigned long long t_start = globaltimer_ns();
                 while (ld_acquire_u64(args.progress + bin) != want) {
                     __nanosleep(64);
-                    if (++spins > (1u << 25)) { s_abort = 1; break; }     // ~3 s: the predecessor is not coming
+                    if (globaltimer_ns() - t_start > kHandOverTimeoutNs) { s_abort = 1; break; }     // 4 s of wall clock: the predecessor is not coming
                 }
             }
         }
@@ -617,8 +617,7 @@ cudaError_t launch_ensemble_mma(const EnsembleArgs &args, const EnsembleShape &s
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;
     EnsembleArgs a = args;
-    k<<<grid, shape.threads, shape.smem_bytes, stream>>>(a);
-    return cudaGetLastError();
+    return launch_maybe_cooperative(k, a, a.n_chunks > 1, grid, shape.threads, shape.smem_bytes, stream);
 }
 
 }  // namespace mda

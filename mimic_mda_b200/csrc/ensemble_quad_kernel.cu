@@ -37,7 +37,7 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
-constexpr int kStatusStalled = 4;        // a unit waited ~3 s for its predecessor: the launch gave up (a guard against a hung GPU)
+constexpr int kStatusStalled = 4;        // a unit waited 4 s (wall clock) for its predecessor: the launch gave up (a guard against a hung GPU)
 constexpr int kQuadMaxThreads = 256;
 
 struct QuadSmem {
@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(con
         unsigned int *gAcc = args.nacc + (size_t)bin * W;
         if (tid == 0 && chunk > 0) {
             const unsigned long long want = args.launch_serial + (unsigned long long)chunk;
-            unsigned int spins = 0;
+            const unsigned long long t_start = globaltimer_ns();
             while (ld_acquire_u64(args.progress + bin) != want) {
                 __nanosleep(64);
-                if (++spins > (1u << 25)) { s_abort = 1; break; }             // ~3 s: the predecessor is not coming
+                if (globaltimer_ns() - t_start > kHandOverTimeoutNs) { s_abort = 1; break; }     // 4 s of wall clock: the predecessor is not coming
             }
         }
         __syncthreads();
@@ -317,8 +317,7 @@ cudaError_t launch_ensemble_quad(const EnsembleArgs &args, const EnsembleShape &
     if (!k || !shape.fits || !shape.quad || !args.quad || grid < 1 || args.chunk_steps < 1 || args.n_chunks < 1 ||
         (args.n_chunks > 1 && !args.progress))
         return cudaErrorInvalidValue;
-    k<<<grid, shape.threads, shape.smem_bytes, stream>>>(args);
-    return cudaGetLastError();
+    return launch_maybe_cooperative(k, args, args.n_chunks > 1, grid, shape.threads, shape.smem_bytes, stream);
 }
 
 }  // namespace mda

@@ -48,7 +48,7 @@ namespace mda {
 namespace {
 
 constexpr int kStatusNaN = 1;
-constexpr int kStatusStalled = 4;        // a unit waited ~3 s for its predecessor: the launch gave up (never seen; a guard against a hung GPU)
+constexpr int kStatusStalled = 4;        // a unit waited 4 s (wall clock) for its predecessor: the launch gave up (never seen; a guard against a hung GPU)
 constexpr int kWalkerWarps = 8;        // at most: one group of 32 walkers each
 constexpr int kMathWarps = 8;          // at most: two per scheduler keep the fp64 pipe fed
 constexpr int GW = 32;                 // walkers of a group (a walker warp's lanes)
@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
             bulk_g2s(smem_raw + lay.consts, args.consts_mma + (size_t)bin * NT * TS, cb, &mbar);
             if (chunk > 0) {
                 const unsigned long long want = args.launch_serial + (unsigned long long)chunk;
-                unsigned int spins = 0;
+                const unsigned long long t_start = globaltimer_ns();
                 while (ld_acquire_u64(args.progress + bin) != want) {
                     __nanosleep(64);
-                    if (++spins > (1u << 25)) { s_abort = 1; break; }     // ~3 s: the predecessor is not coming
+                    if (globaltimer_ns() - t_start > kHandOverTimeoutNs) { s_abort = 1; break; }     // 4 s of wall clock: the predecessor is not coming
                 }
             }
         }
@@ -596,8 +596,7 @@ cudaError_t launch_ensemble_ws(const EnsembleArgs &args, const EnsembleShape &sh
         return cudaErrorInvalidValue;
     EnsembleArgs a = args;
     a.groups = shape.groups;                               // walker warps (the rest of the block are math warps)
-    k<<<grid, shape.threads, shape.smem_bytes, stream>>>(a);
-    return cudaGetLastError();
+    return launch_maybe_cooperative(k, a, a.n_chunks > 1, grid, shape.threads, shape.smem_bytes, stream);
 }
 
 }  // namespace mda

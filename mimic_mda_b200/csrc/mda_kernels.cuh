@@ -149,6 +149,29 @@ int ensemble_qws_capacity(int n_l, const EnsembleShape &shape, int sm_count);   
 // grid == bins: a CTA per bin; grid < bins: the bins' step ranges cut evenly over `grid` CTAs (cooperative launch, args.progress set)
 cudaError_t launch_ensemble_qws(const EnsembleArgs &args, const EnsembleShape &shape, int grid, cudaStream_t stream);
 
+// A stepping launch whose CTAs wait for each other's progress words (units of one bin on different CTAs) must have every
+// CTA resident: launched cooperatively, a grid that cannot be co-resident fails at launch instead of spinning.
+template <typename Kernel>
+inline cudaError_t launch_maybe_cooperative(Kernel k, const EnsembleArgs &args, bool ctas_wait_for_each_other, int grid, int threads,
+                                            size_t smem_bytes, cudaStream_t stream) {
+    if (!ctas_wait_for_each_other) {
+        k<<<grid, threads, smem_bytes, stream>>>(args);
+        return cudaGetLastError();
+    }
+    EnsembleArgs copy = args;
+    void *params[] = {&copy};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k), dim3((unsigned)grid), dim3((unsigned)threads), params, smem_bytes, stream);
+}
+
+// Wall-clock bound of a wait for another CTA's progress word (nanoseconds of %globaltimer): generous enough for a
+// profiler's replay or a sanitizer, short enough not to look like a hung GPU.
+constexpr unsigned long long kHandOverTimeoutNs = 4000000000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
 // gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.
 cudaError_t launch_gram(const double *consts, const int *n_pts, int bins, int n_l, int n_pad, double *gram, double *rhs,

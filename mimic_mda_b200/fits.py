@@ -6,8 +6,7 @@ Mirrors, with the reference's names and argument meaning:
     initial_fits           mda.py:1114-1120  fit from every start, sort by chi^2, keep the best
                                              "Number Walker Generators"  (do_init_fit 1664-1709
                                              runs on the GPU: DeviceStore.fit -> mdaBatchFit)
-    gen_walker_starts      mda.py:1581-1610
-    randomize_position     mda.py:1613-1661
+    gen_walker_starts      mda.py:1581-1661  (with its per-walker helper folded in, vectorised)
 
 The fits are done for all Ex bins and all starts in one library call.
 """
@@ -34,27 +33,16 @@ def initial_fits(store, starts, n_generators):
     return gens, np.take_along_axis(chi, order, axis=1)
 
 
-def randomize_position(gen, ndims, spread, offset_centroid, offset_width, ewsr, rng):
-    """One randomised walker start from a generator (mda.py:1613-1661); ``rng`` supplies
-    ``standard_normal`` (the reference uses the global, unseeded numpy generator)."""
-    rands = spread * rng.standard_normal(ndims)
-    randomizer = np.ones(ndims, dtype=np.float64) - rands
-    base_offsets = offset_width * rng.standard_normal(ndims)
-    offsets = offset_centroid * np.ones(ndims, dtype=np.float64) + base_offsets
-    position = randomizer * (gen + offsets)
-    for i in range(ndims):
-        if position[i] < 0.0:
-            position[i] *= -1.0
-        if position[i] < FLOAT_EPSILON:
-            position[i] = 0.001
-        if position[i] > (1.0 / ewsr[i]):
-            position[i] = (1.0 / ewsr[i]) - 0.001
-    return position
-
-
 def gen_walker_starts(gens, n_walkers, spread, offset_centroid, offset_width, ewsr, rng):
-    """Walker start positions for one bin from its generators (mda.py:1581-1610)."""
-    ndims = gens.shape[1]
-    n_gen = gens.shape[0]
-    return np.array([randomize_position(gens[i % n_gen], ndims, spread, offset_centroid, offset_width, ewsr, rng)
-                     for i in range(n_walkers)])
+    """Walker start positions for one bin, ``[n_walkers, L]``: walker i starts from generator ``i mod n_gen``, shifted by
+    a Gaussian offset (centroid, width) and scaled by ``1 - spread * N(0, 1)`` per parameter, then brought inside the
+    box: negative values are mirrored, values below ``FLOAT_EPSILON`` become 0.001 and values above ``1 / EWSR_l``
+    become ``1 / EWSR_l - 0.001`` (the rule of mda.py:1581-1661, applied to all walkers at once).  ``rng`` supplies
+    ``standard_normal`` (the reference draws from numpy's global, unseeded generator, so no draw order is defined)."""
+    gens = np.asarray(gens, dtype=np.float64)
+    upper = 1.0 / np.asarray(ewsr, dtype=np.float64)
+    noise = rng.standard_normal((n_walkers, 2, gens.shape[1]))
+    base = gens[np.arange(n_walkers) % gens.shape[0]]
+    pos = np.abs((1.0 - spread * noise[:, 0]) * (base + offset_centroid + offset_width * noise[:, 1]))
+    pos = np.where(pos < FLOAT_EPSILON, 0.001, pos)
+    return np.where(pos > upper, upper - 0.001, pos)

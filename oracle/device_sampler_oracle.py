@@ -39,12 +39,15 @@ def uniform53(a, b):
     return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
 
 
-def run(lnpost_fn, p0, n_steps, seed, bin_ids=None, a=2.0, thin=1, step0=0, lnprob0=None, naccepted0=None):
+def run(lnpost_fn, p0, n_steps, seed, bin_ids=None, a=2.0, thin=1, step0=0, lnprob0=None, naccepted0=None, epoch=0):
     """Advance ``p0 [B, W, L]`` by ``n_steps`` steps.  ``lnpost_fn([B, Wc, L]) -> [B, Wc]``.
     Returns dict(pos, lnp, nacc, chain [B, kept, W, L], lnp_chain [B, kept, W])."""
     p = np.array(p0, dtype=np.float64)
     n_bins, n_walk, n_l = p.shape
     bin_ids = np.arange(n_bins, dtype=np.uint64) if bin_ids is None else np.asarray(bin_ids, dtype=np.uint64)
+    # the Philox key: the seed for an ensemble's first state, seed + epoch * 2^64/phi for its epoch-th restart
+    # (mdaEnsembleSetState called again on the same ensemble; chisq_abi.cu: mdaEnsembleAdvance)
+    seed = (seed + epoch * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     lnp = np.array(lnpost_fn(p) if lnprob0 is None else lnprob0, dtype=np.float64)
     nacc = np.zeros((n_bins, n_walk), dtype=np.int64) if naccepted0 is None else np.array(naccepted0)

@@ -31,6 +31,19 @@ def factor(data, dists):
     return np.triu(m[:c]).astype(np.float64)
 
 
+KAPPA_MAX = 1e-13 / (4.0 * 2.0 ** -53)      # chisq_abi.cu: kQuadKappaMax
+
+
+def kappa(t):
+    """|d| / sqrt(min chi^2) of a factor (chisq_abi.cu::factor_bin): chi^2 from T and chi^2 in the reference's order
+    differ by about eps * kappa relative; bins beyond KAPPA_MAX are not evaluated from T by the library."""
+    n_l = t.shape[0] - 1
+    norm_d = float(np.sqrt(np.sum(t[:, n_l].astype(np.longdouble) ** 2)))
+    if norm_d == 0.0:
+        return 1.0
+    return norm_d / abs(t[n_l, n_l]) if t[n_l, n_l] != 0.0 else np.inf
+
+
 def chi(t, params):
     """t [(L+1), (L+1)], params [..., L] -> chi^2 [...], accumulated as the kernels do (row sums, minus the data, squared)."""
     n_l = t.shape[0] - 1

@@ -301,3 +301,31 @@ def test_balanced_schedule_of_the_default_stepper_with_thinning_and_split_runs(c
     ens.close()
     ref.close()
     store.close()
+
+
+def test_restart_on_the_same_ensemble_draws_a_fresh_stream_and_store_changes_are_noticed(cs_lib, oracle_lib):
+    """burn-in, then run_mcmc again on the same ensemble: the second run must not replay the first run's draws (its Philox
+    key is the seed advanced by the restart count); a store modified after set_state invalidates the stored
+    log-probabilities; a store freed before its ensemble stays alive until the ensemble goes."""
+    consts, counts, lo, hi, p0, _ = _problem(3, 4, 12, 32)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=cs_lib)
+    ens = DeviceEnsemble(store, 32, seed=11)
+    ens.run_mcmc(p0, 12)
+    first = ens.chain.copy()
+    ens.run_mcmc(p0, 12)
+    second = ens.chain.copy()
+    assert not np.array_equal(first, second)
+    fn = lambda p: oracle_lib.lnpost_bins(consts, counts, lo, hi, p)
+    np.testing.assert_allclose(first.transpose(0, 2, 1, 3), dso.run(fn, p0, 12, seed=11)["chain"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(second.transpose(0, 2, 1, 3), dso.run(fn, p0, 12, seed=11, epoch=1)["chain"], rtol=1e-12, atol=0)
+    # the store changes under the ensemble
+    store.set_bounds((lo, hi * 0.9))
+    with pytest.raises(chisq.MdaError):
+        ens.advance(1)
+    ens.set_state(p0 * 0.9)
+    ens.advance(2)
+    # freeing the store first is safe
+    store.close()
+    pos, lnp, _ = ens.state()
+    assert np.all(np.isfinite(pos))
+    ens.close()

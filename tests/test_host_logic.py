@@ -136,3 +136,24 @@ def test_device_sampler_restatement_samples_the_same_posterior():
     assert np.all(np.abs(s_d["mean"] - s_h["mean"]) < 0.3 * s_h["std"] + 1e-5)
     assert np.all(dev["chain"] >= lo) and np.all(dev["chain"] <= hi)
     assert 0.2 < dev["nacc"].mean() / 500 < 0.9
+
+
+def test_walker_starts_obey_the_box_rules():
+    """mda.py:1613-1661: negative values mirrored, tiny ones become 0.001, values above 1/EWSR become 1/EWSR - 0.001."""
+    from mimic_mda_b200 import fits
+
+    class Fixed:                                       # a "generator" with chosen normal draws
+        def __init__(self, draws):
+            self.draws = draws
+
+        def standard_normal(self, shape):
+            return np.broadcast_to(self.draws, shape).copy()
+    gens = np.array([[0.2, 0.5, 0.0, 0.9], [0.1, 0.1, 0.1, 0.1]])
+    ewsr = np.array([1.0, 1.0, 1.0, 2.0])                # upper bounds 1, 1, 1, 0.5
+    # spread 1, scale draw 3 -> factor (1 - 3) = -2: values turn negative and are mirrored
+    got = fits.gen_walker_starts(gens, 3, 1.0, 0.0, 0.0, ewsr, Fixed(np.array([[3.0], [0.0]])[None]))
+    np.testing.assert_allclose(got[0], [0.4, 1.0 - 0.001 if 2 * 0.5 > 1.0 else 1.0, 0.001, 0.5 - 0.001])
+    np.testing.assert_allclose(got[1], [0.2, 0.2, 0.2, 0.2])                    # walker 1 starts from generator 1
+    np.testing.assert_allclose(got[2], got[0])                                   # walker 2 from generator 0 again
+    rnd = fits.gen_walker_starts(gens, 500, 2.0, 0.04, 0.02, ewsr, np.random.RandomState(1))
+    assert rnd.shape == (500, 4) and np.all(rnd > 0) and np.all(rnd <= 1.0 / ewsr)

@@ -146,3 +146,29 @@ def test_triangular_factor_evaluation_reproduces_reference_outputs(golden):
             scale = np.maximum(np.abs(want), 1e-300)
             worst = max(worst, float(np.max(np.abs(got - want) / scale))) if want.size else worst
     assert worst <= 1e-12, worst
+
+
+@pytest.mark.parametrize("rel", [5e-2, 1e-2, 1e-3, 3e-4, 1e-4])
+def test_conditioning_guard_of_the_triangular_factor(rel):
+    """Near the minimum the triangular-factor chi^2 and the reference-order chi^2 differ by about eps * kappa,
+    kappa = |d| / sqrt(min chi^2) ~ 1 / (relative error of the cross-sections): inside the 1e-12 bound for kappa up to
+    KAPPA_MAX (which is what the library evaluates from T), beyond it for 0.01 % errors -- those bins must be flagged."""
+    from mimic_mda_b200 import synth
+    from oracle import quad_oracle
+    consts, n_pts, a_true = synth.make_bins(6, 9, 60, rel_err=rel, ragged=True)
+    lo, hi = synth.default_bounds(9)
+    params = synth.make_walkers(a_true, 256, seed=3, scatter=0.04 * rel, oob_frac=0.0)
+    want = numpy_oracle.lnpost_bins(consts, n_pts, lo, hi, params)        # the reference's order (pinned above)
+    worst, kappas = 0.0, []
+    for b in range(6):
+        n = int(n_pts[b])
+        t = quad_oracle.factor(consts[b, 0, :n], consts[b, 1:, :n])
+        kappas.append(quad_oracle.kappa(t))
+        got = -0.5 * quad_oracle.chi(t, params[b])
+        worst = max(worst, float(np.max(np.abs(got - want[b]) / np.abs(want[b]))))
+    k = max(kappas)
+    assert 0.5 / rel < k < 3.0 / rel                                       # kappa tracks 1 / relative error
+    assert worst <= 8.0 * 2.0 ** -53 * k, (worst, k)                       # measured: ~2 eps kappa
+    if k <= quad_oracle.KAPPA_MAX:
+        assert worst <= 1e-13, (worst, k)                                  # what the library evaluates from T: 10x inside the bound
+    assert (k <= quad_oracle.KAPPA_MAX) == (rel >= 1e-2)                   # 1 % and above from T, below in the reference's order

@@ -67,11 +67,14 @@ def test_whole_path_and_sharding(tmp_path, cs_lib):
     np.testing.assert_array_equal(np.array(merged[0][0][0]), np.array(results[0][0][0]))
 
 
-def test_cli_runs_a_reference_style_config(tmp_path, cs_lib):
-    """A configuration file in the reference's format (a Python file filling CONFIG) drives the
-    whole path; keys unrelated to the likelihood path are ignored."""
+def test_config_driver_runs_a_reference_style_config(tmp_path, cs_lib):
+    """tools/run_config.py (a convenience driver outside the package): a configuration file in the reference's
+    format (a Python file filling CONFIG) drives the whole path; keys unrelated to the likelihood path are ignored."""
+    import importlib.util
     import json
-    from mimic_mda_b200 import run
+    spec = importlib.util.spec_from_file_location("run_config", os.path.join(ROOT, "tools", "run_config.py"))
+    run = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(run)
     cfg = _config(tmp_path)
     cfg.update({"Start Pts a0": [0.05, 0.25], "Start Pts a1": [0.05, 0.25], "Start Pts a2": [0.1], "Start Pts a3": [0.05, 0.2],
                 "Shared Lib Path": "./C/libChiSq.so", "Generate Fit Plots": True, "Plot DPI": 300, "Number of Threads": 4})

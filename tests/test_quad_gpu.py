@@ -94,3 +94,44 @@ def test_sampler_log_probabilities_equal_the_oracle_on_the_visited_positions(cs_
         assert rel_err(lnp[:, :, k], want) <= TOL
     ens.close()
     store.close()
+
+
+@pytest.mark.parametrize("rel", [1e-2, 1e-3, 3e-4, 1e-4])
+def test_sampler_stays_within_the_bound_whatever_the_conditioning(cs_lib, oracle_lib, rel):
+    """Near the minimum, chi^2 from T differs from the reference's arithmetic by ~eps |d| / sqrt(chi^2): the library
+    measures kappa per bin when the store is built and steps a store with a bin beyond the limit in the reference's
+    operation order (C/ChiSquare.c:188-210).  Whatever it picks, the sampler's log-probabilities are within 1e-12."""
+    from mimic_mda_b200.ensemble import DeviceEnsemble
+    consts, n_pts, a_true = synth.make_bins(6, 9, 60, rel_err=rel, ragged=True)
+    lo, hi = synth.default_bounds(9)
+    store = chisq.DeviceStore(consts, n_pts, (lo, hi), cs_lib=cs_lib)
+    kappa, limit, safe = store.conditioning()
+    assert kappa.shape == (6,) and np.all(kappa > 0.5 / rel) and np.all(kappa < 3.0 / rel)
+    assert safe == bool(np.all(kappa <= limit)) and safe == (rel >= 1e-2)
+    ens = DeviceEnsemble(store, 256, seed=5)
+    text = ens.describe(24)
+    if safe:
+        assert text.startswith(("ensemble_qws_kernel", "ensemble_quad_kernel")), text
+    else:
+        assert text.startswith("ensemble_kernel") and "reference-order stepper" in text, text
+    ens.run_mcmc(synth.make_walkers(a_true, 256, seed=1, scatter=0.04 * rel, oob_frac=0.0), 24, thin=4)
+    chain, lnp = ens.chain, ens.lnprobability
+    for k in range(chain.shape[2]):
+        want = oracle_lib.lnpost_bins(consts, n_pts, lo, hi, np.ascontiguousarray(chain[:, :, k]))
+        assert rel_err(lnp[:, :, k], want) <= TOL, (rel, rel_err(lnp[:, :, k], want))
+    assert 0.05 < ens.acceptance_fraction.mean() < 0.9
+    ens.close()
+    store.close()
+
+
+def test_one_ill_conditioned_bin_routes_the_store(cs_lib):
+    consts, n_pts, a_true = synth.make_bins(4, 5, 30)
+    bad, _, _ = synth.make_bins(1, 5, 30, rel_err=1e-4, seed_base=77)
+    store = chisq.DeviceStore(consts, n_pts, synth.default_bounds(5), cs_lib=cs_lib)
+    assert store.conditioning()[2]
+    consts[2] = bad[0]
+    mixed = chisq.DeviceStore(consts, n_pts, synth.default_bounds(5), cs_lib=cs_lib)
+    kappa, limit, safe = mixed.conditioning()
+    assert not safe and int(np.argmax(kappa)) == 2 and np.sum(kappa > limit) == 1
+    store.close()
+    mixed.close()

@@ -1,7 +1,9 @@
 """Run a reference configuration file end to end on the GPU(s).
 
-    python -m mimic_mda_b200.run config.py [--seed N] [--out results.json]
-    torchrun --nproc-per-node G -m mimic_mda_b200.run config.py      # bins round-robin over G GPUs
+    python tools/run_config.py config.py [--seed N] [--out results.json]
+    torchrun --nproc-per-node G tools/run_config.py config.py      # bins round-robin over G GPUs
+
+A convenience driver, outside the hot-path scope and therefore not part of the package.
 
 ``config.py`` is the reference's configuration format: a Python file that fills a ``CONFIG``
 dictionary (mda.py:50-53, config_example.py).  The keys on the likelihood path are honoured
@@ -15,9 +17,12 @@ import argparse
 import json
 import sys
 
+import os
+
 import numpy as np
 
-from . import builder, fits, pipeline, shard
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mimic_mda_b200 import builder, chisq, fits, pipeline, shard  # noqa: E402
 
 
 def load_config(path):
@@ -44,7 +49,6 @@ def main(argv=None):
     mine = shard.bins_for_rank(n_bins, rank, world)
     n_l = config["Maximum L"] + 1
     starts = fits.calc_start_params([config["Start Pts a%d" % i] for i in range(n_l)])
-    from . import chisq
     store = chisq.DeviceStore(inputs["consts"][mine], inputs["n_pts"][mine], inputs["bounds"])
     results, ens = pipeline.fit_and_mcmc_all(store, starts, config, ewsr=config["EWSR Fractions"][:n_l], seed=args.seed,
                                              bin_ids=mine, rng=np.random.RandomState(args.seed + 7919 * rank), thin=args.thin,
