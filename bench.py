@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the 200-bins-total strong-scaling companion run")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C5-corner companion measurements")
     return ap.parse_args()
 
 
@@ -252,7 +253,8 @@ def run_reference_impl(args, cfg, rank, world):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * evals_step / base["value"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(cfg, world, "reference CPU path on host cores; bounded sample, see cpu_baseline.sample"),
+        "config": workload_config(cfg, world),
+        "note": "reference CPU path on host cores; bounded sample, see cpu_baseline.sample",
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -260,7 +262,8 @@ def run_reference_impl(args, cfg, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(cfg, world, note):
+def workload_config(cfg, world):
+    """Identical in both arms (the driver compares them); what an arm does with it goes into the line's "note"."""
     return {
         "workload": "%s: %d Ex bins/GPU x %d walkers x %d dists x %d angles (BASELINE.json configs[%s])"
                     % (cfg.get("name", "C4"), cfg["bins"], cfg["walkers"], cfg["n_l"], cfg["n_pts"],
@@ -270,7 +273,6 @@ def workload_config(cfg, world, note):
         "launches_per_step": 2, "partition": "bins round-robin over ranks, no collective",
         "l2_policy": "sampler: state lives in shared memory, chain streams out (nothing to re-read); "
                      "batched_half_step: ring of distinct parameter blocks > 2x126 MB",
-        "note": note,
     }
 
 
@@ -471,7 +473,187 @@ class GpuWorkload:
         self.store.close()
 
 
-def measure_sampler(work, dist, steps, warmup, e2e_cap=192):
+def pinned_block(lib, chisq, shape, keep):
+    n = int(np.prod(shape))
+    ptr = lib.mdaHostAlloc(max(n, 1) * 8)
+    if not ptr:
+        raise chisq.MdaError(lib.mdaLastError(), lib.mdaLastErrorString().decode())
+    keep.append(ptr)
+    return np.frombuffer((ct.c_double * max(n, 1)).from_address(ptr), dtype=np.float64, count=n).reshape(shape)
+
+
+def pcie_peaks(lib, chisq, mbytes=64):
+    """Measured roof of the e2e paths: one cudaMemcpy of `mbytes` MB between pinned host memory and HBM, each way
+    (best of 4, wall clock around the synchronous copy)."""
+    n = mbytes << 20
+    keep = []
+    host = pinned_block(lib, chisq, (n // 8,), keep)
+    host[...] = 1.0
+    dev = lib.mdaDeviceAlloc(n)
+    out = {}
+    for name, fn, a, b in (("d2h_gbs", lib.mdaMemcpyD2H, host.ctypes.data, dev), ("h2d_gbs", lib.mdaMemcpyH2D, dev, host.ctypes.data)):
+        chisq.check(lib, fn(a, b, n))
+        best = 1e30
+        for _ in range(4):
+            t0 = time.perf_counter()
+            chisq.check(lib, fn(a, b, n))
+            best = min(best, time.perf_counter() - t0)
+        out[name] = n / best / 1e9
+    lib.mdaDeviceFree(dev)
+    lib.mdaHostFree(keep[0])
+    out["how"] = "one cudaMemcpy of %d MB, pinned host <-> HBM, best of 4" % mbytes
+    return out
+
+
+def scalar_call_latency(lib, chisq, calls=300):
+    """The seven-symbol path: microseconds per calculateLnLiklihood call through ctypes (a launch + a sync each), next
+    to the same call on the CPU library the reference ships (oracle/_ref, or the oracle port when that did not travel)."""
+    from oracle import reflib
+    consts, n_pts, a_true = synth.make_bins(1, 9, 60)
+    data, dists, a = consts[0, 0, :60], [consts[0, 1 + l, :60] for l in range(9)], np.ascontiguousarray(a_true[0])
+    out = {}
+    cpu_path = reflib.reference_lib_path() or reflib.ORACLE_LIB
+    for name, handle, mod in (("gpu_us", lib, chisq), ("cpu_us", reflib.prepare_shared_object(cpu_path), reflib)):
+        st = mod.make_calc_struct(handle, data, dists)
+        ptr = a.ctypes.data_as(ct.POINTER(ct.c_double))
+        for _ in range(20):
+            handle.calculateLnLiklihood(st, ptr)
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            handle.calculateLnLiklihood(st, ptr)
+        out[name] = (time.perf_counter() - t0) / calls * 1e6
+        handle.freeMdaStruct(st)
+    out["what"] = ("calculateLnLiklihood(L=9, N=60) per call through ctypes: the GPU library pays a kernel launch and a stream sync "
+                   "per call, so unmodified mda.py pointed at it is slower per call than the CPU library -- the batched entry points exist for that")
+    return out
+
+
+def batched_point(lib, chisq, orc, bins, walkers, n_l, n_pts, launches, peak_tf, hbm_peak):
+    """The batched likelihood kernel at one shape: ring of distinct parameter blocks larger than 2 x L2 (at least two),
+    CUDA events around `launches` launches; roofline per SURVEY.md 8d; parity of a sample against the oracle."""
+    consts, counts, a_true = synth.make_bins(bins, n_l, n_pts)
+    lo, hi = synth.default_bounds(n_l)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=lib)
+    blk = synth.make_walkers(a_true, walkers, seed=3)
+    n_ring = max(2, 2 * L2_BYTES // blk.nbytes + 1)
+    dps, dos = [], []
+    rng = np.random.default_rng(5)
+    for i in range(n_ring):
+        dp, do = lib.mdaDeviceAlloc(blk.nbytes), lib.mdaDeviceAlloc(bins * walkers * 8)
+        src = blk if i < 2 else np.clip(blk + 1e-3 * rng.standard_normal((1, 1, n_l)), lo, hi)
+        chisq.check(lib, lib.mdaMemcpyH2D(dp, src.ctypes.data, blk.nbytes))
+        dps.append(dp)
+        dos.append(do)
+    ev0, ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
+    store.lnpost_device_many(walkers, dps, dos, max(3, min(launches, 2 * n_ring)))
+    store.synchronize()
+    lib.mdaEventRecord(ev0, store.handle)
+    store.lnpost_device_many(walkers, dps, dos, launches)
+    lib.mdaEventRecord(ev1, store.handle)
+    lib.mdaEventSynchronize(ev1)
+    ms = ct.c_float()
+    lib.mdaEventElapsedMs(ev0, ev1, ct.byref(ms))
+    sec = ms.value * 1e-3 / launches
+    # parity: block 0's results for the first bins / walkers against the oracle
+    got = np.empty((bins, walkers))
+    chisq.check(lib, lib.mdaMemcpyD2H(got.ctypes.data, dos[0], got.nbytes))
+    nb, nw = min(bins, 4), min(walkers, 256)
+    want = orc.lnpost_bins(consts[:nb], counts[:nb], lo, hi, np.ascontiguousarray(blk[:nb, :nw]))
+    fin = np.isfinite(want)
+    same_inf = bool(np.array_equal(np.isneginf(got[:nb, :nw]), np.isneginf(want)))
+    err = float(np.max(np.abs(got[:nb, :nw][fin] - want[fin]) / np.abs(want[fin])))
+    t, w, g = store.get_tile(walkers)
+    for ptr in dps + dos:
+        lib.mdaDeviceFree(ptr)
+    lib.mdaEventDestroy(ev0)
+    lib.mdaEventDestroy(ev1)
+    store.close()
+    flops = 2.0 * n_pts * (n_l + 1) * bins * walkers                      # SURVEY.md 8d
+    nbytes = 8.0 * (n_l + 1) * bins * (walkers + n_pts)
+    f64, fhbm = flops / sec / 1e12 / peak_tf, nbytes / sec / 1e9 / hbm_peak
+    kernel = ("lnpost_tile_kernel %dx%d" % (t, w) if w > 0 else ("lnpost_mma_kernel (fp64 DMMA)" if w == 0 else "lnpost_split_kernel G=%d" % -w))
+    return {"shape": "%d bins x %d walkers x %d dists x %d angles" % (bins, walkers, n_l, n_pts), "kernel": kernel + ", %d CTAs" % g,
+            "us_per_launch": sec * 1e6, "value": bins * walkers / sec, "unit": UNIT, "launches": launches, "ring_blocks": n_ring,
+            "roofline": {"bound": "fp64" if f64 >= fhbm else "hbm", "frac": max(f64, fhbm), "frac_fp64": f64, "frac_hbm": fhbm,
+                         "achieved": flops / sec / 1e12 if f64 >= fhbm else nbytes / sec / 1e9,
+                         "peak": peak_tf if f64 >= fhbm else hbm_peak, "unit": "TFLOP/s" if f64 >= fhbm else "GB/s"},
+            "parity_max_rel_err": err, "inf_positions_equal": same_inf}
+
+
+def sampler_point(lib, chisq, orc, name, steps, hbm_peak, e2e_steps=48):
+    """The device-resident sampler on another BASELINE config (one GPU's worth): resident value, e2e to pinned host
+    memory, the chain's HBM fraction, parity of the visited positions."""
+    from mimic_mda_b200.ensemble import DeviceEnsemble
+    cfg = synth.CONFIGS[name]
+    bins, walkers, n_l, n_pts = cfg["bins"], cfg["walkers"], cfg["n_l"], cfg["n_pts"]
+    consts, counts, a_true = synth.make_bins(bins, n_l, n_pts)
+    lo, hi = synth.default_bounds(n_l)
+    store = chisq.DeviceStore(consts, counts, (lo, hi), cs_lib=lib)
+    ens = DeviceEnsemble(store, walkers, seed=20261020)
+    p0 = synth.make_walkers(a_true, walkers, seed=7, oob_frac=0.0)
+    ens.set_state(p0)
+    thin = max(1, -(-steps // 2048))
+    ens.reserve_chain(steps // thin + 8)
+    ens.advance(8, thin)
+    ev0, ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
+    lib.mdaEventRecord(ev0, store.handle)
+    ens.advance(steps, thin, wait=False)
+    lib.mdaEventRecord(ev1, store.handle)
+    lib.mdaEventSynchronize(ev1)
+    ens.synchronize()
+    ms = ct.c_float()
+    lib.mdaEventElapsedMs(ev0, ev1, ct.byref(ms))
+    text = ens.describe(steps)
+    # parity on the last kept sample
+    chain = np.ascontiguousarray(ens.chain[:, :, -1, :])
+    want = orc.lnpost_bins(consts, counts, lo, hi, chain)
+    fin = np.isfinite(want)
+    err = float(np.max(np.abs(ens.lnprobability[:, :, -1][fin] - want[fin]) / np.abs(want[fin])))
+    # e2e: host start positions in, whole chain + log-probabilities out (pinned)
+    keep = []
+    e2e_steps = max(1, min(steps, e2e_steps))
+    h_p0 = pinned_block(lib, chisq, p0.shape, keep)
+    h_p0[...] = p0
+    h_chain = pinned_block(lib, chisq, (e2e_steps, bins, walkers, n_l), keep)
+    h_lnp = pinned_block(lib, chisq, (e2e_steps, bins, walkers), keep)
+    ens.set_state(h_p0)
+    ens.run_to_host(min(e2e_steps, 4), 1, 0, h_chain[:min(e2e_steps, 4)], h_lnp[:min(e2e_steps, 4)])
+    store.synchronize()
+    t0 = time.perf_counter()
+    ens.set_state(h_p0)
+    ens.run_to_host(e2e_steps, 1, 0, h_chain, h_lnp)
+    secs = time.perf_counter() - t0
+    ens.close()
+    for ptr in keep:
+        lib.mdaHostFree(ptr)
+    lib.mdaEventDestroy(ev0)
+    lib.mdaEventDestroy(ev1)
+    store.close()
+    sec = ms.value * 1e-3
+    chain_bytes = 8.0 * (n_l + 1) * bins * walkers * (steps // thin)
+    return {"shape": "%s: %d bins x %d walkers x %d dists x %d angles" % (name, bins, walkers, n_l, n_pts), "kernel": text.split(":")[0],
+            "value": bins * walkers * steps / sec, "unit": UNIT, "steps": steps, "ms_per_step": ms.value / steps,
+            "roofline": {"bound": "hbm", "frac": chain_bytes / sec / 1e9 / hbm_peak, "achieved": chain_bytes / sec / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "what": "the chain going out, 8 (L+1) bytes per evaluation kept (thin %d)" % thin},
+            "e2e": {"value": bins * walkers * e2e_steps / secs, "unit": UNIT, "steps": e2e_steps,
+                    "d2h_bytes_per_step": bins * walkers * (n_l + 1) * 8, "pcie_gbs": bins * walkers * (n_l + 1) * 8 * e2e_steps / secs / 1e9},
+            "parity_max_rel_err": err}
+
+
+def other_configs(lib, chisq, orc, steps, peak_tf, hbm_peak):
+    """BASELINE.json's other configs in the driver's record: C2 and C3 (sampler resident + e2e, batched half-step) and four
+    corners of the C5 sweep of the batched kernel at 200 bins x 8192 walkers."""
+    out = {}
+    for name in ("C2", "C3"):
+        cfg = synth.CONFIGS[name]
+        out[name] = {"sampler": sampler_point(lib, chisq, orc, name, steps, hbm_peak),
+                     "batched_half_step": batched_point(lib, chisq, orc, cfg["bins"], cfg["walkers"] // 2, cfg["n_l"], cfg["n_pts"], 200, peak_tf, hbm_peak)}
+    out["C5_batched_200x8192"] = [batched_point(lib, chisq, orc, 200, 8192, l, n, 12, peak_tf, hbm_peak)
+                                  for (l, n) in ((4, 16), (5, 30), (9, 60), (12, 256))]
+    return out
+
+
+def measure_sampler(work, dist, steps, warmup, e2e_steps=192):
     """Device-resident sampler: resident (events) and host-buffer e2e (wall), max over ranks."""
     work.store.synchronize()
     dist.barrier()
@@ -479,7 +661,9 @@ def measure_sampler(work, dist, steps, warmup, e2e_cap=192):
     work.store.synchronize()
     dist.barrier()
     ms = dist.max(ms)
-    e2e_steps = max(1, min(steps, e2e_cap))
+    # The e2e run is always 192 steps (1.6 GB of chain per GPU at C4), whatever K is: one run_mcmc call of the reference is
+    # 16 385 steps (mda_config0.py:103), so the per-call costs (start positions H2D, first log-probabilities, a pass over p0)
+    # belong to a run, not to a step; at K = 20 they would be a quarter of a 4 ms region.
     host_p0 = work.pinned_array(work.p0.shape)
     host_p0[...] = work.p0
     host_chain = work.pinned_array((e2e_steps, work.bins, work.walkers, work.n_l))
@@ -491,7 +675,7 @@ def measure_sampler(work, dist, steps, warmup, e2e_cap=192):
     secs = dist.max(secs)
     work.sampler_summary_e2e(min(e2e_steps, 16), host_p0)                     # warm-up
     dist.barrier()
-    sum_steps = max(4, min(steps, 1024))
+    sum_steps = 1024                                        # a fixed-length run, like e2e above (8.4 GB of chain in HBM at C4)
     sum_secs = []
     for _ in range(2):                                      # wall clock of a ~15 ms region: a host hiccup (seen once: 650 ms) is not the path
         secs_i, _ = work.sampler_summary_e2e(sum_steps, host_p0)
@@ -618,6 +802,9 @@ def main():
             "peak": peak_tf.value if by_flops else hbm_peak,
             "unit": "TFLOP/s" if by_flops else "GB/s",
             "frac": f64 if by_flops else fhbm, "traffic": traffic_of(traffic_key),
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture named in profiles/traffic.json, "
+                              "per step x this launch's steps for the sampler (a capture of another launch length, scaled -- not a "
+                              "measurement of the timed launch)",
             "kernel": kernel, "launch_us": seconds_per_launch * 1e6,
             "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
             "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf.value, "frac": f64,
@@ -686,20 +873,39 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_arm(cfg, args.cpu_seconds, work.consts, work.n_pts, work.params)
+    # rank 0's GPU only (the other ranks wait at the closing barrier): the copy roofs of the e2e paths, the scalar-call
+    # latency, and BASELINE.json's other configs
+    pcie = scalar = configs = None
+    if rank == 0:
+        pcie = pcie_peaks(lib, chisq)
+        scalar = scalar_call_latency(lib, chisq)
+        if not args.no_configs:
+            configs = other_configs(lib, chisq, orc, args.steps, peak_tf.value, hbm_peak)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": s_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(cfg, world, "device-resident stretch-move sampler: proposal, box prior, fp64 chi-square "
-                                      "log-likelihood and accept/reject in one persistent kernel; chain kept in HBM (thin %d)" % s_thin),
+            "config": workload_config(cfg, world),
+            "note": "device-resident stretch-move sampler: proposal, box prior, fp64 chi-square log-likelihood and accept/reject in "
+                    "one persistent kernel; chain kept in HBM (thin %d).  scaling = weak: every GPU owns %d bins; the literal "
+                    "200-bins-in-total split of BASELINE configs[3] is value_strong / e2e_strong" % (s_thin, cfg["bins"]),
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": s_e2e_steps,
                     "h2d_bytes_per_step": bins * cfg["walkers"] * n_l * 8 // s_e2e_steps,
                     "d2h_bytes_per_step": bins * cfg["walkers"] * (n_l + 1) * 8,
                     "ensemble_steps_per_s": s_e2e_steps / s_secs,
+                    # the roof of this path is the host link: bytes delivered per second against one big pinned copy
+                    "pcie_gbs": world * bins * cfg["walkers"] * (n_l + 1) * 8 * s_e2e_steps / s_secs / 1e9,
+                    "pcie_gbs_per_gpu": bins * cfg["walkers"] * (n_l + 1) * 8 * s_e2e_steps / s_secs / 1e9,
+                    "d2h_peak_gbs": pcie["d2h_gbs"], "h2d_peak_gbs": pcie["h2d_gbs"], "peak_how": pcie["how"] + " (rank 0's GPU alone)",
+                    "frac_of_d2h_peak": bins * cfg["walkers"] * (n_l + 1) * 8 * s_e2e_steps / s_secs / 1e9 / pcie["d2h_gbs"],
+                    "limit": "PCIe: 8 (L+1) = %d bytes per evaluation cross the host link (Save Chain Data, mda.py:1244-1250: the reference "
+                             "keeps the whole chain on the host)%s" % (8 * (n_l + 1), "" if world == 1 else
+                             "; with several GPUs the VM's host bridge is shared -- frac_of_d2h_peak is per GPU against a lone GPU's copy rate"),
                     "path": "mdaEnsembleSetState(pinned host p0) + mdaEnsembleRunToHost: full chain + lnprob delivered to pinned "
-                            "host memory, chunked D2H overlapped with stepping (PCIe bound: 80 B per evaluation)"},
+                            "host memory, chunked D2H overlapped with stepping (PCIe bound: 80 B per evaluation); one call of "
+                            "%d steps whatever --steps is (a run_mcmc call of the reference is 16 385 steps)" % s_e2e_steps},
             "e2e_summaries": {"value": evals_step * work.summary_e2e[1] / work.summary_e2e[0], "unit": UNIT,
                               "steps": work.summary_e2e[1], "seconds": work.summary_e2e[0],
                               "h2d_bytes": bins * cfg["walkers"] * n_l * 8, "d2h_bytes": bins * (n_l * 6 + 1) * 8,
@@ -711,11 +917,15 @@ def main():
             "gpu_launches_total_in_run": int(total_launches),
             "ensemble_steps_per_s": args.steps / (s_ms * 1e-3),
             "roofline": roofline, "direct_evaluation": direct, "batched_half_step": batched, "cpu_baseline": cpu, "clocks": clocks,
+            "scalar_call_us": scalar, "configs": configs,
             "parity_max_rel_err": worst,
             "device": {"name": name.value.decode(), "sms": sms.value, "cc": cc.value},
         }
-        if strong is not None:
+        if strong is not None:                     # BASELINE configs[3] read literally, first class: 200 bins in total over the GPUs
             line["strong_200_bins_total"] = strong
+            line["value_strong"] = strong["value"]
+            line["e2e_strong"] = strong["e2e"]
+            line["scaling_strong"] = "strong: %d bins in total, %d per GPU" % (strong["bins_total"], strong["bins_per_gpu"])
         print(json.dumps(line))
     work.close()
     dist.close()

@@ -108,6 +108,9 @@ MDA_API void  mdaDeviceFree(void *p);
 MDA_API int   mdaMemcpyH2D(void *dst, const void *src, size_t bytes);
 MDA_API int   mdaMemcpyD2H(void *dst, const void *src, size_t bytes);
 MDA_API int   mdaDeviceSynchronize(void);
+/* Free and total HBM of the selected device: callers size groups of bins (chains are numWalkers x kept x (numL + 1)
+ * doubles per bin) from it. */
+MDA_API int   mdaDeviceMemInfo(size_t *freeBytes, size_t *totalBytes);
 
 /* ------------------------------------------------------------------------
  * 4. Device-resident multi-bin store (B Ex bins, uniform numL, ragged numPts)
@@ -141,10 +144,13 @@ MDA_API int   mdaStoreMaxPts(void *store);
 /* Force the kernel tiling (threads per CTA in {32,64,128,256}, walkers per
  * thread in {1,2,4}); 0,0 restores the built-in heuristic. */
 MDA_API int   mdaStoreSetTile(void *store, int threads, int walkersPerThread);
-/* Reports the tiling the next call with walkersPerBin walkers would use.  walkersPerThread = 0: the
+/* Reports the tiling the next call with walkersPerBin walkers would use.  walkersPerThread = -G: the angle-split
+ * kernel (lnpost_split_kernel: 256 threads, G lanes per walker, chi^2 handed from lane to lane in the reference's
+ * order; opt-in with MDA_BATCH_IMPL = split -- measured slower than the default).  walkersPerThread = 0: the
  * DMMA kernel (lnpost_mma_kernel: 128 threads, one warp per item of 32 walkers), the default for
  * numL 4 .. 16 with more than 88 angles; a forced tiling selects the register-tiled DFMA kernel,
- * MDA_BATCH_IMPL = mma | dfma either one. */
+ * MDA_BATCH_IMPL = split | mma | dfma any one.  The split and register-tiled kernels are bit-identical to each other
+ * (the reference's operation order); the DMMA kernel sums a residual's terms in tensor-fragment order (<= 1e-14). */
 MDA_API int   mdaStoreGetTile(void *store, int walkersPerBin, int *threads, int *walkersPerThread, int *gridSize);
 
 /* ------------------------------------------------------------------------

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libChiSq.so")
-SOURCES = ["chisq_abi.cu", "lnpost_kernel.cu", "lnpost_mma_kernel.cu", "lnpost_quad_kernel.cu", "ensemble_kernel.cu", "ensemble_mma_kernel.cu", "ensemble_ws_kernel.cu", "ensemble_quad_kernel.cu", "ensemble_qws_kernel.cu", "fit_kernel.cu", "summary_kernel.cu", "autocorr_kernel.cu", "scalar_kernel.cu", "peaks.cu"]
+SOURCES = ["chisq_abi.cu", "lnpost_kernel.cu", "lnpost_mma_kernel.cu", "lnpost_quad_kernel.cu", "lnpost_split_kernel.cu", "ensemble_kernel.cu", "ensemble_mma_kernel.cu", "ensemble_ws_kernel.cu", "ensemble_quad_kernel.cu", "ensemble_qws_kernel.cu", "fit_kernel.cu", "summary_kernel.cu", "autocorr_kernel.cu", "scalar_kernel.cu", "peaks.cu"]
 HEADERS = [os.path.join(CSRC, "mda_kernels.cuh"), os.path.join(CSRC, "likelihood.cuh"), os.path.join(CSRC, "philox.cuh"), os.path.join(CSRC, "mma_chi.cuh"), os.path.join(CSRC, "quad_chi.cuh"),
            os.path.join(HERE, "..", "include", "mda_chisq.h")]
 

@@ -86,6 +86,7 @@ def prepare_shared_object(path=None):
         "mdaStoreSetBinFromStruct": (ct.c_int, [_VP, ct.c_int, _VP]),
         "mdaStoreSetBounds": (ct.c_int, [_VP, _DP, _DP]),
         "mdaStoreUpload": (ct.c_int, [_VP]),
+        "mdaDeviceMemInfo": (ct.c_int, [ct.POINTER(ct.c_size_t), ct.POINTER(ct.c_size_t)]),
         "mdaStoreConditioning": (ct.c_int, [_VP, _DP, _DP, ct.POINTER(ct.c_int)]),
         "mdaStoreNumBins": (ct.c_int, [_VP]),
         "mdaStoreNumL": (ct.c_int, [_VP]),

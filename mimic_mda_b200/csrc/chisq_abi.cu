@@ -392,6 +392,19 @@ bool use_batch_mma(const MdaStore *s) {
     return s->n_tiles >= 12;
 }
 
+// The angle-split kernel (G lanes per walker, chi^2 handed from lane to lane in the reference's order: the same bits as
+// the tile kernel, a G-th of the latency chain) was built for launches too small to give every SM a few hundred walkers --
+// the half-step of a host-driven sampler on BASELINE.json's shapes.  Measured, it loses at every size (C4 half-step
+// 14.4 us against 8.3; profiles/experiments/r02_split_kernel.md): G times the threads means several waves of CTAs, each
+// paying the ~2 us staging latency again, while the tile kernel's launch is already within ~4 us of an EMPTY launch
+// (4.2 us per launch through this path).  Kept selectable: MDA_BATCH_IMPL = split.
+bool use_batch_split(const MdaStore *s, int) {
+    if (s->force_threads > 0 || s->force_wpt > 0) return false;
+    if (!lnpost_split_lanes(s->n_l, s->n_pad)) return false;
+    const char *impl = getenv("MDA_BATCH_IMPL");
+    return impl && strcmp(impl, "split") == 0;
+}
+
 // Enqueue one evaluation of device-resident params on the store's stream.
 int enqueue_eval(MdaStore *s, int walkers, const double *d_params, double *d_out, int mode) {
     BatchArgs args;
@@ -411,6 +424,11 @@ int enqueue_eval(MdaStore *s, int walkers, const double *d_params, double *d_out
     if (batch_impl && strcmp(batch_impl, "quad") == 0 && lnpost_quad_supported(s->n_l) && s->force_threads == 0 && s->force_wpt == 0) {
         args.quad = s->d_quad;
         MDA_CUDA(launch_batch_quad(args, s->stream), "batched likelihood launch (triangular factor)");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return MDA_OK;
+    }
+    if (use_batch_split(s, walkers)) {
+        MDA_CUDA(launch_batch_split(args, s->stream, nullptr), "batched likelihood launch (angle-split)");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return MDA_OK;
     }
@@ -655,6 +673,18 @@ int qws_grid(const MdaStore *s, const EnsembleShape &shape) {
     if (force_grid > 0) grid = std::max(1, std::min(force_grid, grid));
     return grid;
 }
+
+// MDA_E2E_TIMING=1: wall-clock laps of the host-buffer calls on stderr (where a millisecond-long e2e region goes)
+struct LapTimer {
+    bool on = getenv("MDA_E2E_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mda e2e] %-40s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 MdaEnsemble *as_ensemble(void *p, const char *fn) {
     MdaEnsemble *e = static_cast<MdaEnsemble *>(p);
@@ -909,6 +939,16 @@ int mdaStoreUpload(void *store) {
     return upload_store(s);
 }
 
+int mdaDeviceMemInfo(size_t *freeBytes, size_t *totalBytes) {
+    int rc = ensure_runtime();
+    if (rc) return rc;
+    size_t f = 0, t = 0;
+    MDA_CUDA(cudaMemGetInfo(&f, &t), "mdaDeviceMemInfo");
+    if (freeBytes) *freeBytes = f;
+    if (totalBytes) *totalBytes = t;
+    return MDA_OK;
+}
+
 int mdaStoreConditioning(void *store, double *kappa, double *kappaMax, int *quadSafe) {
     MdaStore *s = as_store(store, "mdaStoreConditioning");
     if (!s) return MDA_ERR_BAD_ARGUMENT;
@@ -941,6 +981,13 @@ int mdaStoreGetTile(void *store, int walkersPerBin, int *threads, int *walkersPe
     if (!s) return MDA_ERR_BAD_ARGUMENT;
     int rc = ensure_runtime();
     if (rc) return rc;
+    if (use_batch_split(s, walkersPerBin > 0 ? walkersPerBin : 1)) {   // the angle-split kernel: 256 threads, G lanes per walker -> reported as -G
+        const int g = lnpost_split_lanes(s->n_l, s->n_pad), wpc = 256 / g;
+        if (threads) *threads = 256;
+        if (walkersPerThread) *walkersPerThread = -g;
+        if (gridSize) *gridSize = s->bins * (((walkersPerBin > 0 ? walkersPerBin : 1) + wpc - 1) / wpc);
+        return MDA_OK;
+    }
     if (use_batch_mma(s)) {                            // the DMMA kernel: 128 threads, a warp per 32 walkers -> reported as 0 walkers per thread
         const long n_items = ((walkersPerBin > 0 ? walkersPerBin : 1) + 31) / 32, total = n_items * s->bins;
         long passes = (total + 4 * 8L * g_rt.sm_count - 1) / (4 * 8L * g_rt.sm_count);
@@ -1153,17 +1200,40 @@ int mdaEnsembleSetState(void *ens, const double *p0) {
     if (!p0) return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSetState: p0 is NULL");
     MdaStore *s = e->store;
     const size_t n_eval = (size_t)s->bins * (size_t)e->walkers;
-    for (size_t i = 0; i < n_eval * (size_t)s->n_l; ++i)
-        if (!std::isfinite(p0[i]))
-            return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSetState: at least one parameter value was %s", std::isnan(p0[i]) ? "NaN" : "infinite");
+    LapTimer laps;
     int rc = ensure_runtime();
     if (rc) return rc;
     if ((rc = upload_store(s))) return rc;
+    laps.lap("SetState: store upload (if dirty)");
+    e->has_state = false;                                  // until everything below has succeeded
     MDA_CUDA(cudaMemcpyAsync(e->d_pos, p0, sizeof(double) * n_eval * s->n_l, cudaMemcpyHostToDevice, s->stream), "ensemble p0 H2D");
     MDA_CUDA(cudaMemsetAsync(e->d_nacc, 0, sizeof(unsigned int) * n_eval, s->stream), "ensemble counters");
     MDA_CUDA(cudaMemsetAsync(e->d_status, 0, sizeof(int), s->stream), "ensemble status");
     if (n_eval && (rc = enqueue_eval(s, e->walkers, e->d_pos, e->d_lnp, kLnPost))) return rc;
+    // While the copy and the first log-probabilities are under way: every start position must be finite (emcee raises on
+    // NaN / inf positions).  x * 0 is 0 for finite x and NaN otherwise -- one vectorisable pass over the block instead of a
+    // million classified compares (this call is inside the e2e region; the pass is a read of pinned memory).
+    bool finite = true;
+    {
+        const size_t count = n_eval * (size_t)s->n_l;
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        size_t i = 0;
+        for (; i + 8 <= count; i += 8)
+            for (int k = 0; k < 8; ++k) acc[k] += p0[i + k] * 0.0;
+        for (; i < count; ++i) acc[0] += p0[i] * 0.0;
+        double total = 0.0;
+        for (int k = 0; k < 8; ++k) total += acc[k];
+        finite = total == 0.0;
+    }
+    laps.lap("SetState: finiteness of p0 (under the H2D copy)");
     MDA_CUDA(cudaStreamSynchronize(s->stream), "mdaEnsembleSetState");
+    laps.lap("SetState: p0 H2D + log-probabilities");
+    if (!finite) {
+        const size_t count = n_eval * (size_t)s->n_l;
+        for (size_t i = 0; i < count; ++i)
+            if (!std::isfinite(p0[i]))
+                return set_error(MDA_ERR_BAD_ARGUMENT, "mdaEnsembleSetState: at least one parameter value was %s", std::isnan(p0[i]) ? "NaN" : "infinite");
+    }
     if (e->state_generation != 0) ++e->epoch;             // a restart on the same ensemble draws from a fresh stream
     e->state_generation = s->generation;
     e->steps = 0;
@@ -1435,7 +1505,9 @@ int mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double
     }
     chunkSteps = std::max(thin, chunkSteps / thin * thin);
     const long long chunk_keep = chunkSteps / thin, total_keep = nSteps / thin;
+    LapTimer laps;
     if ((rc = mdaEnsembleReserveChain(ens, 2 * chunk_keep))) return rc;
+    laps.lap("RunToHost: chain ring reservation");
     if (!e->copy_stream) {
         MDA_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking), "copy stream");
         for (int i = 0; i < 2; ++i) {
@@ -1468,9 +1540,13 @@ int mdaEnsembleRunToHost(void *ens, int nSteps, int thin, int chunkSteps, double
         done_keep += keeps;
         remaining -= steps;
     }
+    laps.lap("RunToHost: launches and copies enqueued");
     MDA_CUDA(cudaStreamSynchronize(e->copy_stream), "mdaEnsembleRunToHost (copies)");
+    laps.lap("RunToHost: copies drained");
     e->kept = 0;                                                     // the device chain was only a staging ring
-    return mdaEnsembleSynchronize(ens);
+    rc = mdaEnsembleSynchronize(ens);
+    laps.lap("RunToHost: final synchronise");
+    return rc;
 }
 
 namespace {

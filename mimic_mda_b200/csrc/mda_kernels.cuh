@@ -61,6 +61,11 @@ bool lnpost_mma_supported(int n_l, int n_tiles, size_t smem_optin);
 cudaError_t configure_lnpost_mma_kernels(size_t smem_optin);
 cudaError_t launch_batch_mma(BatchArgs &args, int sm_count, cudaStream_t stream, int *grid_out, int *threads_out);
 
+// The same evaluation with G lanes per walker for small launches (lnpost_split_kernel.cu): residuals of a lane's run of
+// angles in parallel, chi^2 handed from lane to lane in the reference's order -- bit-identical to the tile kernel.
+int lnpost_split_lanes(int n_l, int n_pad);                    // G (2 .. 32), or 0 when the shape is not served
+cudaError_t launch_batch_split(BatchArgs &args, cudaStream_t stream, int *grid_out);
+
 // The same evaluation from the bins' triangular factors (lnpost_quad_kernel.cu), numL <= kMaxRegL, args.quad set.
 bool lnpost_quad_supported(int n_l);
 cudaError_t launch_batch_quad(const BatchArgs &args, cudaStream_t stream);

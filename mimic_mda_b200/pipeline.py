@@ -90,3 +90,52 @@ def fit_and_mcmc_all(store, start_params, config, ewsr=None, seed=0, bin_ids=Non
         acor_time = [] if acor is None else acor[b].copy()
         results.append((values, (acor_time, (float(chis[b, 0]), float(chis[b, 1])), float(summ["acceptance_fraction"][b]))))
     return results, ens
+
+
+def chain_bytes_per_bin(config, n_l, thin=1):
+    """HBM a bin's kept chain and log-probabilities take (plus its state): what limits how many bins run at once."""
+    cfg = dict(DEFAULTS)
+    cfg.update(config)
+    kept = cfg["Sample Points"] // thin
+    return 8 * cfg["Number of Walkers"] * (n_l + 1) * (kept + 2)
+
+
+def bins_per_group(config, n_l, n_bins, thin=1, free_bytes=None, cs_lib=None, headroom=0.6):
+    """How many bins' chains fit the device at once: ``headroom`` of the free HBM (the posterior reductions need
+    scratch of the order of a histogram per bin and parameter, the chain itself is the bulk).  The reference's own
+    defaults (mda_config0.py: 2500 walkers x 16385 samples x 8 parameters) are 2.95 GB per bin -- its full energy
+    range, ~116 bins, does not fit one 180 GB part at once, so bins are worked through in groups."""
+    if free_bytes is None:
+        import ctypes as ct
+        from . import chisq
+        lib = chisq.prepare_shared_object() if cs_lib is None else cs_lib
+        free, total = ct.c_size_t(), ct.c_size_t()
+        chisq.check(lib, lib.mdaDeviceMemInfo(ct.byref(free), ct.byref(total)), "mdaDeviceMemInfo")
+        free_bytes = free.value
+    per_bin = chain_bytes_per_bin(config, n_l, thin)
+    return int(max(1, min(n_bins, (headroom * free_bytes) // per_bin)))
+
+
+def fit_and_mcmc_grouped(consts, n_pts, bounds, start_params, config, ewsr=None, seed=0, bin_ids=None, rng=None, thin=1,
+                         energies=None, group_size=None, cs_lib=None):
+    """``fit_and_mcmc_all`` over groups of bins sized to the device's free memory (``group_size`` bins at a time;
+    default: ``bins_per_group``).  Every group gets its own store and ensemble, closed before the next one starts; chain
+    files ("Save Chain Data") are written per group.  Results do not depend on the grouping: the sampler's random
+    streams are keyed by the global bin index and the walker-start draws are made bin by bin in order."""
+    from . import chisq
+    consts = np.asarray(consts)
+    n_bins, n_l = consts.shape[0], consts.shape[1] - 1
+    bin_ids = np.arange(n_bins) if bin_ids is None else np.asarray(bin_ids)
+    rng = np.random.RandomState(seed) if rng is None else rng
+    if group_size is None:
+        group_size = bins_per_group(config, n_l, n_bins, thin, cs_lib=cs_lib)
+    results = []
+    for first in range(0, n_bins, group_size):
+        sel = slice(first, min(first + group_size, n_bins))
+        store = chisq.DeviceStore(consts[sel], np.asarray(n_pts)[sel], bounds, cs_lib=cs_lib)
+        part, ens = fit_and_mcmc_all(store, start_params, config, ewsr=ewsr, seed=seed, bin_ids=bin_ids[sel], rng=rng, thin=thin,
+                                     energies=None if energies is None else list(energies)[sel])
+        results.extend(part)
+        ens.close()
+        store.close()
+    return results

@@ -148,6 +148,38 @@ def test_every_tiling_is_bit_identical(cs_lib, oracle_lib, monkeypatch):
     store.close()
 
 
+@pytest.mark.parametrize("shape", [(3, 4, 18, 33), (2, 9, 60, 1), (5, 12, 256, 200), (2, 16, 24, 95), (1, 7, 41, 700),
+                                   (150, 5, 30, 128), (4, 8, 61, 77), (200, 9, 60, 256), (3, 1, 17, 40), (2, 3, 100, 64), (2, 8, 350, 9)])
+def test_angle_split_kernel_is_bit_identical_to_the_tile_kernel(cs_lib, oracle_lib, monkeypatch, shape):
+    """lnpost_split_kernel (G lanes per walker, MDA_BATCH_IMPL=split) hands chi^2 from lane to lane in the
+    reference's order: the same bits as the thread-per-walker kernel whatever the shape -- ragged and odd angle counts,
+    NaN and infinite parameters, chi^2 and log-posterior modes -- and within the oracle tolerance."""
+    n_bins, n_l, n_pts, walkers = shape
+    consts, n_pts_arr, a_true = synth.make_bins(n_bins, n_l, n_pts, ragged=n_pts > 8)
+    lo, hi = synth.default_bounds(n_l)
+    params = synth.make_walkers(a_true, walkers, seed=12)
+    if walkers > 4:
+        params[0, 1, 0] = np.nan
+        params[-1, 2, n_l - 1] = np.inf                    # chi^2 = inf, not NaN: pads are never multiplied
+        params[0, 3, 0] = -np.inf
+    store = chisq.DeviceStore(consts, n_pts_arr, (lo, hi), cs_lib=cs_lib)
+    monkeypatch.setenv("MDA_BATCH_IMPL", "split")
+    threads, wpt, grid = store.get_tile(walkers)
+    assert threads == 256 and wpt < 0 and (-wpt) & (-wpt - 1) == 0 and -wpt * 16 >= n_pts     # -G lanes per walker, 16 angles each
+    got_ln, got_chi = store.lnpost(params), store.chi(params)
+    monkeypatch.setenv("MDA_BATCH_IMPL", "dfma")
+    assert store.get_tile(walkers)[1] > 0
+    tile_ln, tile_chi = store.lnpost(params), store.chi(params)
+    np.testing.assert_array_equal(got_ln, tile_ln)
+    np.testing.assert_array_equal(got_chi, tile_chi)
+    want = oracle_lib.lnpost_bins(consts, n_pts_arr, lo, hi, params)
+    assert same_special(got_ln, want) and rel_err(got_ln, want) <= TOL
+    # it is opt-in: measured slower than the tile kernel at every size (profiles/experiments/r02_split_kernel.md)
+    monkeypatch.delenv("MDA_BATCH_IMPL")
+    assert store.get_tile(walkers)[1] >= 0
+    store.close()
+
+
 @pytest.mark.parametrize("shape", [(3, 4, 16, 33), (2, 9, 60, 1), (5, 12, 256, 200), (2, 16, 24, 95), (1, 7, 41, 8192),
                                    (150, 5, 30, 128), (4, 8, 60, 2500)])
 @pytest.mark.parametrize("mode", ["lnpost", "chi"])

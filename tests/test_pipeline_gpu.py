@@ -87,3 +87,28 @@ def test_config_driver_runs_a_reference_style_config(tmp_path, cs_lib):
     for row in table:
         assert 0.05 < row["acceptance_fraction"] < 0.95 and row["chi2_percentile"] > 0
         assert all(0.0 <= row["a%d" % l]["percentile"][0] <= 1.25 for l in range(4))
+
+
+def test_grouped_pipeline_equals_the_one_group_run(tmp_path, cs_lib):
+    """Bins worked through in groups sized to the free memory (the reference's own sizes are ~3 GB of chain per bin): the
+    results are those of all bins at once, because the random streams are keyed by the global bin index."""
+    cfg = _config(tmp_path)
+    cfg.update({"Number of Walkers": 32, "Sample Points": 60, "Burn-in Points": 10, "Number Walker Generators": 3, "Num Bins": 50})
+    inputs = builder.build_inputs(cfg)
+    starts = fits.calc_start_params([[0.05, 0.25], [0.05, 0.25], [0.05, 0.25], [0.05, 0.2]])
+    ewsr = cfg["EWSR Fractions"][:4]
+    whole = pipeline.fit_and_mcmc_grouped(inputs["consts"], inputs["n_pts"], inputs["bounds"], starts, cfg, ewsr=ewsr, seed=4,
+                                          rng=np.random.RandomState(9), group_size=100, cs_lib=cs_lib)
+    parts = pipeline.fit_and_mcmc_grouped(inputs["consts"], inputs["n_pts"], inputs["bounds"], starts, cfg, ewsr=ewsr, seed=4,
+                                          rng=np.random.RandomState(9), group_size=4, cs_lib=cs_lib)
+    assert len(whole) == len(parts) == len(inputs["energies"])
+    for a, b in zip(whole, parts):
+        np.testing.assert_array_equal(np.array(a[0][0]), np.array(b[0][0]))
+        np.testing.assert_array_equal(np.array(a[0][1]), np.array(b[0][1]))
+        assert a[1][1] == b[1][1] and a[1][2] == b[1][2]
+    # sizing: the reference's defaults are 2.95 GB per bin; a 180 GB part takes a few dozen at a time, never zero
+    per_bin = pipeline.chain_bytes_per_bin({}, 8)
+    assert 2.9e9 < per_bin < 3.0e9
+    assert pipeline.bins_per_group({}, 8, 116, free_bytes=170e9) == 34
+    assert pipeline.bins_per_group({}, 8, 116, free_bytes=1e9) == 1
+    assert 1 <= pipeline.bins_per_group(cfg, 4, 6, cs_lib=cs_lib) <= 6

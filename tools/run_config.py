@@ -38,6 +38,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default="")
     ap.add_argument("--thin", type=int, default=1)
+    ap.add_argument("--group-size", type=int, default=0, help="bins sampled at once (default: what the free HBM holds)")
     args = ap.parse_args(argv)
     config = load_config(args.config)
     rank, _, world = shard.rank_and_world()
@@ -49,12 +50,11 @@ def main(argv=None):
     mine = shard.bins_for_rank(n_bins, rank, world)
     n_l = config["Maximum L"] + 1
     starts = fits.calc_start_params([config["Start Pts a%d" % i] for i in range(n_l)])
-    store = chisq.DeviceStore(inputs["consts"][mine], inputs["n_pts"][mine], inputs["bounds"])
-    results, ens = pipeline.fit_and_mcmc_all(store, starts, config, ewsr=config["EWSR Fractions"][:n_l], seed=args.seed,
-                                             bin_ids=mine, rng=np.random.RandomState(args.seed + 7919 * rank), thin=args.thin,
-                                             energies=[inputs["energies"][b] for b in mine])
-    ens.close()
-    store.close()
+    # bins in groups sized to the free HBM: the reference's own sizes (2500 walkers x 16385 samples) are ~3 GB of chain per bin
+    results = pipeline.fit_and_mcmc_grouped(inputs["consts"][mine], inputs["n_pts"][mine], inputs["bounds"], starts, config,
+                                            ewsr=config["EWSR Fractions"][:n_l], seed=args.seed, bin_ids=mine,
+                                            rng=np.random.RandomState(args.seed + 7919 * rank), thin=args.thin,
+                                            energies=[inputs["energies"][b] for b in mine], group_size=args.group_size or None)
     merged = shard.gather_results(results, n_bins)
     if rank == 0:
         table = []

@@ -78,6 +78,9 @@ def main():
     elif args.shapes == "big":
         shapes = [(200, 8192, 9, 60), (200, 2048, 9, 60), (200, 8192, 12, 256), (200, 8192, 4, 16), (200, 8192, 5, 30),
                   (200, 8192, 8, 40)]
+    elif args.shapes == "cross":           # where the angle-split kernel stops paying: 200 bins, growing ensembles
+        shapes = [(200, w, 9, 60) for w in (64, 128, 256, 512, 1024, 2048, 4096)] + [(100, w, 5, 30) for w in (128, 512, 2048)] + \
+                 [(100, w, 12, 256) for w in (128, 512, 2048)]
     else:
         shapes = [(100, w, l, n) for w in (32, 128, 512, 2048, 8192) for n in (16, 64, 256) for l in (4, 8, 12)]
     tiles = [None]
