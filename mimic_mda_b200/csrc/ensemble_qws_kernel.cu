@@ -333,8 +333,10 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
         if (s_abort) break;
         const long long step_first = args.step0 + unit.s0;
         const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = 2u * (uint32_t)(args.step0 + unit.s1);
-        int until_keep = args.thin - (int)((uint64_t)step_first % (uint64_t)args.thin);
-        long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
+        // (step counters stay below 2^31 -- mdaEnsembleAdvance refuses more: 32-bit divisions, a tenth of the 64-bit ones' cost)
+        const uint32_t thin_u = (uint32_t)args.thin, first_u = (uint32_t)step_first;
+        int until_keep = args.thin - (int)(first_u % thin_u);
+        long long slot = args.keep0 + (long long)(first_u / thin_u - (uint32_t)args.step0 / thin_u);
         double *sPos = pos_of(buf), *sLnp = lnp_of(buf);
         for (uint32_t t = t_begin; t < t_end; ++t) {
             const uint32_t half = t & 1u;
@@ -358,8 +360,8 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
                     pending_release = -1;
                 }
                 if (kept_step) {
-                    if (args.groups >> 2) {              // (debug bits 2..: the store is issued this many hundreds of cycles after the barrier)
-                        const long long until = clock64() + 100ll * (args.groups >> 2);
+                    if (args.groups >> 3) {              // (debug bits 3..: the store is issued this many hundreds of cycles after the barrier)
+                        const long long until = clock64() + 100ll * (args.groups >> 3);
                         while (clock64() < until) __nanosleep(20);
                     }
                     double *dst = args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L;
@@ -537,8 +539,10 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         }
         const long long step_first = args.step0 + unit.s0;
         const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = 2u * (uint32_t)(args.step0 + unit.s1);
-        int until_keep = args.thin - (int)((uint64_t)step_first % (uint64_t)args.thin);
-        long long slot = args.keep0 + (step_first / args.thin - args.step0 / args.thin);
+        // (step counters stay below 2^31 -- mdaEnsembleAdvance refuses more: 32-bit divisions, a tenth of the 64-bit ones' cost)
+        const uint32_t thin_u = (uint32_t)args.thin, first_u = (uint32_t)step_first;
+        int until_keep = args.thin - (int)(first_u % thin_u);
+        long long slot = args.keep0 + (long long)(first_u / thin_u - (uint32_t)args.step0 / thin_u);
         unsigned int acc0 = 0u, acc1 = 0u;                   // proposals accepted in this piece, per walker of either half
         long long p_w[PROF ? 5 : 1] = {};
         if (ustamp) ustamp[2] = clock64();
@@ -562,13 +566,24 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
             long long w0 = 0;
             if constexpr (PROF) w0 = clock64();
             const uint32_t next_off = ring_off + ring_bytes == ring_span ? 0u : ring_off + ring_bytes;
+            // The partner rows: 256 random 72-byte rows are ~530 shared-memory wavefronts (3.7 per half-warp access: bank
+            // collisions of random rows), a burst that all eight walker warps would wait out together before they queue
+            // for the fp64 pipe together.  Skewed instead: warps 4..7 issue their loads only after warps 0..3 have issued
+            // theirs (the load queue of a scheduler is served in order), so each scheduler's first warp sums its chi^2 while
+            // the second one's rows arrive, and has the fp64 pipe to itself.
+            // (the lone-CTA build only, and only when whole warps own walkers -- H a multiple of 32 -- so that every lane of warps
+            // 0..3 arrives and every lane of the owning warps 4.. waits: the barrier's count is the H owning threads.  Debug bit 2
+            // switches it off.)
+            const bool skew = TREG && H > kWalkerThreads / 2 && (H & 31) == 0 && (args.groups & 4) == 0;
             if (owner) {
+                if (skew && tid >= kWalkerThreads / 2) asm volatile("bar.sync 3, %0;" ::"r"(H) : "memory");
                 const uint32_t crow = pos_a + (uint32_t)(c_base + ((args.groups & 1) ? me : (int)pf.x)) * (uint32_t)(L * 8);   // (debug bit 0: no gather conflicts)
-                const uint32_t xrow = pos_a + (uint32_t)(s_base + me) * (uint32_t)(L * 8);
-                const uint32_t nrow = pos_a + (uint32_t)(c_base + me) * (uint32_t)(L * 8);      // my walker of the other half: the next one
                 double c[L];
 #pragma unroll
                 for (int l = 0; l < L; ++l) c[l] = q_lds_f64(crow + 8u * l);
+                if (skew && tid < kWalkerThreads / 2) asm volatile("bar.arrive 3, %0;" ::"r"(H) : "memory");
+                const uint32_t xrow = pos_a + (uint32_t)(s_base + me) * (uint32_t)(L * 8);
+                const uint32_t nrow = pos_a + (uint32_t)(c_base + me) * (uint32_t)(L * 8);      // my walker of the other half: the next one
                 // accept for sure if lnp(q) - lnp(x) + fast > 1e-4, reject for sure if < -1e-4 (fast: the float estimate of
                 // (L-1) ln z - ln u', error < 2e-5); with lnp = -chi^2 / 2 both are thresholds on chi^2, ready before it is
                 const double fast_d = (double)__uint_as_float(pf.y);
@@ -599,7 +614,9 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
                     acc += 1u;
                 }
                 // the next half-step's operands: its draw (in place since the last barrier; of this piece or of the next one) and
-                // my walker of the other half -- not the next piece's, which is fetched when that piece starts
+                // my walker of the other half -- not the next piece's, which is fetched when that piece starts.  (Fetched here, not
+                // under the chi^2 sum: behind the other warp group's gather in the scheduler's load queue they would hold this warp
+                // at their issue -- measured 4 % slower.)
                 if (t + 1 < t_end || has_next) { z = q_lds_f64(draw_a + next_off); pf = q_lds_u2(draw_a + 2u * ring_span + next_off); }
                 if (t + 1 < t_end) {
 #pragma unroll
