@@ -291,7 +291,8 @@ class Dist:
             self.torch, self.dist = torch, dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-                os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+                os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own lines (its version banner) go to stderr
             try:
                 torch.cuda.set_device(local_rank)
                 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -385,6 +386,10 @@ class GpuWorkload:
         self.ens.reserve_chain(max(warmup, 1) // thin + steps // thin + 2)
         if warmup > 0:
             self.ens.advance(warmup, thin)
+        # More untimed steps, enqueued without waiting: the device is still busy with them while the host enqueues the start
+        # event, the timed launch and the stop event, so the events bracket the K steps on the device and not the host's
+        # launch latency (~7 us of a 70 us region at K = 20).  Nothing of them is kept (thin beyond their length).
+        self.ens.advance(max(warmup, 40), 10 ** 6, wait=False)
         self.chisq.check(lib, lib.mdaEventRecord(self.ev0, self.store.handle))
         self.ens.advance(steps, thin, wait=False)
         self.chisq.check(lib, lib.mdaEventRecord(self.ev1, self.store.handle))
@@ -596,6 +601,7 @@ def sampler_point(lib, chisq, orc, name, steps, hbm_peak, e2e_steps=48):
     ens.reserve_chain(steps // thin + 8)
     ens.advance(8, thin)
     ev0, ev1 = lib.mdaEventCreate(), lib.mdaEventCreate()
+    ens.advance(40, 10 ** 6, wait=False)                  # untimed, keeps the device busy while the timed launch is enqueued
     lib.mdaEventRecord(ev0, store.handle)
     ens.advance(steps, thin, wait=False)
     lib.mdaEventRecord(ev1, store.handle)
@@ -717,6 +723,8 @@ def main():
         return
 
     os.environ.setdefault("LOCAL_RANK", str(local_rank))
+    all_cpus = os.sched_getaffinity(0)
+    numa = shard.bind_to_gpu_numa_node(local_rank) if os.environ.get("MDA_BENCH_NUMA", "1") != "0" else "off"
     from mimic_mda_b200 import chisq
     lib = chisq.prepare_shared_object()               # raises if the CUDA library is missing
     if lib.mdaDeviceCount() < 1:
@@ -776,9 +784,19 @@ def main():
             traffic = {}
 
     def traffic_of(key):                     # DRAM bytes per launch from the ncu capture (per step x steps for the sampler)
+        exact = "%s_%dstep_launch" % (key, args.steps)
+        if exact in traffic:                 # a capture of a launch of exactly this length exists
+            return traffic[exact]
         if key + "_per_step" in traffic:
             return traffic[key + "_per_step"] * args.steps
         return traffic.get(key)
+
+    def traffic_source_of(key):
+        if "%s_%dstep_launch" % (key, args.steps) in traffic:
+            return ("dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture of a launch of this very length "
+                    "(profiles/traffic.json names the capture)")
+        return ("dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture named in profiles/traffic.json, per step x this "
+                "launch's steps for the sampler (a capture of another launch length, scaled -- not a measurement of the timed launch)")
 
     def roofline_of(kernel, seconds_per_launch, flops_launch, bytes_launch, traffic_key, tensor_note, executed_flops=None):
         tf = flops_launch / seconds_per_launch / 1e12
@@ -791,8 +809,10 @@ def main():
                      "note": "this kernel obtains chi^2 from the bin's triangular factor with (L+1)(L+2) + 5 L flops per evaluation "
                              "(fp64_executed) instead of the 2 N (L+1) of SURVEY.md 8d (fp64: the ALGORITHMIC rate, which the pipe peak "
                              "does not cap), so the roofline that can bind it is HBM: the chain, 8 (L+1) bytes per evaluation, going "
-                             "out (achieved / frac).  At C4 (1.35 bins per SM) it is limited by latency and instruction issue per "
-                             "half-step before that; with four bins per SM the chain reaches 56 % of the HBM rate"}
+                             "out (achieved / frac).  What limits it before that is the SM's shared-memory pipe: the stretch move "
+                             "gathers a RANDOM partner row per walker and half-step, 3.7 wavefronts per half-warp access instead of 1 "
+                             "(profiles/r02_ncu_full_*: 1000 wavefronts per bin and half-step, 83 % of the pipe's peak with four bins per "
+                             "SM, where the chain reaches 56 % of the HBM rate); at C4 there are only 1.35 bins per SM to overlap"}
         # the triangular-factor kernel executes a tenth of the algorithmic flops: the roofline that can bind it is HBM
         # (the chain going out); its algorithmic flop rate is reported in "fp64" below, not as the headline fraction
         by_flops = f64 >= fhbm and executed_flops is None
@@ -802,9 +822,7 @@ def main():
             "peak": peak_tf.value if by_flops else hbm_peak,
             "unit": "TFLOP/s" if by_flops else "GB/s",
             "frac": f64 if by_flops else fhbm, "traffic": traffic_of(traffic_key),
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture named in profiles/traffic.json, "
-                              "per step x this launch's steps for the sampler (a capture of another launch length, scaled -- not a "
-                              "measurement of the timed launch)",
+            "traffic_source": traffic_source_of(traffic_key),
             "kernel": kernel, "launch_us": seconds_per_launch * 1e6,
             "flops_per_launch": flops_launch, "bytes_per_launch": bytes_launch,
             "fp64": {"achieved_tflops": tf, "peak_tflops": peak_tf.value, "frac": f64,
@@ -872,6 +890,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                  # the reference arm gets every host core again
         cpu = cpu_reference_arm(cfg, args.cpu_seconds, work.consts, work.n_pts, work.params)
     # rank 0's GPU only (the other ranks wait at the closing barrier): the copy roofs of the e2e paths, the scalar-call
     # latency, and BASELINE.json's other configs
@@ -898,6 +917,7 @@ def main():
                     # the roof of this path is the host link: bytes delivered per second against one big pinned copy
                     "pcie_gbs": world * bins * cfg["walkers"] * (n_l + 1) * 8 * s_e2e_steps / s_secs / 1e9,
                     "pcie_gbs_per_gpu": bins * cfg["walkers"] * (n_l + 1) * 8 * s_e2e_steps / s_secs / 1e9,
+                    "numa": numa,
                     "d2h_peak_gbs": pcie["d2h_gbs"], "h2d_peak_gbs": pcie["h2d_gbs"], "peak_how": pcie["how"] + " (rank 0's GPU alone)",
                     "frac_of_d2h_peak": bins * cfg["walkers"] * (n_l + 1) * 8 * s_e2e_steps / s_secs / 1e9 / pcie["d2h_gbs"],
                     "limit": "PCIe: 8 (L+1) = %d bytes per evaluation cross the host link (Save Chain Data, mda.py:1244-1250: the reference "

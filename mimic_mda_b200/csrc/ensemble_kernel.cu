@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512) ensemble_kernel(const EnsembleArgs args) 
         double *zbuf = sZ + (size_t)(t & 1u) * H;
         float *fast = sFast + (size_t)(t & 1u) * H;
         for (int w = tid; w < H; w += T) {
-            const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + w), bin_id, t, 0u}, k0, k1);
+            const Philox4 r = philox4x32_10_keys(Philox4{(uint32_t)(s_base + w), bin_id, t, 0u}, args.round_keys);
             const double u = uniform53(r.x, r.y);
             // numpy arithmetic is one rounding per operation: no FMA contraction here
             const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);

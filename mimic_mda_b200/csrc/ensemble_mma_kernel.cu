@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
             const bool live = lane < IW && wl < H;
             auto publish = [&](uint32_t t) {
                 const int s_base = (t & 1u) ? H : 0, c_base = (t & 1u) ? 0 : H;
-                const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + min(wl, H - 1)), bin_id, t, 0u}, seed0, seed1);
+                const Philox4 r = philox4x32_10_keys(Philox4{(uint32_t)(s_base + min(wl, H - 1)), bin_id, t, 0u}, args.round_keys);
                 const double u = uniform53(r.x, r.y);
                 const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);          // numpy: one rounding per operation
                 const double z2 = __dmul_rn(zr, zr);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
         float fast_next = 0.f;                             // (L-1) ln z - ln u'
         auto draw = [&](uint32_t t) {
             const int s_base = (t & 1u) ? H : 0, c_base = (t & 1u) ? 0 : H;
-            const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + dw), bin_id, t, 0u}, seed0, seed1);
+            const Philox4 r = philox4x32_10_keys(Philox4{(uint32_t)(s_base + dw), bin_id, t, 0u}, args.round_keys);
             const double u = uniform53(r.x, r.y);
             // numpy arithmetic is one rounding per operation: no FMA contraction here
             const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps * (DW ? 2 : 1), DW ? 1 : 2) ens
             if (fabs(est) > 1e-4 || !decides) {
                 accept = est > 0.0;                    // far from a tie: the float logs (error < 2e-5) cannot change the sign
             } else {                                   // emcee's test in full precision (rare: redo the draw)
-                const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
+                const Philox4 r = philox4x32_10_keys(Philox4{(uint32_t)gw, bin_id, t, 0u}, args.round_keys);
                 const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
                 const double z2 = __dmul_rn(zr, zr);
                 const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(con
         const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = t_begin + 2u * (uint32_t)steps_here;
 
         auto draw = [&](uint32_t tt, int i) {
-            return philox4x32_10(Philox4{(uint32_t)(((tt & 1u) ? H : 0) + i), bin_id, tt, 0u}, seed0, seed1);
+            return philox4x32_10_keys(Philox4{(uint32_t)(((tt & 1u) ? H : 0) + i), bin_id, tt, 0u}, args.round_keys);
         };
         const bool one_each = OCC != 4 && H <= T;                   // one walker per thread (every BASELINE.json shape)
         const int my_i = min(tid, H - 1);

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
             // depend on positions).  emcee draws per half: u -> z, the partner index, then u'.
             auto draw = [&](uint32_t t, int i) {
                 const int s_base = (t & 1u) ? H : 0, c_base = (t & 1u) ? 0 : H;
-                const Philox4 r = philox4x32_10(Philox4{(uint32_t)(s_base + i), bin_id, t, 0u}, seed0, seed1);
+                const Philox4 r = philox4x32_10_keys(Philox4{(uint32_t)(s_base + i), bin_id, t, 0u}, args.round_keys);
                 const double u = uniform53(r.x, r.y);
                 // numpy arithmetic is one rounding per operation: no FMA contraction here
                 const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, u), 1.0);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(32 * (kWalkerWarps + kMathWarps), 1) ensemble_
                 if (fabs(est) > 1e-4) {
                     accept = est > 0.0;                // far from a tie: the float logs (error < 2e-5) cannot change the sign
                 } else {                               // emcee's test in full precision (rare: redo the draw)
-                    const Philox4 r = philox4x32_10(Philox4{(uint32_t)gw, bin_id, t, 0u}, seed0, seed1);
+                    const Philox4 r = philox4x32_10_keys(Philox4{(uint32_t)gw, bin_id, t, 0u}, args.round_keys);
                     const double zr = __dadd_rn(__dmul_rn(a_scale - 1.0, uniform53(r.x, r.y)), 1.0);
                     const double z2 = __dmul_rn(zr, zr);
                     const double z = (a_scale == 2.0) ? z2 * 0.5 : z2 / a_scale;

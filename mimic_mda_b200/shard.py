@@ -22,6 +22,35 @@ def rank_and_world():
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Best effort, before any pinned allocation: run this process on the CPUs of the NUMA node the GPU hangs off, so that
+    first-touch places the pinned chain buffers there (with one process per GPU all chains otherwise cross whichever socket
+    the processes happen to start on).  Returns a short description of what was done; never raises."""
+    try:
+        import subprocess
+        bus = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return "no pci bus id"
+        bus = bus[-12:]                                    # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return "gpu %s: numa node unknown (-1)" % bus
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return "gpu %s: node %d has no allowed cpus" % (bus, node)
+        os.sched_setaffinity(0, allowed)
+        return "gpu %s: bound to %d cpus of numa node %d" % (bus, len(allowed), node)
+    except Exception as exc:                               # an unusual sysfs / no nvidia-smi: stay where we are
+        return "not bound (%s)" % type(exc).__name__
+
+
 def bins_for_rank(n_bins, rank, world):
     """Global bin indices owned by ``rank``: rank, rank + world, rank + 2*world, ..."""
     if world < 1 or not 0 <= rank < world:
