@@ -423,6 +423,7 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
         next_loaded = false;
     }
     if constexpr (PROF) if (d == 0 && args.prof) for (int k = 0; k < 5; ++k) args.prof[(size_t)blockIdx.x * 128 + (DRAWS ? 112 : 120) + k] = p_d[k];
+    if constexpr (PROF) if (copier && args.prof) args.prof[(size_t)blockIdx.x * 128 + 125] = (long long)q_globaltimer_ns();     // before the last copies are waited for
     if (copier) {
         q_bulk_wait_all();
         if (pending_release >= 0) {
@@ -431,6 +432,7 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
             q_st_release_u64(args.progress + pending_release, args.launch_serial + 1ull);
         }
     }
+    if constexpr (PROF) if (copier && args.prof) args.prof[(size_t)blockIdx.x * 128 + 127] = (long long)q_globaltimer_ns();     // the CTA's last instruction but a few
 }
 
 // PROF: thread 0 stamps the phases of every piece of work into args.prof[cta][...] (debug build, selected when
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
     auto lnp_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes + lay.lnp); };
     auto fac_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * lay.buf_bytes + lay.fac); };
 
+    if constexpr (PROF) if (tid == 0 && args.prof) args.prof[(size_t)blockIdx.x * 128 + 126] = (long long)q_globaltimer_ns();   // kernel entry (wall clock)
     if (tid == 0) {
         q_mbar_init(&s_bar[0], 1);
         q_mbar_init(&s_bar[1], 1);

@@ -66,6 +66,10 @@ def main():
         cyc = ens.profile().astype(float)
         if ens.describe(args.steps).startswith("ensemble_qws"):
             ctas = min(args.bins, 148)
+            wall = cyc[:ctas, 124:128]                     # ns (globaltimer): -, before the last wait, kernel entry, kernel exit
+            t0 = wall[:, 2].min()
+            out["wall_ns"] = {"entry_spread": float(wall[:, 2].max() - t0), "last_cta_before_final_wait": float(wall[:, 1].max() - t0), "last_cta_exit": float(wall[:, 3].max() - t0),
+                              "first_cta_exit": float(wall[:, 3].min() - t0)}
             for name, o in (("walker_t0", 0), ("walker_t255", 8)):
                 v = cyc[:ctas, o:o + 5].sum(axis=0)
                 out[name + "_cycles_per_half_step"] = dict(zip(["gather+propose", "chi2", "accept+store+prefetch", "barrier"], [round(x / max(v[4], 1), 1) for x in v[:4]]))
