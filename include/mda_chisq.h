@@ -301,6 +301,10 @@ MDA_API void mdaPhilox4x32(const unsigned int *counter, const unsigned int *key,
  * numL <= 16.  Host pointers; synchronous.
  * --------------------------------------------------------------------- */
 MDA_API int mdaBatchFit(void *store, int startsPerBin, int sharedStarts, const double *starts, double *params, double *chi);
+/* What the calling thread's last mdaBatchFit met: fits that hit the iteration limit (the returned point is feasible but
+ * need not be the minimiser), fits in which a free set had a numerically null column (a bin with fewer independent angles
+ * than distributions: every value along it is a minimiser, the start's is kept), and the largest iteration count. */
+MDA_API int mdaBatchFitStats(long long *unconverged, long long *nullColumn, int *maxIterations);
 
 /* ------------------------------------------------------------------------
  * 8. Roofline denominators measured on the device this process uses

@@ -86,6 +86,7 @@ def prepare_shared_object(path=None):
         "mdaStoreSetBinFromStruct": (ct.c_int, [_VP, ct.c_int, _VP]),
         "mdaStoreSetBounds": (ct.c_int, [_VP, _DP, _DP]),
         "mdaStoreUpload": (ct.c_int, [_VP]),
+        "mdaBatchFitStats": (ct.c_int, [ct.POINTER(ct.c_longlong), ct.POINTER(ct.c_longlong), ct.POINTER(ct.c_int)]),
         "mdaDeviceMemInfo": (ct.c_int, [ct.POINTER(ct.c_size_t), ct.POINTER(ct.c_size_t)]),
         "mdaStoreConditioning": (ct.c_int, [_VP, _DP, _DP, ct.POINTER(ct.c_int)]),
         "mdaStoreNumBins": (ct.c_int, [_VP]),
@@ -279,6 +280,13 @@ class DeviceStore:
         check(self.lib, self.lib.mdaBatchFit(self.handle, n_s, 1 if shared else 0, starts.ctypes.data, params.ctypes.data,
                                              chi.ctypes.data), "mdaBatchFit")
         return params, chi
+
+    def fit_stats(self):
+        """What this thread's last ``fit`` met: ``(unconverged, null_column, max_iterations)`` -- fits that hit the
+        iteration limit, fits that met a numerically null column (rank-deficient bins), the largest iteration count."""
+        unconv, null_col, max_it = ct.c_longlong(), ct.c_longlong(), ct.c_int()
+        check(self.lib, self.lib.mdaBatchFitStats(ct.byref(unconv), ct.byref(null_col), ct.byref(max_it)), "mdaBatchFitStats")
+        return unconv.value, null_col.value, max_it.value
 
     # -- pinned staging + CUDA graph ---------------------------------------------------
     def staging(self, walkers):

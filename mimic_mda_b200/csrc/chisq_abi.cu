@@ -674,6 +674,10 @@ int qws_grid(const MdaStore *s, const EnsembleShape &shape) {
     return grid;
 }
 
+// what the last mdaBatchFit of this thread met (mdaBatchFitStats)
+struct FitStats { long long unconverged = 0, null_column = 0; int max_iterations = 0; };
+thread_local FitStats t_fit_stats;
+
 // MDA_E2E_TIMING=1: wall-clock laps of the host-buffer calls on stderr (where a millisecond-long e2e region goes)
 struct LapTimer {
     bool on = getenv("MDA_E2E_TIMING") != nullptr;
@@ -1097,24 +1101,39 @@ int mdaBatchFit(void *store, int startsPerBin, int sharedStarts, const double *s
     if ((rc = upload_store(s))) return rc;
     const size_t L = (size_t)s->n_l, B = (size_t)s->bins, S = (size_t)startsPerBin;
     const size_t n_start = (sharedStarts ? 1 : B) * S * L;
-    double *d_gram = nullptr, *d_rhs = nullptr, *d_starts = nullptr, *d_fit = nullptr, *d_chi = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_gram, sizeof(double) * B * L * L);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_rhs, sizeof(double) * B * L);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_starts, sizeof(double) * n_start);
+    double *d_starts = nullptr, *d_fit = nullptr, *d_chi = nullptr;
+    int *d_iters = nullptr;
+    std::vector<int> h_iters(B * S);
+    cudaError_t e = cudaMalloc((void **)&d_starts, sizeof(double) * n_start);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_fit, sizeof(double) * B * S * L);
     if (e == cudaSuccess) e = cudaMalloc((void **)&d_chi, sizeof(double) * B * S);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_iters, sizeof(int) * B * S);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_starts, starts, sizeof(double) * n_start, cudaMemcpyHostToDevice, s->stream);
-    if (e == cudaSuccess) e = launch_gram(s->d_consts, s->d_npts, s->bins, s->n_l, s->n_pad, d_gram, d_rhs, s->stream);
-    if (e == cudaSuccess) e = launch_bvls(d_gram, d_rhs, s->d_lo, s->d_hi, d_starts, s->bins, s->n_l, startsPerBin, sharedStarts != 0, d_fit, nullptr, s->stream);
-    if (e == cudaSuccess) g_launches.fetch_add(2, std::memory_order_relaxed);
+    // the active-set solves run on the bins' triangular factors (no normal equations: fit_kernel.cu)
+    if (e == cudaSuccess) e = launch_bvls(s->d_quad, s->d_lo, s->d_hi, d_starts, s->bins, s->n_l, startsPerBin, sharedStarts != 0, d_fit, d_iters, s->stream);
+    if (e == cudaSuccess) g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e == cudaSuccess) rc = enqueue_eval(s, startsPerBin, d_fit, d_chi, kChi);
     if (e == cudaSuccess && rc == MDA_OK && params) e = cudaMemcpyAsync(params, d_fit, sizeof(double) * B * S * L, cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess && rc == MDA_OK && chi) e = cudaMemcpyAsync(chi, d_chi, sizeof(double) * B * S, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && rc == MDA_OK) e = cudaMemcpyAsync(h_iters.data(), d_iters, sizeof(int) * B * S, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e2 = cudaStreamSynchronize(s->stream);
-    cudaFree(d_gram); cudaFree(d_rhs); cudaFree(d_starts); cudaFree(d_fit); cudaFree(d_chi);
+    cudaFree(d_starts); cudaFree(d_fit); cudaFree(d_chi); cudaFree(d_iters);
     if (e != cudaSuccess) return cuda_fail(e, "mdaBatchFit");
     if (rc != MDA_OK) return rc;
     if (e2 != cudaSuccess) return cuda_fail(e2, "mdaBatchFit");
+    t_fit_stats = FitStats{};
+    for (int v : h_iters) {
+        if (v < 0) { ++t_fit_stats.unconverged; t_fit_stats.max_iterations = std::max(t_fit_stats.max_iterations, -v); continue; }
+        if (v & (1 << 16)) ++t_fit_stats.null_column;
+        t_fit_stats.max_iterations = std::max(t_fit_stats.max_iterations, v & 0xFFFF);
+    }
+    return MDA_OK;
+}
+
+int mdaBatchFitStats(long long *unconverged, long long *nullColumn, int *maxIterations) {
+    if (unconverged) *unconverged = t_fit_stats.unconverged;
+    if (nullColumn) *nullColumn = t_fit_stats.null_column;
+    if (maxIterations) *maxIterations = t_fit_stats.max_iterations;
     return MDA_OK;
 }
 

@@ -7,91 +7,77 @@
 // quadratic and the constraints are a box, so every start has the same constrained
 // minimiser; here each (bin, start) pair is solved exactly by one thread with a
 // bounded-variable least-squares active-set method (Stark & Parker's BVLS, warm-started at
-// the clipped start point) on the bin's normal equations:
-//   gram_kernel   G = D D^T, b = D d per bin, accumulated in ascending angle order
-//   bvls_kernel   one thread per (bin, start): free-set Cholesky solves + feasible steps
+// the clipped start point).
+//
+// The linear algebra runs on the bin's TRIANGULAR FACTOR, the one the sampler uses (chisq_abi.cu:
+// factor_bin; [D^T | d] = Q [R t; 0 tau], computed in long double when the store is built):
+// chi^2(a) = |R a - t|^2 + tau^2.  A free set's minimiser is the least-squares solution of
+// R[:, free] x = t - R[:, bound] a_bound, obtained by Householder reflections on those columns -- never
+// through the normal equations D D^T, whose condition number is the square of D's (small-angle DWBA
+// multipoles are close to collinear).  The multipliers of the bound variables are R^T (t - R a).
+// Columns that are numerically null (a bin with fewer angles than distributions) keep their current
+// value: every value is a minimiser along them.
 // The chi^2 of every solution is then evaluated by the batched likelihood kernel in kChi
-// mode (not through G: the Gram form cancels catastrophically).
-#include "mda_kernels.cuh"
+// mode, in the reference's operation order.
+#include "quad_chi.cuh"
 
 namespace mda {
 
 namespace {
 
-// G[bin][L][L], b[bin][L] from the store layout consts[bin][n_pad/2][1+L] double2.
-__global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ consts, const int *__restrict__ n_pts,
-                                                   int n_l, int n_pad, double *__restrict__ gram, double *__restrict__ rhs) {
-    const int bin = blockIdx.x;
-    const int row = n_l + 1;
-    const double2 *c = reinterpret_cast<const double2 *>(consts) + (size_t)bin * (n_pad / 2) * row;
-    const int n = n_pts[bin];
-    const int pairs = n >> 1;
-    // entries (l, m) with m <= l of G, and (l, -1) for b
-    const int n_entries = n_l * (n_l + 1) / 2 + n_l;
-    for (int e = threadIdx.x; e < n_entries; e += blockDim.x) {
-        int l, m;
-        if (e < n_l) { l = e; m = -1; }
-        else {
-            int t = e - n_l;
-            l = 0;
-            while (t >= l + 1) { t -= l + 1; ++l; }
-            m = t;
-        }
-        double acc = 0.0;
-        for (int j2 = 0; j2 < pairs; ++j2) {
-            const double2 x = c[(size_t)j2 * row + 1 + l];
-            const double2 y = c[(size_t)j2 * row + 1 + m];      // m == -1 -> the data pair
-            acc = fma(x.x, y.x, acc);
-            acc = fma(x.y, y.y, acc);
-        }
-        if (n & 1) acc = fma(c[(size_t)pairs * row + 1 + l].x, c[(size_t)pairs * row + 1 + m].x, acc);
-        if (m < 0) rhs[(size_t)bin * n_l + l] = acc;
-        else {
-            gram[((size_t)bin * n_l + l) * n_l + m] = acc;
-            gram[((size_t)bin * n_l + m) * n_l + l] = acc;
-        }
-    }
-}
-
-// Solve M z = r for the nf x nf leading block (M symmetric positive definite, lower part used).
-// Returns false if a pivot is not positive.
+// Least-squares solution over the free set.  A is the L x nf matrix of the free columns of R (row-major, stride L), y the
+// right-hand side; both are overwritten.  x[p] = the minimiser's component for free variable p, or keep[p] where the
+// column carries no information (pivot below `tiny`).  Returns the number of such null columns.
 template <int L>
-__device__ bool cholesky_solve(double (&M)[L * L], double (&r)[L], int nf) {
-    for (int j = 0; j < nf; ++j) {
-        double d = M[j * L + j];
-        for (int k = 0; k < j; ++k) d -= M[j * L + k] * M[j * L + k];
-        if (!(d > 0.0)) return false;
-        d = sqrt(d);
-        M[j * L + j] = d;
-        for (int i = j + 1; i < nf; ++i) {
-            double s = M[i * L + j];
-            for (int k = 0; k < j; ++k) s -= M[i * L + k] * M[j * L + k];
-            M[i * L + j] = s / d;
+__device__ int householder_solve(double *A, double *y, int nf, const double *keep, double tiny, double *x) {
+    unsigned null_cols = 0;
+    for (int p = 0; p < nf; ++p) {
+        double norm2 = 0.0;
+        for (int k = p; k < L; ++k) norm2 = fma(A[k * L + p], A[k * L + p], norm2);
+        if (!(norm2 > tiny)) { null_cols |= 1u << p; continue; }
+        const double norm = sqrt(norm2), x0 = A[p * L + p];
+        const double alpha = x0 > 0.0 ? -norm : norm;
+        const double v0 = x0 - alpha;
+        const double vv = norm2 - x0 * x0 + v0 * v0;               // |v|^2 with v = column - alpha e_p
+        if (!(vv > 0.0)) { A[p * L + p] = alpha; continue; }
+        for (int q = p + 1; q <= nf; ++q) {                        // q == nf: the right-hand side
+            double dot = v0 * (q < nf ? A[p * L + q] : y[p]);
+            for (int k = p + 1; k < L; ++k) dot = fma(A[k * L + p], q < nf ? A[k * L + q] : y[k], dot);
+            const double f = 2.0 * dot / vv;
+            if (q < nf) {
+                A[p * L + q] -= f * v0;
+                for (int k = p + 1; k < L; ++k) A[k * L + q] -= f * A[k * L + p];
+            } else {
+                y[p] -= f * v0;
+                for (int k = p + 1; k < L; ++k) y[k] -= f * A[k * L + p];
+            }
         }
+        A[p * L + p] = alpha;
     }
-    for (int i = 0; i < nf; ++i) {                      // forward
-        double s = r[i];
-        for (int k = 0; k < i; ++k) s -= M[i * L + k] * r[k];
-        r[i] = s / M[i * L + i];
+    int n_null = 0;
+    for (int p = nf - 1; p >= 0; --p) {                            // back substitution
+        if (null_cols >> p & 1u) { x[p] = keep[p]; ++n_null; continue; }
+        double s = y[p];
+        for (int q = p + 1; q < nf; ++q) s -= A[p * L + q] * x[q];
+        x[p] = s / A[p * L + p];
     }
-    for (int i = nf - 1; i >= 0; --i) {                 // backward
-        double s = r[i];
-        for (int k = i + 1; k < nf; ++k) s -= M[k * L + i] * r[k];
-        r[i] = s / M[i * L + i];
-    }
-    return true;
+    return n_null;
 }
 
 template <int L>
-__global__ void __launch_bounds__(128) bvls_kernel(const double *__restrict__ gram, const double *__restrict__ rhs,
-                                                   const double *__restrict__ lo_g, const double *__restrict__ hi_g,
-                                                   const double *__restrict__ starts, int starts_per_bin,
-                                                   int shared_starts, double *__restrict__ out, int *__restrict__ iters) {
-    __shared__ double sG[L * L], sB[L], sLo[L], sHi[L];
+__global__ void __launch_bounds__(128) bvls_kernel(const double *__restrict__ quad, const double *__restrict__ lo_g,
+                                                   const double *__restrict__ hi_g, const double *__restrict__ starts,
+                                                   int starts_per_bin, int shared_starts, double *__restrict__ out,
+                                                   int *__restrict__ iters) {
+    __shared__ double sR[L * L], sT[L], sLo[L], sHi[L];            // R dense (zeros below the diagonal), t
     const int bin = blockIdx.y;
-    for (int i = threadIdx.x; i < L * L; i += blockDim.x) sG[i] = gram[(size_t)bin * L * L + i];
+    const double *packed = quad + (size_t)bin * quad_stride(L);
+    for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+        const int i = e / L, c = e - i * L;
+        sR[e] = c >= i ? packed[quad_row_offset(L, i) + (c - i)] : 0.0;
+    }
     if (threadIdx.x < L) {
-        sB[threadIdx.x] = rhs[(size_t)bin * L + threadIdx.x];
+        sT[threadIdx.x] = packed[quad_row_offset(L, threadIdx.x) + (L - threadIdx.x)];
         sLo[threadIdx.x] = lo_g[threadIdx.x];
         sHi[threadIdx.x] = hi_g[threadIdx.x];
     }
@@ -102,19 +88,22 @@ __global__ void __launch_bounds__(128) bvls_kernel(const double *__restrict__ gr
 
     double a[L];
     unsigned free_mask = 0;
-    double scale = 0.0;
+    double scale = 0.0;                                            // largest squared column norm of R = largest diagonal of D D^T
     for (int i = 0; i < L; ++i) {
         double v = a0[i];
         v = v < sLo[i] ? sLo[i] : (v > sHi[i] ? sHi[i] : v);       // NaN start -> falls to the lower bound below
         if (!(v == v)) v = sLo[i];
         a[i] = v;
         if (v > sLo[i] && v < sHi[i]) free_mask |= 1u << i;
-        scale = fmax(scale, sG[i * L + i]);
+        double col = 0.0;
+        for (int k = 0; k <= i; ++k) col = fma(sR[k * L + i], sR[k * L + i], col);
+        scale = fmax(scale, col);
     }
-    const double ridge = scale * 1e-15;                 // only matters for rank-deficient bins (N < L)
+    const double tiny = scale * 1e-28;                             // squared pivot below (1e-14)^2 of the largest column: null
     const double tol = 1e-12;
 
     int it = 0;
+    int null_seen = 0;
     const int max_it = 6 * L + 12;
     unsigned tabu = 0;                  // variables that, once freed, wanted straight back out through their bound
     int just = -1;                      // variable freed by the current outer iteration (-1: warm start)
@@ -126,16 +115,16 @@ __global__ void __launch_bounds__(128) bvls_kernel(const double *__restrict__ gr
             int nf = 0;
             for (int i = 0; i < L; ++i)
                 if (free_mask >> i & 1u) idx[nf++] = i;
-            double M[L * L], r[L];
-            for (int p = 0; p < nf; ++p) {
-                const int i = idx[p];
-                double v = sB[i];
-                for (int j = 0; j < L; ++j)
-                    if (!(free_mask >> j & 1u)) v -= sG[i * L + j] * a[j];
-                r[p] = v;
-                for (int q = 0; q <= p; ++q) M[p * L + q] = sG[i * L + idx[q]] + (p == q ? ridge : 0.0);
+            double A[L * L], y[L], r[L], keep[L];
+            for (int k = 0; k < L; ++k) {
+                double v = sT[k];
+                for (int j = k; j < L; ++j)
+                    if (!(free_mask >> j & 1u)) v -= sR[k * L + j] * a[j];
+                y[k] = v;
+                for (int p = 0; p < nf; ++p) A[k * L + p] = sR[k * L + idx[p]];
             }
-            if (!cholesky_solve<L>(M, r, nf)) { free_mask = 0; break; }
+            for (int p = 0; p < nf; ++p) keep[p] = a[idx[p]];
+            null_seen |= householder_solve<L>(A, y, nf, keep, tiny, r) > 0 ? 1 : 0;
             double alpha = 1.0;
             int hit = -1;
             for (int p = 0; p < nf; ++p) {
@@ -175,14 +164,21 @@ __global__ void __launch_bounds__(128) bvls_kernel(const double *__restrict__ gr
         }
         if (just >= 0 && !bounced) tabu = 0;            // progress was made: forget old bounces
         if (++it > max_it) break;
-        // ---- outer loop: KKT test on the bound variables, free the most violating one
+        // ---- outer loop: KKT test on the bound variables, free the most violating one.  w = R^T (t - R a) is minus half
+        // the gradient of chi^2.
+        double resid[L];
+        for (int k = 0; k < L; ++k) {
+            double v = sT[k];
+            for (int j = k; j < L; ++j) v -= sR[k * L + j] * a[j];
+            resid[k] = v;
+        }
         int best = -1;
         double best_w = 0.0;
         for (int i = 0; i < L; ++i) {
             if ((free_mask >> i & 1u) || (tabu >> i & 1u) || !(sHi[i] > sLo[i])) continue;
-            double w = sB[i];
-            for (int j = 0; j < L; ++j) w -= sG[i * L + j] * a[j];      // minus half the gradient
-            const double thr = tol * (fabs(sB[i]) + scale);
+            double w = 0.0, b = 0.0;
+            for (int k = 0; k <= i; ++k) { w = fma(sR[k * L + i], resid[k], w); b = fma(sR[k * L + i], sT[k], b); }
+            const double thr = tol * (fabs(b) + scale);
             const bool wants_in = (a[i] <= sLo[i] && w > thr) || (a[i] >= sHi[i] && w < -thr);
             if (wants_in && fabs(w) > best_w) { best_w = fabs(w); best = i; }
         }
@@ -192,11 +188,12 @@ __global__ void __launch_bounds__(128) bvls_kernel(const double *__restrict__ gr
     }
     double *o = out + ((size_t)bin * starts_per_bin + s) * L;
     for (int i = 0; i < L; ++i) o[i] = a[i];
-    if (iters) iters[(size_t)bin * starts_per_bin + s] = it;
+    // iterations taken; negative: the iteration limit was hit (the point is feasible but need not be the minimiser);
+    // bit 16 set: a free set met a numerically null column (a rank-deficient bin: any value along it is a minimiser)
+    if (iters) iters[(size_t)bin * starts_per_bin + s] = (it > max_it ? -it : it) | (null_seen && it <= max_it ? 1 << 16 : 0);
 }
 
-using BvlsKernel = void (*)(const double *, const double *, const double *, const double *, const double *, int, int,
-                            double *, int *);
+using BvlsKernel = void (*)(const double *, const double *, const double *, const double *, int, int, double *, int *);
 
 BvlsKernel pick_bvls(int n_l) {
     switch (n_l) {
@@ -210,21 +207,14 @@ BvlsKernel pick_bvls(int n_l) {
 
 }  // namespace
 
-cudaError_t launch_gram(const double *consts, const int *n_pts, int bins, int n_l, int n_pad, double *gram, double *rhs,
-                        cudaStream_t stream) {
-    if (bins <= 0) return cudaSuccess;
-    gram_kernel<<<bins, 256, 0, stream>>>(consts, n_pts, n_l, n_pad, gram, rhs);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_bvls(const double *gram, const double *rhs, const double *lo, const double *hi, const double *starts,
+cudaError_t launch_bvls(const double *quad, const double *lo, const double *hi, const double *starts,
                         int bins, int n_l, int starts_per_bin, bool shared_starts, double *out, int *iters,
                         cudaStream_t stream) {
     if (bins <= 0 || starts_per_bin <= 0) return cudaSuccess;
     BvlsKernel k = pick_bvls(n_l);
     if (!k || bins > 65535) return cudaErrorInvalidValue;
     dim3 grid((unsigned)((starts_per_bin + 127) / 128), (unsigned)bins);
-    k<<<grid, 128, 0, stream>>>(gram, rhs, lo, hi, starts, starts_per_bin, shared_starts ? 1 : 0, out, iters);
+    k<<<grid, 128, 0, stream>>>(quad, lo, hi, starts, starts_per_bin, shared_starts ? 1 : 0, out, iters);
     return cudaGetLastError();
 }
 

@@ -178,12 +178,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // ---- batched initial fits (fit_kernel.cu) -----------------------------------------------------
-// gram[bins][L][L] = D D^T and rhs[bins][L] = D d of every bin of the store.
-cudaError_t launch_gram(const double *consts, const int *n_pts, int bins, int n_l, int n_pad, double *gram, double *rhs,
-                        cudaStream_t stream);
-// One thread per (bin, start): box-constrained least-squares minimiser, warm-started at the start.
-// starts is [starts_per_bin][L] when shared, else [bins][starts_per_bin][L]; out [bins][starts_per_bin][L].
-cudaError_t launch_bvls(const double *gram, const double *rhs, const double *lo, const double *hi, const double *starts,
+// One thread per (bin, start): box-constrained least-squares minimiser on the bin's packed triangular factor (quad:
+// [bins][quad_stride(L)], see quad_chi.cuh), warm-started at the start.  starts is [starts_per_bin][L] when shared, else
+// [bins][starts_per_bin][L]; out [bins][starts_per_bin][L]; iters (optional) [bins][starts_per_bin]: iterations, negative
+// when the limit was hit, bit 16 set when a free set met a numerically null column.
+cudaError_t launch_bvls(const double *quad, const double *lo, const double *hi, const double *starts,
                         int bins, int n_l, int starts_per_bin, bool shared_starts, double *out, int *iters,
                         cudaStream_t stream);
 
