@@ -30,6 +30,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <utility>
 #include <cstdlib>
 
 namespace mda {
@@ -243,27 +244,20 @@ __global__ void __launch_bounds__(kQuadMaxThreads, OCC) ensemble_quad_kernel(con
 
 using EnsKernel = void (*)(const EnsembleArgs);
 
-EnsKernel pick_quad_kernel(int n_l, int occ) {
-    switch (n_l) {
-        case 1: return occ == 1 ? ensemble_quad_kernel<1, 1> : (occ == 3 ? ensemble_quad_kernel<1, 3> : ensemble_quad_kernel<1, 4>);
-        case 2: return occ == 1 ? ensemble_quad_kernel<2, 1> : (occ == 3 ? ensemble_quad_kernel<2, 3> : ensemble_quad_kernel<2, 4>);
-        case 3: return occ == 1 ? ensemble_quad_kernel<3, 1> : (occ == 3 ? ensemble_quad_kernel<3, 3> : ensemble_quad_kernel<3, 4>);
-        case 4: return occ == 1 ? ensemble_quad_kernel<4, 1> : (occ == 3 ? ensemble_quad_kernel<4, 3> : ensemble_quad_kernel<4, 4>);
-        case 5: return occ == 1 ? ensemble_quad_kernel<5, 1> : (occ == 3 ? ensemble_quad_kernel<5, 3> : ensemble_quad_kernel<5, 4>);
-        case 6: return occ == 1 ? ensemble_quad_kernel<6, 1> : (occ == 3 ? ensemble_quad_kernel<6, 3> : ensemble_quad_kernel<6, 4>);
-        case 7: return occ == 1 ? ensemble_quad_kernel<7, 1> : (occ == 3 ? ensemble_quad_kernel<7, 3> : ensemble_quad_kernel<7, 4>);
-        case 8: return occ == 1 ? ensemble_quad_kernel<8, 1> : (occ == 3 ? ensemble_quad_kernel<8, 3> : ensemble_quad_kernel<8, 4>);
-        case 9: return occ == 1 ? ensemble_quad_kernel<9, 1> : (occ == 3 ? ensemble_quad_kernel<9, 3> : ensemble_quad_kernel<9, 4>);
-        case 10: return occ == 1 ? ensemble_quad_kernel<10, 1> : (occ == 3 ? ensemble_quad_kernel<10, 3> : ensemble_quad_kernel<10, 4>);
-        case 11: return occ == 1 ? ensemble_quad_kernel<11, 1> : (occ == 3 ? ensemble_quad_kernel<11, 3> : ensemble_quad_kernel<11, 4>);
-        case 12: return occ == 1 ? ensemble_quad_kernel<12, 1> : (occ == 3 ? ensemble_quad_kernel<12, 3> : ensemble_quad_kernel<12, 4>);
-        case 13: return occ == 1 ? ensemble_quad_kernel<13, 1> : (occ == 3 ? ensemble_quad_kernel<13, 3> : ensemble_quad_kernel<13, 4>);
-        case 14: return occ == 1 ? ensemble_quad_kernel<14, 1> : (occ == 3 ? ensemble_quad_kernel<14, 3> : ensemble_quad_kernel<14, 4>);
-        case 15: return occ == 1 ? ensemble_quad_kernel<15, 1> : (occ == 3 ? ensemble_quad_kernel<15, 3> : ensemble_quad_kernel<15, 4>);
-        case 16: return occ == 1 ? ensemble_quad_kernel<16, 1> : (occ == 3 ? ensemble_quad_kernel<16, 3> : ensemble_quad_kernel<16, 4>);
-        default: return nullptr;
-    }
+// every numL 1 .. kMaxRegL x the three occupancy builds (1, 3 or 4 CTAs per SM)
+template <int L>
+EnsKernel pick_occ(int occ) {
+    return occ == 1 ? ensemble_quad_kernel<L, 1> : (occ == 3 ? ensemble_quad_kernel<L, 3> : ensemble_quad_kernel<L, 4>);
 }
+
+template <int... Ls>
+EnsKernel pick_from(int n_l, int occ, std::integer_sequence<int, Ls...>) {
+    EnsKernel k = nullptr;
+    ((n_l == Ls + 1 ? (k = pick_occ<Ls + 1>(occ), 0) : 0), ...);
+    return k;
+}
+
+EnsKernel pick_quad_kernel(int n_l, int occ) { return pick_from(n_l, occ, std::make_integer_sequence<int, kMaxRegL>{}); }
 
 }  // namespace
 
