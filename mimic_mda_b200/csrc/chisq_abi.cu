@@ -418,6 +418,7 @@ int enqueue_eval(MdaStore *s, int walkers, const double *d_params, double *d_out
     args.n_l = s->n_l;
     args.n_pad = s->n_pad;
     args.mode = mode;
+    args.params_bulk = (reinterpret_cast<uintptr_t>(d_params) & 15u) == 0 && !getenv("MDA_BATCH_NO_BULK_PARAMS");
     if (s->n_l <= kMaxRegL)
         for (int l = 0; l < s->n_l; ++l) { args.lo[l] = s->lo[l]; args.hi[l] = s->hi[l]; }
     const char *batch_impl = getenv("MDA_BATCH_IMPL");

@@ -23,6 +23,10 @@
 // Tensor cores are deliberately not used: the contraction is K = L <= 16 deep in fp64.
 #include "likelihood.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+#include <utility>
+
 namespace mda {
 
 namespace {
@@ -61,17 +65,21 @@ __global__ void __launch_bounds__(256) lnpost_tile_kernel(const BatchArgs args) 
     }
     __syncthreads();
 
-    // constants of the first chunk: one bulk copy, issued before anything else
+    // The tile's walker parameters are one contiguous block [nw][L] of the caller's array: ONE bulk copy brings it in
+    // (16-byte aligned and sized whenever the block starts on an even double and holds an even number of them -- always
+    // for even L or even tiles; args.params_bulk says the array itself is 16-byte aligned).  Otherwise: coalesced 8-byte
+    // cp.async into rows padded to an odd stride.  Both land on the same mbarrier phase as the first chunk of constants.
+    const bool bulk_p = args.params_bulk && ((((size_t)bin * args.walkers + w0) * L) & 1) == 0 && ((nw * L) & 1) == 0;
+    const int lp = bulk_p ? L : LP;                  // row stride of the staged parameters (doubles)
     const int first_cols = min(chunk, n_pad);
-    if (tid == 0 && first_cols > 0) {
-        const uint32_t bytes = (uint32_t)first_cols * ROW * 8u;
-        mbar_arrive_expect_tx(&mbar, bytes);
-        bulk_g2s(sC, gC, bytes, &mbar);
+    const double *gP = args.params + ((size_t)bin * args.walkers + w0) * L;
+    if (tid == 0 && (first_cols > 0 || bulk_p)) {
+        const uint32_t c_bytes = (uint32_t)first_cols * ROW * 8u, p_bytes = bulk_p ? (uint32_t)nw * L * 8u : 0u;
+        mbar_arrive_expect_tx(&mbar, c_bytes + p_bytes);
+        if (c_bytes) bulk_g2s(sC, gC, c_bytes, &mbar);
+        if (p_bytes) bulk_g2s(sP, gP, p_bytes, &mbar);
     }
-
-    // this tile's walker parameters: coalesced 8-byte async copies into padded rows
-    {
-        const double *gP = args.params + ((size_t)bin * args.walkers + w0) * L;
+    if (!bulk_p) {
         const int count = nw * L;
         for (int i = tid; i < count; i += T) {
             const int w = i / L;
@@ -80,8 +88,15 @@ __global__ void __launch_bounds__(256) lnpost_tile_kernel(const BatchArgs args) 
         }
     }
     const int n = args.n_pts[bin];                   // latency overlaps the copies above
-    cp_async_commit_wait_all();
-    __syncthreads();
+    if (!bulk_p) {
+        cp_async_commit_wait_all();
+        __syncthreads();
+    }
+    uint32_t parity = 0;
+    if (first_cols > 0 || bulk_p) {                  // parameters (bulk path) and the first chunk of constants are in
+        mbar_wait(&mbar, 0);
+        parity = 1u;
+    }
 
     double a[WPT][L];
     bool outside[WPT];
@@ -89,19 +104,27 @@ __global__ void __launch_bounds__(256) lnpost_tile_kernel(const BatchArgs args) 
     for (int k = 0; k < WPT; ++k) {
         const int w = min(tid + k * T, nw - 1);      // clamp: idle slots repeat the last walker
         outside[k] = false;
+        if ((L & 1) == 0 && bulk_p) {                // dense rows of an even L are 16-byte aligned: 128-bit reads
+            const double2 *row = reinterpret_cast<const double2 *>(sP + (size_t)w * L);
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-            a[k][l] = sP[w * LP + l];
-            // mda.py:1575 -- "params[i] < lo or params[i] > hi"; NaN compares false
-            outside[k] = outside[k] || (a[k][l] < args.lo[l]) || (a[k][l] > args.hi[l]);
+            for (int l2 = 0; l2 < L / 2; ++l2) {
+                const double2 v = row[l2];
+                a[k][2 * l2] = v.x;
+                a[k][2 * l2 + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int l = 0; l < L; ++l) a[k][l] = sP[w * lp + l];
         }
+#pragma unroll
+        for (int l = 0; l < L; ++l)                  // mda.py:1575 -- "params[i] < lo or params[i] > hi"; NaN compares false
+            outside[k] = outside[k] || (a[k][l] < args.lo[l]) || (a[k][l] > args.hi[l]);
     }
 
     double chi[WPT];
 #pragma unroll
     for (int k = 0; k < WPT; ++k) chi[k] = 0.0;
 
-    uint32_t parity = 0;
     for (int c0 = 0; c0 < n; c0 += chunk) {
         if (c0 > 0) {
             __syncthreads();                          // every thread is done with the old chunk
@@ -110,14 +133,11 @@ __global__ void __launch_bounds__(256) lnpost_tile_kernel(const BatchArgs args) 
                 mbar_arrive_expect_tx(&mbar, bytes);
                 bulk_g2s(sC, gC + (size_t)(c0 / 2) * ROW, bytes, &mbar);
             }
+            mbar_wait(&mbar, parity);
+            parity ^= 1u;
         }
-        mbar_wait(&mbar, parity);
-        parity ^= 1u;
-
         accumulate_chi<L, WPT>(sC, min(chunk, n - c0), a, chi);
     }
-    // a bin with n == 0 never waited on the first chunk's copy: drain it before exit
-    if (n <= 0 && first_cols > 0) mbar_wait(&mbar, 0);
 
     double *out = args.out + (size_t)bin * args.walkers + w0;
 #pragma unroll
@@ -228,29 +248,17 @@ TileKernel pick_wpt(int wpt) {
     }
 }
 
-TileKernel pick_kernel(int n_l, int wpt) {
-    switch (n_l) {
-        case 1: return pick_wpt<1>(wpt);
-        case 2: return pick_wpt<2>(wpt);
-        case 3: return pick_wpt<3>(wpt);
-        case 4: return pick_wpt<4>(wpt);
-        case 5: return pick_wpt<5>(wpt);
-        case 6: return pick_wpt<6>(wpt);
-        case 7: return pick_wpt<7>(wpt);
-        case 8: return pick_wpt<8>(wpt);
-        case 9: return pick_wpt<9>(wpt);
-        case 10: return pick_wpt<10>(wpt);
-        case 11: return pick_wpt<11>(wpt);
-        case 12: return pick_wpt<12>(wpt);
-        case 13: return pick_wpt<13>(wpt);
-        case 14: return pick_wpt<14>(wpt);
-        case 15: return pick_wpt<15>(wpt);
-        case 16: return pick_wpt<16>(wpt);
-        default: return nullptr;
-    }
+template <int... Ls>
+TileKernel pick_from(int n_l, int wpt, std::integer_sequence<int, Ls...>) {
+    TileKernel k = nullptr;
+    ((n_l == Ls + 1 ? (k = pick_wpt<Ls + 1>(wpt), 0) : 0), ...);
+    return k;
 }
 
+TileKernel pick_kernel(int n_l, int wpt) { return pick_from(n_l, wpt, std::make_integer_sequence<int, kMaxRegL>{}); }
+
 inline int round_down_even(long v) { return (int)(v & ~1L); }
+
 
 }  // namespace
 
@@ -307,6 +315,7 @@ cudaError_t configure_kernels(size_t smem_optin) {
             cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(pick_kernel(l, wpts[i])),
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
             if (e != cudaSuccess) return e;
+
         }
     return cudaFuncSetAttribute(reinterpret_cast<const void *>(lnpost_generic_kernel),
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);

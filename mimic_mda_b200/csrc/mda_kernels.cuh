@@ -33,6 +33,7 @@ struct BatchArgs {
     const double *consts_mma;   // DMMA kernel: fragment-major constants [bins][n_tiles][8 (1+L)] (see mma_chi.cuh)
     int n_tiles;                // DMMA kernel: angle tiles of 8
     const double *quad;         // triangular-factor kernel: [bins][quad_stride(L)] packed T (see quad_chi.cuh)
+    int params_bulk;            // params is 16-byte aligned: a tile's parameter block may come in by one bulk copy
 };
 
 struct TileShape {
