@@ -528,8 +528,9 @@ def scalar_call_latency(lib, chisq, calls=300):
             handle.calculateLnLiklihood(st, ptr)
         out[name] = (time.perf_counter() - t0) / calls * 1e6
         handle.freeMdaStruct(st)
-    out["what"] = ("calculateLnLiklihood(L=9, N=60) per call through ctypes: the GPU library pays a kernel launch and a stream sync "
-                   "per call, so unmodified mda.py pointed at it is slower per call than the CPU library -- the batched entry points exist for that")
+    out["what"] = ("calculateLnLiklihood(L=9, N=60) per call through ctypes: the GPU library pays a kernel launch per call (parameters in "
+                   "the argument block, result and completion ticket written to mapped host memory, no stream synchronisation), so "
+                   "unmodified mda.py pointed at it is slower per call than the CPU library -- the batched entry points exist for that")
     return out
 
 

@@ -222,8 +222,8 @@ cudaError_t launch_series_acf(const double *series, long long stride, int n, int
 // Legacy scalar path (one bin, one parameter vector), see scalar_kernel.cu.
 //   consts [1+L][n] dense (row 0 data, rows 1..L dists), params[L], result[0] = value,
 //   resid (may be null) [n]
-cudaError_t launch_scalar(const double *consts, int n, int n_l, const double *params,
-                          double *result, double *resid, int mode, cudaStream_t stream);
+cudaError_t launch_scalar(const double *consts, int n, int n_l, const double *params_host, const double *params_dev, double *result,
+                          double *resid, int mode, unsigned long long *done, unsigned long long ticket, cudaStream_t stream);
 
 // Roofline denominators, see peaks.cu.
 cudaError_t measure_fp64_peak(int repeats, int sm_count, double *tflops);
