@@ -116,26 +116,56 @@ def bins_per_group(config, n_l, n_bins, thin=1, free_bytes=None, cs_lib=None, he
     return int(max(1, min(n_bins, (headroom * free_bytes) // per_bin)))
 
 
+class _DrawnNoise:
+    """Hands out normal draws made beforehand, bin by bin: the walker starts of a bin must not depend on which group the
+    bin is sampled in."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+
+    def standard_normal(self, shape):
+        block = self.blocks.pop(0)
+        assert block.shape == tuple(shape)
+        return block
+
+
 def fit_and_mcmc_grouped(consts, n_pts, bounds, start_params, config, ewsr=None, seed=0, bin_ids=None, rng=None, thin=1,
-                         energies=None, group_size=None, cs_lib=None):
+                         energies=None, group_size=None, cs_lib=None, split_by_conditioning=True):
     """``fit_and_mcmc_all`` over groups of bins sized to the device's free memory (``group_size`` bins at a time;
     default: ``bins_per_group``).  Every group gets its own store and ensemble, closed before the next one starts; chain
-    files ("Save Chain Data") are written per group.  Results do not depend on the grouping: the sampler's random
-    streams are keyed by the global bin index and the walker-start draws are made bin by bin in order."""
+    files ("Save Chain Data") are written per group.  With ``split_by_conditioning`` the bins whose triangular-factor
+    likelihood is not safe (``DeviceStore.conditioning``: cross-section errors below ~0.5 %) are sampled in groups of
+    their own, so that one such bin sends only itself -- not the spectrum -- to the slower reference-order stepper.
+    Results do not depend on the grouping: the sampler's random streams are keyed by the global bin index and the
+    walker-start draws are made bin by bin, in order, before any group runs."""
     from . import chisq
     consts = np.asarray(consts)
+    n_pts = np.asarray(n_pts)
     n_bins, n_l = consts.shape[0], consts.shape[1] - 1
+    cfg = dict(DEFAULTS)
+    cfg.update(config)
     bin_ids = np.arange(n_bins) if bin_ids is None else np.asarray(bin_ids)
     rng = np.random.RandomState(seed) if rng is None else rng
+    noise = [rng.standard_normal((cfg["Number of Walkers"], 2, n_l)) for _ in range(n_bins)]
     if group_size is None:
         group_size = bins_per_group(config, n_l, n_bins, thin, cs_lib=cs_lib)
-    results = []
-    for first in range(0, n_bins, group_size):
-        sel = slice(first, min(first + group_size, n_bins))
-        store = chisq.DeviceStore(consts[sel], np.asarray(n_pts)[sel], bounds, cs_lib=cs_lib)
-        part, ens = fit_and_mcmc_all(store, start_params, config, ewsr=ewsr, seed=seed, bin_ids=bin_ids[sel], rng=rng, thin=thin,
-                                     energies=None if energies is None else list(energies)[sel])
-        results.extend(part)
-        ens.close()
-        store.close()
+    order = [np.arange(n_bins)]
+    if split_by_conditioning and n_bins:
+        probe = chisq.DeviceStore(consts, n_pts, bounds, cs_lib=cs_lib)
+        kappa, limit, safe = probe.conditioning()
+        probe.close()
+        if not safe:
+            order = [np.nonzero(kappa <= limit)[0], np.nonzero(~(kappa <= limit))[0]]
+    results = [None] * n_bins
+    for members in order:
+        for first in range(0, len(members), group_size):
+            sel = members[first:first + group_size]
+            store = chisq.DeviceStore(consts[sel], n_pts[sel], bounds, cs_lib=cs_lib)
+            part, ens = fit_and_mcmc_all(store, start_params, config, ewsr=ewsr, seed=seed, bin_ids=bin_ids[sel],
+                                         rng=_DrawnNoise(noise[b] for b in sel), thin=thin,
+                                         energies=None if energies is None else [list(energies)[b] for b in sel])
+            for b, res in zip(sel, part):
+                results[b] = res
+            ens.close()
+            store.close()
     return results

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from mimic_mda_b200 import builder, fits, pipeline, shard
+from mimic_mda_b200 import builder, fits, pipeline, shard, synth
 from oracle import posterior_oracle
 
 pytestmark = pytest.mark.gpu
@@ -112,3 +112,26 @@ def test_grouped_pipeline_equals_the_one_group_run(tmp_path, cs_lib):
     assert pipeline.bins_per_group({}, 8, 116, free_bytes=170e9) == 34
     assert pipeline.bins_per_group({}, 8, 116, free_bytes=1e9) == 1
     assert 1 <= pipeline.bins_per_group(cfg, 4, 6, cs_lib=cs_lib) <= 6
+
+
+def test_an_ill_conditioned_bin_is_sampled_in_a_group_of_its_own(tmp_path, cs_lib):
+    """One bin with 0.01 % errors in a spectrum: only that bin goes to the reference-order stepper, and every bin's result
+    is the one it has when the whole spectrum is sampled at once."""
+    cfg = {"Number of Walkers": 32, "Sample Points": 40, "Burn-in Points": 8, "Number Walker Generators": 3, "Num Bins": 40}
+    consts, n_pts, _ = synth.make_bins(5, 4, 30)
+    bad, _, _ = synth.make_bins(1, 4, 30, rel_err=1e-4, seed_base=77)
+    consts[3] = bad[0]
+    bounds = synth.default_bounds(4)
+    starts = fits.calc_start_params([[0.05, 0.25]] * 4)
+    split = pipeline.fit_and_mcmc_grouped(consts, n_pts, bounds, starts, cfg, seed=2, rng=np.random.RandomState(5), cs_lib=cs_lib)
+    whole = pipeline.fit_and_mcmc_grouped(consts, n_pts, bounds, starts, cfg, seed=2, rng=np.random.RandomState(5), cs_lib=cs_lib,
+                                          split_by_conditioning=False)
+    assert len(split) == 5 and all(r is not None for r in split)
+    for b, (a, w) in enumerate(zip(split, whole)):
+        if b == 3:
+            continue        # sampled by the same (reference-order) stepper in both runs, but next to different bins: same chain
+        # the well-conditioned bins ran on the triangular-factor stepper in one run and on the reference-order stepper in the
+        # other: same decisions, so the same samples and summaries
+        np.testing.assert_array_equal(np.array(a[0][0]), np.array(w[0][0]))
+        assert a[1][2] == w[1][2]
+    np.testing.assert_array_equal(np.array(split[3][0][0]), np.array(whole[3][0][0]))
