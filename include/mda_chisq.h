@@ -206,15 +206,21 @@ MDA_API unsigned long long mdaKernelLaunchCount(void);
  * stepper: chi^2(a) = |T [a; -1]|^2 from the triangular factor T of the bin's
  * [distributions | data] matrix (QR in long double when the store is uploaded):
  * (L+1)(L+2)/2 multiply-adds per evaluation whatever the number of angles, same
- * decisions and chains as the angle-by-angle steppers, lnL within ~1e-14 of
- * C/ChiSquare.c:176-213.  MDA_ENS_IMPL=direct selects those: chi^2 angle by angle
- * on the fp64 tensor path (DMMA.8x8x4; two schedules picked by bins per SM,
- * DESIGN.md 4.2; ensembles of more than 512 walkers or numL < 4 on the DFMA
- * stepper).  Random numbers come
- * from Philox4x32-10 with counter
- * (walker, bin id, 2*step+half, draw) and key = seed, so a chain depends only
- * on (seed, bin id, start positions) -- not on launch shape or GPU count.
- * Kept samples are appended to a chain held in HBM.
+ * decisions and chains as the angle-by-angle steppers.  Its lnL is within
+ * ~eps * kappa of C/ChiSquare.c:176-213, kappa = |data| / sqrt(min chi^2): ~1e-14
+ * at 1 % cross-section errors; a store with a bin whose kappa exceeds the limit
+ * of mdaStoreConditioning (errors below ~0.5 %) is stepped in the reference's
+ * operation order instead, so the 1e-12 bound holds whatever the data.
+ * MDA_ENS_IMPL=direct selects the angle-by-angle steppers on the fp64 tensor path
+ * (DMMA.8x8x4; two schedules picked by bins per SM; they sum a
+ * residual's terms in fragment order and share the sensitivity to kappa), dfma
+ * the reference-order one.  Random numbers come from Philox4x32-10 with counter
+ * (walker, bin id, 2*step+half, 0) and key = seed + restarts * 0x9E3779B97F4A7C15
+ * (restarts = mdaEnsembleSetState calls on this ensemble before the current one),
+ * so a chain depends only on (seed, bin id, start positions, restart count) --
+ * not on launch shape, stepper or GPU count.  Kept samples are appended to a
+ * chain held in HBM; thin keeps the steps whose 1-based index is a multiple of
+ * it (emcee 2.x keeps 0-based multiples: shift by one step to compare).
  * --------------------------------------------------------------------- */
 MDA_API void *mdaEnsembleCreate(void *store, int nWalkers, unsigned long long seed, double stretchA);
 MDA_API void  mdaEnsembleFree(void *ens);
@@ -222,7 +228,9 @@ MDA_API void  mdaEnsembleFree(void *ens);
  * bin's index in the whole spectrum when bins are sharded over GPUs. */
 MDA_API int   mdaEnsembleSetBinIds(void *ens, const int *binIds);
 /* p0[bin][walker][l] (host).  Evaluates the starting log-posteriors, zeroes
- * the acceptance counters and the step counter.  Rejects NaN/inf positions. */
+ * the acceptance counters and the step counter.  Rejects NaN/inf positions.
+ * Must be called again after mdaStoreSetBin / mdaStoreSetBounds (Advance
+ * refuses a state whose log-probabilities belong to the old store). */
 MDA_API int   mdaEnsembleSetState(void *ens, const double *p0);
 /* Room for `capacity` kept samples: chain[kept][bin][walker][l] and
  * lnprob[kept][bin][walker] in HBM (step-major, so a run streams out as
