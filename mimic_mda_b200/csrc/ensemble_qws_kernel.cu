@@ -147,7 +147,8 @@ struct QwsUnit {
 __device__ __forceinline__ bool qws_next_unit(const EnsembleArgs &args, long long &p, long long r1, QwsUnit &u) {
     if (p >= r1) return false;
     const long long K = args.n_steps;
-    const long long b = p / K, o = p - b * K;
+    // (a 64-bit division is a subroutine of a few hundred cycles, at every piece switch; ribbons below 2^31 bin-steps take the 32-bit one)
+    const long long b = (r1 >> 31) == 0 ? (long long)((uint32_t)p / (uint32_t)K) : p / K, o = p - b * K;
     const long long len = min(K - o, r1 - p);
     u.bin = (int)b;
     if (o == 0 && len == K) { u.s0 = 0; u.s1 = (int)K; u.waits = u.signals = false; }
@@ -425,11 +426,15 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
     if constexpr (PROF) if (d == 0 && args.prof) for (int k = 0; k < 5; ++k) args.prof[(size_t)blockIdx.x * 128 + (DRAWS ? 112 : 120) + k] = p_d[k];
     if constexpr (PROF) if (copier && args.prof) args.prof[(size_t)blockIdx.x * 128 + 125] = (long long)q_globaltimer_ns();     // before the last copies are waited for
     if (copier) {
-        q_bulk_wait_all();
+        // Shared memory must outlive the copies' reads; their writes are complete when the grid is (nobody inside this launch
+        // reads them, except the CTA that waits for a progress word: that one needs the full wait before the release).
         if (pending_release >= 0) {
+            q_bulk_wait_all();
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
             q_st_release_u64(args.progress + pending_release, args.launch_serial + 1ull);
+        } else {
+            q_bulk_wait_read_all();
         }
     }
     if constexpr (PROF) if (copier && args.prof) args.prof[(size_t)blockIdx.x * 128 + 127] = (long long)q_globaltimer_ns();     // the CTA's last instruction but a few
