@@ -62,7 +62,8 @@ struct QwsSmem {
         ua = off; off += 3 * h * 8;                                           // [3][H] acceptance uniform
         pf = off; off += 3 * h * 8;                                           // [3][H] {partner index, float (L-1) ln z - ln u'}
         off = (off + 15) & ~(size_t)15;
-        tri = off; if (tri_in_smem) off += (size_t)quad_padded_doubles(n_l) * 8;
+        tri = off; off += (size_t)quad_padded_doubles(n_l) * 8;               // T, rows padded (all of it, or the short rows of the register build)
+        (void)tri_in_smem;
         total = (off + 15) & ~(size_t)15;
     }
 };
@@ -524,26 +525,29 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         q_mbar_wait(&s_bar[buf], buf ? load_parity[1] : load_parity[0]);      // the piece's state has arrived
         if (buf) load_parity[1] ^= 1u; else load_parity[0] ^= 1u;
         if (ustamp) ustamp[1] = clock64();
-        double tri_regs[TREG ? quad_padded_doubles(L) : 1];
+        // The register build keeps the first kSplit rows of T in registers and the rest in shared memory (16-byte broadcast
+        // loads).  With 32-bit shared addressing there is room for ALL of T and the thread's own two rows (x0, x1 below) in
+        // the 208 registers of a walker thread, so kSplit = L + 1; measured at L = 9 (us per step, one bin per SM): 6 rows 1.88,
+        // 7: 1.87, 8: 1.92, 9: 1.76, 10: 1.76.
+        constexpr int kSplit = TREG ? L + 1 : 0;
+        constexpr int kTriRegs = quad_padded_offset(L, kSplit) > 0 ? quad_padded_offset(L, kSplit) : 1;
+        double tri_regs[kTriRegs];
         {
             const double *packed = fac_of(buf);
-            if constexpr (TREG) {
 #pragma unroll
-                for (int k = 0; k < quad_padded_doubles(L); ++k) tri_regs[k] = 0.0;
+            for (int k = 0; k < kTriRegs; ++k) tri_regs[k] = 0.0;
 #pragma unroll
-                for (int i = 0; i <= L; ++i)
+            for (int i = 0; i < kSplit; ++i)
 #pragma unroll
-                    for (int k = 0; k < L + 1 - i; ++k) tri_regs[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
-            } else {
-                // rows padded for 16-byte broadcast reads (walker warps only: named barrier 1, 256 threads; the previous piece's
-                // last read of sTri lies before its barrier (D))
-                for (int k = tid; k < quad_padded_doubles(L); k += kWalkerThreads) sTri[k] = 0.0;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int k = 0; k < L + 1 - i; ++k) tri_regs[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
+            // rows padded for 16-byte broadcast reads (walker warps only: named barrier 1, 256 threads; the previous piece's
+            // last read of sTri lies before its barrier (D))
+            for (int k = tid; k < quad_padded_doubles(L); k += kWalkerThreads) sTri[k] = 0.0;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i <= L; ++i)
-                    for (int k = tid; k < L + 1 - i; k += kWalkerThreads) sTri[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
+            for (int i = kSplit; i <= L; ++i)
+                for (int k = tid; k < L + 1 - i; k += kWalkerThreads) sTri[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         const long long step_first = args.step0 + unit.s0;
         const uint32_t t_begin = 2u * (uint32_t)step_first, t_end = 2u * (uint32_t)(args.step0 + unit.s1);
@@ -560,15 +564,24 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         const uint32_t draw_a = q_smem_addr(sZ) + (uint32_t)me * 8u;       // my slot of ring position 0; Ua and PF lie 3 H and 6 H doubles on
         const uint32_t ring_bytes = (uint32_t)H * 8u, ring_span = 3u * ring_bytes;
         uint32_t ring_off = (uint32_t)ring * ring_bytes;                   // ring position of this half-step's draw
-        // The row and log-probability of the walker I update next: fetched at the end of the half-step before (its half is
-        // not written meanwhile), so that after the barrier only the partner row is still to come.
-        double x[L], oldlnp = 0.0;
+        // My two walkers' rows and log-probabilities.  Register build: both stay in registers for the whole piece (reloading
+        // the next half-step's row from shared memory at the end of every half-step cost 6 % of the step).  Other build: the
+        // next half-step's row is fetched at the end of the half-step before (its half is not written meanwhile).
+        constexpr bool XREG = TREG;
+        double x0[L], x1[XREG ? L : 1], lnp0 = 0.0, lnp1 = 0.0;
         if (owner) {
 #pragma unroll
-            for (int l = 0; l < L; ++l) x[l] = q_lds_f64(pos_a + (uint32_t)me * (uint32_t)(L * 8) + 8u * l);
-            oldlnp = q_lds_f64(lnp_a + (uint32_t)me * 8u);
+            for (int l = 0; l < L; ++l) x0[l] = q_lds_f64(pos_a + (uint32_t)me * (uint32_t)(L * 8) + 8u * l);
+            lnp0 = q_lds_f64(lnp_a + (uint32_t)me * 8u);
+            if constexpr (XREG) {
+#pragma unroll
+                for (int l = 0; l < L; ++l) x1[XREG ? l : 0] = q_lds_f64(pos_a + (uint32_t)(H + me) * (uint32_t)(L * 8) + 8u * l);
+                lnp1 = q_lds_f64(lnp_a + (uint32_t)(H + me) * 8u);
+            }
         }
-        auto half_step = [&](const int half, uint32_t t, unsigned int &acc) {   // half: a literal at both call sites
+        // x, oldlnp: the row and log-probability of the walker updated in this half-step (register build: x0/lnp0 or x1/lnp1;
+        // other build: always x0/lnp0, reloaded at the end of every half-step)
+        auto half_step = [&](const int half, uint32_t t, double (&x)[L], double &oldlnp, unsigned int &acc) {   // half: a literal at both call sites
             const int s_base = half ? H : 0, c_base = half ? 0 : H;           // updated half; partners come from the other one
             const bool kept_step = keeping && until_keep == 1 && slot < args.keep_cap;
             long long w0 = 0;
@@ -605,7 +618,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
                 }
                 if constexpr (PROF) { const long long w1 = clock64(); p_w[0] += w1 - w0; w0 = w1; }
                 double chi;
-                if constexpr (TREG) chi = outside ? CUDART_INF : chi_from_factor_regs<L>(tri_regs, q);
+                if constexpr (TREG) chi = outside ? CUDART_INF : chi_from_factor_split<L, kSplit>(tri_regs, sTri, q);
                 else chi = outside ? CUDART_INF : chi_from_factor<L>(sTri, q);
                 saw_nan = saw_nan || (chi != chi);
                 if constexpr (PROF) { const long long w1 = clock64() + (long long)(chi == -1.0); p_w[1] += w1 - w0; w0 = w1; }
@@ -620,16 +633,23 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
                     for (int l = 0; l < L; ++l) q_sts_f64(xrow + 8u * l, q[l]);
                     q_sts_f64(lnp_a + (uint32_t)(s_base + me) * 8u, chi * -0.5);
                     acc += 1u;
+                    if constexpr (XREG) {                    // the register copy follows
+#pragma unroll
+                        for (int l = 0; l < L; ++l) x[l] = q[l];
+                        oldlnp = chi * -0.5;
+                    }
                 }
                 // the next half-step's operands: its draw (in place since the last barrier; of this piece or of the next one) and
                 // my walker of the other half -- not the next piece's, which is fetched when that piece starts.  (Fetched here, not
                 // under the chi^2 sum: behind the other warp group's gather in the scheduler's load queue they would hold this warp
                 // at their issue -- measured 4 % slower.)
                 if (t + 1 < t_end || has_next) { z = q_lds_f64(draw_a + next_off); pf = q_lds_u2(draw_a + 2u * ring_span + next_off); }
-                if (t + 1 < t_end) {
+                if constexpr (!XREG) {
+                    if (t + 1 < t_end) {
 #pragma unroll
-                    for (int l = 0; l < L; ++l) x[l] = q_lds_f64(nrow + 8u * l);
-                    oldlnp = q_lds_f64(lnp_a + (uint32_t)(c_base + me) * 8u);
+                        for (int l = 0; l < L; ++l) x[l] = q_lds_f64(nrow + 8u * l);
+                        oldlnp = q_lds_f64(lnp_a + (uint32_t)(c_base + me) * 8u);
+                    }
                 }
             }
             ring_off = next_off;
@@ -644,8 +664,9 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
             }
         };
         for (uint32_t t = t_begin; t < t_end; t += 2) {      // t_begin is even: a step is the update of half 0, then of half 1
-            half_step(0, t, acc0);
-            half_step(1, t + 1, acc1);
+            half_step(0, t, x0, lnp0, acc0);
+            if constexpr (XREG) half_step(1, t + 1, x1, lnp1, acc1);
+            else half_step(1, t + 1, x0, lnp0, acc1);
         }
         if (ustamp) ustamp[3] = clock64();
         q_fence_proxy_async();

@@ -85,4 +85,50 @@ __device__ __forceinline__ double chi_from_factor_regs(const double (&t)[quad_pa
     return chi;
 }
 
+// Rows 0 .. SPLIT-1 of T from registers (t[] in the padded layout, only those rows filled), rows SPLIT .. L from shared
+// memory (padded layout, 16-byte broadcast reads): the long rows where registers pay, the short ones where a handful of
+// broadcast loads is cheaper than the registers they would occupy.  Same per-row and chi^2 order: the same bits.
+template <int L, int SPLIT, int G = 5>
+__device__ __forceinline__ double chi_from_factor_split(const double (&t)[quad_padded_offset(L, SPLIT) > 0 ? quad_padded_offset(L, SPLIT) : 1],
+                                                        const double *__restrict__ tri, const double (&a)[L]) {
+    double chi = 0.0;
+#pragma unroll
+    for (int i0 = 0; i0 < SPLIT; i0 += G) {
+        double u[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) u[g] = 0.0;
+#pragma unroll
+        for (int k = i0; k < L; ++k)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int i = i0 + g;
+                if (i <= k && i < SPLIT) u[g] = fma(t[quad_padded_offset(L, i < SPLIT ? i : 0) + (k - i)], a[k], u[g]);
+            }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int i = i0 + g;
+            if (i < SPLIT) {
+                u[g] -= t[quad_padded_offset(L, i) + (L - i)];
+                chi = fma(u[g], u[g], chi);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = SPLIT; i <= L; ++i) {
+        const int len = L + 1 - i;
+        const double2 *row = reinterpret_cast<const double2 *>(tri + quad_padded_offset(L, i));
+        double u = 0.0, data = 0.0;
+#pragma unroll
+        for (int k2 = 0; k2 < (len + 1) / 2; ++k2) {
+            const double2 v = row[k2];
+            const int k = 2 * k2;
+            if (k < len - 1) u = fma(v.x, a[i + k], u); else if (k == len - 1) data = v.x;
+            if (k + 1 < len - 1) u = fma(v.y, a[i + k + 1], u); else if (k + 1 == len - 1) data = v.y;
+        }
+        u -= data;
+        chi = fma(u, u, chi);
+    }
+    return chi;
+}
+
 }  // namespace mda
