@@ -49,7 +49,7 @@ constexpr int kThreads = kWalkerThreads + kDrawThreads;          // two CTAs per
 constexpr int kThreadsLone = kThreads + 128;                      // a CTA with its SM to itself: plus a copy warpgroup (see qws_service)
 
 struct QwsSmem {
-    size_t lnp, fac, buf_bytes, z, ua, pf, tri, total;       // a piece's buffer: positions at 0, then lnp, then fac; buffer b at b * buf_bytes
+    size_t lnp, fac, buf_bytes, z, ua, pf, tri, pad, total;       // a piece's buffer: positions at 0, then lnp, then fac; buffer b at b * buf_bytes
     __host__ __device__ QwsSmem(int walkers, int n_l, bool tri_in_smem) {
         const size_t h = (size_t)walkers / 2;
         size_t off = 0;
@@ -63,7 +63,11 @@ struct QwsSmem {
         pf = off; off += 3 * h * 8;                                           // [3][H] {partner index, float (L-1) ln z - ln u'}
         off = (off + 15) & ~(size_t)15;
         tri = off; off += (size_t)quad_padded_doubles(n_l) * 8;               // T, rows padded (all of it, or the short rows of the register build)
-        (void)tri_in_smem;
+        off = (off + 15) & ~(size_t)15;
+        // Register build, even L: a second copy of the positions with rows of L + 1 doubles, for the partner gather only.  Dense
+        // rows of an even L are 8 L bytes apart -- at L = 8 only two residue classes of bank pairs, at L = 16 one: a random
+        // gather collides 8- to 16-fold (2.5 us per step at L = 8 against 1.6 with the copy); an odd stride spreads rows evenly.
+        pad = off; if (!tri_in_smem && (n_l & 1) == 0) off += (size_t)walkers * (size_t)(n_l + 1) * 8;
         total = (off + 15) & ~(size_t)15;
     }
 };
@@ -530,6 +534,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         // the 208 registers of a walker thread, so kSplit = L + 1; measured at L = 9 (us per step, one bin per SM): 6 rows 1.88,
         // 7: 1.87, 8: 1.92, 9: 1.76, 10: 1.76.
         constexpr int kSplit = TREG ? L + 1 : 0;
+        constexpr bool kPadGather = TREG && (L & 1) == 0;
         constexpr int kTriRegs = quad_padded_offset(L, kSplit) > 0 ? quad_padded_offset(L, kSplit) : 1;
         double tri_regs[kTriRegs];
         {
@@ -547,6 +552,16 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
 #pragma unroll
             for (int i = kSplit; i <= L; ++i)
                 for (int k = tid; k < L + 1 - i; k += kWalkerThreads) sTri[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
+            if constexpr (kPadGather) {                      // the odd-stride copy of the positions the partner gather reads (see QwsSmem)
+                if (owner) {
+                    double *sPad = reinterpret_cast<double *>(smem_raw + lay.pad);
+#pragma unroll
+                    for (int l = 0; l < L; ++l) {
+                        sPad[(size_t)me * (L + 1) + l] = sPos[(size_t)me * L + l];
+                        sPad[(size_t)(H + me) * (L + 1) + l] = sPos[(size_t)(H + me) * L + l];
+                    }
+                }
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         const long long step_first = args.step0 + unit.s0;
@@ -560,7 +575,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         if (ustamp) ustamp[2] = clock64();
 
         // 32-bit shared-memory addresses, formed once per piece: the partner row's is then one multiply-add from the draw
-        const uint32_t pos_a = q_smem_addr(sPos), lnp_a = q_smem_addr(sLnp);
+        const uint32_t pos_a = q_smem_addr(sPos), lnp_a = q_smem_addr(sLnp), pad_a = q_smem_addr(smem_raw + lay.pad);
         const uint32_t draw_a = q_smem_addr(sZ) + (uint32_t)me * 8u;       // my slot of ring position 0; Ua and PF lie 3 H and 6 H doubles on
         const uint32_t ring_bytes = (uint32_t)H * 8u, ring_span = 3u * ring_bytes;
         uint32_t ring_off = (uint32_t)ring * ring_bytes;                   // ring position of this half-step's draw
@@ -598,7 +613,8 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
             const bool skew = TREG && H > kWalkerThreads / 2 && (H & 31) == 0 && (args.groups & 4) == 0;
             if (owner) {
                 if (skew && tid >= kWalkerThreads / 2) asm volatile("bar.sync 3, %0;" ::"r"(H) : "memory");
-                const uint32_t crow = pos_a + (uint32_t)(c_base + ((args.groups & 1) ? me : (int)pf.x)) * (uint32_t)(L * 8);   // (debug bit 0: no gather conflicts)
+                const uint32_t partner = (uint32_t)(c_base + ((args.groups & 1) ? me : (int)pf.x));   // (debug bit 0: no gather conflicts)
+                const uint32_t crow = kPadGather ? pad_a + partner * (uint32_t)((L + 1) * 8) : pos_a + partner * (uint32_t)(L * 8);
                 double c[L];
 #pragma unroll
                 for (int l = 0; l < L; ++l) c[l] = q_lds_f64(crow + 8u * l);
@@ -633,6 +649,11 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
                     for (int l = 0; l < L; ++l) q_sts_f64(xrow + 8u * l, q[l]);
                     q_sts_f64(lnp_a + (uint32_t)(s_base + me) * 8u, chi * -0.5);
                     acc += 1u;
+                    if constexpr (kPadGather) {              // and the copy the partners read
+                        const uint32_t prow = pad_a + (uint32_t)(s_base + me) * (uint32_t)((L + 1) * 8);
+#pragma unroll
+                        for (int l = 0; l < L; ++l) q_sts_f64(prow + 8u * l, q[l]);
+                    }
                     if constexpr (XREG) {                    // the register copy follows
 #pragma unroll
                         for (int l = 0; l < L; ++l) x[l] = q[l];
