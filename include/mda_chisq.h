@@ -160,9 +160,13 @@ MDA_API int   mdaStoreGetTile(void *store, int walkersPerBin, int *threads, int 
  * vectorised log-prob function, one per bin), out[bin][walker].
  * LnPost = flat box prior of mda.py:1574-1576 (-inf outside, NaN falls
  * through) then calculateLnLiklihood; Chi = calculateChi, no prior.
- * Per (bin, walker) the operation order is the reference's
- * (C/ChiSquare.c:188-212), so a result does not depend on batch shape,
- * tiling or GPU count.  All return MDA_OK or an error code.
+ * Up to 88 angles per bin (the register-tiled kernel) the operation order per
+ * (bin, walker) is the reference's (C/ChiSquare.c:188-212), bit for bit whatever
+ * the tiling; above that the default is the fp64 tensor-path kernel, which sums
+ * a residual's terms in fragment order (<= 1e-14 relative of the other; either
+ * can be forced, MDA_BATCH_IMPL = dfma | mma).  With either kernel a result
+ * does not depend on batch shape, tiling or GPU count.  All return MDA_OK or
+ * an error code.
  * --------------------------------------------------------------------- */
 
 /* Host pointers; copies in, launches, copies out, synchronises. */
