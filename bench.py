@@ -835,7 +835,10 @@ def main():
     # sampler launch: 2 N (L+1) flop per evaluation; HBM: kept chain + lnprob out,
     # constants + state in/out once
     s_flops = 2.0 * n_ang * (n_l + 1) * bins * cfg["walkers"] * args.steps
-    s_bytes = 8.0 * (n_l + 1) * bins * (cfg["walkers"] * (args.steps // s_thin + 2) + n_ang)
+    # 8 (L+1) bytes per evaluation (here: per kept sample, the chain and its log-probability going out) plus the
+    # bins' constants once per launch.  The state that comes in and goes back (2 x 8 (L+1) bytes per walker per launch) is real
+    # traffic too but not part of 8d's figure: left out of the fraction, so that it is the one a reader recomputes.
+    s_bytes = 8.0 * (n_l + 1) * bins * (cfg["walkers"] * (args.steps // s_thin) + n_ang)
     dmma_note = ("fp64 tensor path: mma.sync m8n8k4 f64 (DMMA.8x8x4) for 8 of the 9 distributions, DFMA for the rest; it shares the "
                  "DFMA pipe and its peak (measured: 36.8 vs 37.1 TFLOP/s) and holds the scheduler's issue port while it runs, so the "
                  "denominator is the same fp64 peak; tcgen05 has no fp64 kind")
