@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
     double z = 0.0;
     uint2 pf = make_uint2(0u, 0u);
     __syncthreads();                                         // (A)
+    if constexpr (PROF) if (tid == 0 && args.prof) args.prof[(size_t)blockIdx.x * 128 + 119] = (long long)q_globaltimer_ns();   // first draws made
     if (owner) { z = sZ[me]; pf = sPF[me]; }                 // the first half-step's draw; from then on fetched one half-step ahead
     while (true) {
         const bool has_next = qws_next_unit(args, ribbon, ribbon_end, next);
@@ -537,21 +538,22 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         constexpr bool kPadGather = TREG && (L & 1) == 0;
         constexpr int kTriRegs = quad_padded_offset(L, kSplit) > 0 ? quad_padded_offset(L, kSplit) : 1;
         double tri_regs[kTriRegs];
-        {
-            const double *packed = fac_of(buf);
+        if constexpr (TREG) {
+            // all of T into registers: the packed factor lies 16-byte aligned in the piece's buffer (quad_stride is even), so it
+            // is read with 16-byte broadcast loads and sorted into the padded register layout at compile time
+            const double2 *packed2 = reinterpret_cast<const double2 *>(fac_of(buf));
+            double2 flat[quad_stride(L) / 2];
+#pragma unroll
+            for (int k = 0; k < quad_stride(L) / 2; ++k) flat[k] = packed2[k];
 #pragma unroll
             for (int k = 0; k < kTriRegs; ++k) tri_regs[k] = 0.0;
 #pragma unroll
-            for (int i = 0; i < kSplit; ++i)
+            for (int i = 0; i <= L; ++i)
 #pragma unroll
-                for (int k = 0; k < L + 1 - i; ++k) tri_regs[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
-            // rows padded for 16-byte broadcast reads (walker warps only: named barrier 1, 256 threads; the previous piece's
-            // last read of sTri lies before its barrier (D))
-            for (int k = tid; k < quad_padded_doubles(L); k += kWalkerThreads) sTri[k] = 0.0;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-            for (int i = kSplit; i <= L; ++i)
-                for (int k = tid; k < L + 1 - i; k += kWalkerThreads) sTri[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
+                for (int k = 0; k < L + 1 - i; ++k) {
+                    const int e = quad_row_offset(L, i) + k;
+                    tri_regs[quad_padded_offset(L, i) + k] = (e & 1) ? flat[e >> 1].y : flat[e >> 1].x;
+                }
             if constexpr (kPadGather) {                      // the odd-stride copy of the positions the partner gather reads (see QwsSmem)
                 if (owner) {
                     double *sPad = reinterpret_cast<double *>(smem_raw + lay.pad);
@@ -561,7 +563,18 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
                         sPad[(size_t)(H + me) * (L + 1) + l] = sPos[(size_t)(H + me) * L + l];
                     }
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // walker warps only (named barrier 1)
             }
+        } else {
+            // T into shared memory, rows padded for 16-byte broadcast reads (walker warps only: named barrier 1, 256 threads; the
+            // previous piece's last read of sTri lies before its barrier (D))
+            const double *packed = fac_of(buf);
+            tri_regs[0] = 0.0;
+            for (int k = tid; k < quad_padded_doubles(L); k += kWalkerThreads) sTri[k] = 0.0;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i <= L; ++i)
+                for (int k = tid; k < L + 1 - i; k += kWalkerThreads) sTri[quad_padded_offset(L, i) + k] = packed[quad_row_offset(L, i) + k];
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         const long long step_first = args.step0 + unit.s0;
@@ -573,6 +586,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         unsigned int acc0 = 0u, acc1 = 0u;                   // proposals accepted in this piece, per walker of either half
         long long p_w[PROF ? 5 : 1] = {};
         if (ustamp) ustamp[2] = clock64();
+        if constexpr (PROF) if (tid == 0 && args.prof && unit_index == 1) args.prof[(size_t)blockIdx.x * 128 + 118] = (long long)q_globaltimer_ns();   // first piece ready to step
 
         // 32-bit shared-memory addresses, formed once per piece: the partner row's is then one multiply-add from the draw
         const uint32_t pos_a = q_smem_addr(sPos), lnp_a = q_smem_addr(sLnp), pad_a = q_smem_addr(smem_raw + lay.pad);
@@ -698,6 +712,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
             if (acc1) atomicAdd(gAcc + H + tid, acc1);
         }
         if (ustamp) ustamp[4] = clock64();
+        if constexpr (PROF) if (tid == 0 && args.prof) args.prof[(size_t)blockIdx.x * 128 + 117] = (long long)q_globaltimer_ns();   // (last) piece done
         if constexpr (PROF) if ((tid == 0 || tid == 255) && args.prof) for (int k = 0; k < 5; ++k) atomicAdd((unsigned long long *)args.prof + (size_t)blockIdx.x * 128 + (tid ? 8 : 0) + k, (unsigned long long)p_w[k]);
         if (!has_next) break;
         unit = next;

@@ -68,6 +68,12 @@ def main():
             ctas = min(args.bins, 148)
             wall = cyc[:ctas, 124:128]                     # ns (globaltimer): -, before the last wait, kernel entry, kernel exit
             t0 = wall[:, 2].min()
+            extra = cyc[:ctas, 117:120]                     # ns: last piece done, first piece ready to step, first draws made
+            out["wall_ns_median_since_own_entry"] = {"first_draws_made": float(np.median(extra[:, 2] - wall[:, 2])),
+                                                     "first_piece_ready": float(np.median(extra[:, 1] - wall[:, 2])),
+                                                     "last_piece_done": float(np.median(extra[:, 0] - wall[:, 2])),
+                                                     "before_final_wait": float(np.median(wall[:, 1] - wall[:, 2])),
+                                                     "exit": float(np.median(wall[:, 3] - wall[:, 2]))}
             out["wall_ns"] = {"entry_spread": float(wall[:, 2].max() - t0), "last_cta_before_final_wait": float(wall[:, 1].max() - t0), "last_cta_exit": float(wall[:, 3].max() - t0),
                               "first_cta_exit": float(wall[:, 3].min() - t0)}
             for name, o in (("walker_t0", 0), ("walker_t255", 8)):
