@@ -176,6 +176,11 @@ struct QwsCtx {
 // The barrier that only the walker warps and the thread that copies take part in (state of a piece complete / whole-state
 // chain store read).  In the build with a copy warpgroup the draw warps do not track pieces of work at all: they count
 // half-steps (qws_draw_loop), so these hand-offs are a named barrier of the other 384 threads.
+
+// Whether the walker warps of the build with a copy warpgroup gather in two groups (see the walker warps): more than four
+// warps of owners, whole warps only.  Debug bit 2 switches it off.
+__device__ __forceinline__ bool qws_skewed(int H, int debug) { return H > kWalkerThreads / 2 && (H & 31) == 0 && (debug & 4) == 0; }
+constexpr long long kChainStoreHoldCycles = 100;  // see qws_service
 template <bool COPYWG>
 __device__ __forceinline__ void qws_piece_barrier() {
     if constexpr (COPYWG) asm volatile("bar.sync 2, 384;" ::: "memory");
@@ -274,6 +279,7 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
     const int W = cx.W, H = cx.H;
     const long long total = cx.total, ribbon_end = cx.ribbon_end;
     const bool keeping = cx.keeping, split = cx.split;
+    const bool hold = !DRAWS && qws_skewed(H, args.groups) && (args.groups & 8) == 0;     // (debug bit 3: no hold)
     const QwsSmem &lay = cx.lay;
     double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
     double *sUa = reinterpret_cast<double *>(smem_raw + lay.ua);
@@ -366,8 +372,14 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
                     pending_release = -1;
                 }
                 if (kept_step) {
-                    if (args.groups >> 3) {              // (debug bits 3..: the store is issued this many hundreds of cycles after the barrier)
-                        const long long until = clock64() + 100ll * (args.groups >> 3);
+                    // The store reads 8 H (L + 1) bytes of shared memory while the next half-step's partner gather saturates that
+                    // pipe.  Issued right behind (B) its reads delay walker warps 0..3 and with them warps 4..7, which start
+                    // their gather behind those (the skew, see the walker warps).  Held back ~100 cycles -- warps 0..3 have
+                    // issued their loads by then -- a step takes 1.70 instead of 1.76 us (512 x 9; 2.31 instead of 2.38 at C4;
+                    // 1 to 2.5 % at 384 x 9, 512 x 4, 512 x 7, 512 x 8); held 300 cycles or more the time comes back as a wait
+                    // for the store's reads before the next (B), and with no skew (256 x 5) any hold costs 10 %.
+                    if (hold) {
+                        const long long until = clock64() + kChainStoreHoldCycles;
                         while (clock64() < until) __nanosleep(20);
                     }
                     double *dst = args.chain + (((size_t)slot * args.bins + (size_t)bin) * W) * L;
@@ -624,7 +636,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
             // (the lone-CTA build only, and only when whole warps own walkers -- H a multiple of 32 -- so that every lane of warps
             // 0..3 arrives and every lane of the owning warps 4.. waits: the barrier's count is the H owning threads.  Debug bit 2
             // switches it off.)
-            const bool skew = TREG && H > kWalkerThreads / 2 && (H & 31) == 0 && (args.groups & 4) == 0;
+            const bool skew = TREG && qws_skewed(H, args.groups);
             if (owner) {
                 if (skew && tid >= kWalkerThreads / 2) asm volatile("bar.sync 3, %0;" ::"r"(H) : "memory");
                 const uint32_t partner = (uint32_t)(c_base + ((args.groups & 1) ? me : (int)pf.x));   // (debug bit 0: no gather conflicts)
