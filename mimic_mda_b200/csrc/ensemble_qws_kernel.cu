@@ -66,7 +66,7 @@ struct QwsSmem {
         off = (off + 15) & ~(size_t)15;
         // Register build, even L: a second copy of the positions with rows of L + 1 doubles, for the partner gather only.  Dense
         // rows of an even L are 8 L bytes apart -- at L = 8 only two residue classes of bank pairs, at L = 16 one: a random
-        // gather collides 8- to 16-fold (2.5 us per step at L = 8 against 1.6 with the copy); an odd stride spreads rows evenly.
+        // gather collides 8- to 16-fold (2.54 us per step at L = 8 against 1.95 with the copy); an odd stride spreads rows evenly.
         pad = off; if (!tri_in_smem && (n_l & 1) == 0) off += (size_t)walkers * (size_t)(n_l + 1) * 8;
         total = (off + 15) & ~(size_t)15;
     }
@@ -103,6 +103,23 @@ __device__ __forceinline__ void q_mbar_wait(uint64_t *bar, uint32_t parity) {
         "}\n" ::"r"(q_smem_addr(bar)),
         "r"(parity)
         : "memory");
+}
+// The same wait, given up when *abort is set (the copy thread's hand-over timed out: the state is not coming).
+__device__ __forceinline__ bool q_mbar_wait_or_abort(uint64_t *bar, uint32_t parity, const int *abort) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(q_smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (done) return true;
+        if (*reinterpret_cast<const volatile int *>(abort)) return false;
+    }
 }
 __device__ __forceinline__ unsigned long long q_ld_acquire_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -539,7 +556,11 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         ++unit_index;
         if (ustamp) { ustamp[0] = clock64(); ustamp[6] = unit.s1 - unit.s0; }
         double *sPos = pos_of(buf), *sLnp = lnp_of(buf);
-        q_mbar_wait(&s_bar[buf], buf ? load_parity[1] : load_parity[0]);      // the piece's state has arrived
+        // the piece's state has arrived (or never will: the walker warps do not wait at (D), where the copy thread settles the flag)
+        if (!q_mbar_wait_or_abort(&s_bar[buf], buf ? load_parity[1] : load_parity[0], &s_abort)) {
+            if (tid == 0) atomicOr(args.status, kStatusStalled);
+            break;
+        }
         if (buf) load_parity[1] ^= 1u; else load_parity[0] ^= 1u;
         if (ustamp) ustamp[1] = clock64();
         // The register build keeps the first kSplit rows of T in registers and the rest in shared memory (16-byte broadcast
@@ -717,7 +738,11 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         }
         if (ustamp) ustamp[3] = clock64();
         q_fence_proxy_async();
-        qws_piece_barrier<COPYWG>();                         // (D)
+        // (D) my last writes are fenced.  With a copy warpgroup the walker warps only say so and go on to the next piece (its
+        // buffer is the other one; the copy thread, which waits here, stores this one): they met the copy thread ~700 cycles
+        // late at every switch.
+        if constexpr (COPYWG) asm volatile("bar.arrive 2, 384;" ::: "memory");
+        else qws_piece_barrier<COPYWG>();
         if (owner) {                                         // the bin is mine alone: plain adds; issued after the barrier, so that no fence
             unsigned int *gAcc = args.nacc + (size_t)bin * W;   // of this piece waits for them (the next barrier orders them before a release)
             if (acc0) atomicAdd(gAcc + tid, acc0);
