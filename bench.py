@@ -389,7 +389,8 @@ class GpuWorkload:
         # More untimed steps, enqueued without waiting: the device is still busy with them while the host enqueues the start
         # event, the timed launch and the stop event, so the events bracket the K steps on the device and not the host's
         # launch latency (~7 us of a 70 us region at K = 20).  Nothing of them is kept (thin beyond their length).
-        self.ens.advance(max(warmup, 40), 10 ** 6, wait=False)
+        # (150 steps ~ 350 us: the clock-sampling thread may hold the interpreter while this thread wants to enqueue)
+        self.ens.advance(max(warmup, 150), 10 ** 6, wait=False)
         self.chisq.check(lib, lib.mdaEventRecord(self.ev0, self.store.handle))
         self.ens.advance(steps, thin, wait=False)
         self.chisq.check(lib, lib.mdaEventRecord(self.ev1, self.store.handle))
