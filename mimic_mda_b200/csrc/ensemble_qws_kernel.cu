@@ -62,7 +62,7 @@ struct QwsSmem {
         ua = off; off += 3 * h * 8;                                           // [3][H] acceptance uniform
         pf = off; off += 3 * h * 8;                                           // [3][H] {partner index, float (L-1) ln z - ln u'}
         off = (off + 15) & ~(size_t)15;
-        tri = off; off += (size_t)quad_padded_doubles(n_l) * 8;               // T, rows padded (all of it, or the short rows of the register build)
+        tri = off; off += (size_t)quad_padded_doubles(n_l) * 8;               // T, rows padded (the build with T in shared memory; the register build leaves it unused)
         off = (off + 15) & ~(size_t)15;
         // Register build, even L: a second copy of the positions with rows of L + 1 doubles, for the partner gather only.  Dense
         // rows of an even L are 8 L bytes apart -- at L = 8 only two residue classes of bank pairs, at L = 16 one: a random
