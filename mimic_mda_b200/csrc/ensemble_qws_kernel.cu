@@ -73,6 +73,13 @@ struct QwsSmem {
 };
 
 __device__ __forceinline__ uint32_t q_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// The same, opaque to the compiler: an address formed once per piece stays in its register (the plain conversion is
+// re-materialised in every half-step -- a read of the CTA's shared-memory window, SR_CgaCtaId, in front of the gather).
+__device__ __forceinline__ uint32_t q_smem_addr_once(const void *p) {
+    uint32_t a;
+    asm volatile("{\n.reg .u64 t;\ncvta.to.shared.u64 t, %1;\ncvt.u32.u64 %0, t;\n}" : "=r"(a) : "l"(p));
+    return a;
+}
 __device__ __forceinline__ void q_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void q_bulk_s2g(void *dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(q_smem_addr(src)), "r"(bytes) : "memory");
@@ -534,7 +541,11 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
 
     // =============================================================== walker warps
     if constexpr (TREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    const bool owner = tid < H;
+    // (an opaque flag: the compiler would otherwise re-read %tid.x and compare in every half-step -- a special-register read of
+    // ~40 cycles in front of the half-step's fence and barrier -- rather than keep one of 208 registers for it)
+    unsigned int owner_flag;
+    asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %1, %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(owner_flag) : "r"(tid), "r"(H));
+    const bool owner = owner_flag != 0u;
     const int me = min(tid, H - 1);
     const double dim_m1 = (double)(L - 1);
     bool saw_nan = false;
@@ -622,8 +633,8 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         if constexpr (PROF) if (tid == 0 && args.prof && unit_index == 1) args.prof[(size_t)blockIdx.x * 128 + 118] = (long long)q_globaltimer_ns();   // first piece ready to step
 
         // 32-bit shared-memory addresses, formed once per piece: the partner row's is then one multiply-add from the draw
-        const uint32_t pos_a = q_smem_addr(sPos), lnp_a = q_smem_addr(sLnp), pad_a = q_smem_addr(smem_raw + lay.pad);
-        const uint32_t draw_a = q_smem_addr(sZ) + (uint32_t)me * 8u;       // my slot of ring position 0; Ua and PF lie 3 H and 6 H doubles on
+        const uint32_t pos_a = q_smem_addr_once(sPos), lnp_a = q_smem_addr_once(sLnp), pad_a = q_smem_addr_once(smem_raw + lay.pad);
+        const uint32_t draw_a = q_smem_addr_once(sZ) + (uint32_t)me * 8u;       // my slot of ring position 0; Ua and PF lie 3 H and 6 H doubles on
         const uint32_t ring_bytes = (uint32_t)H * 8u, ring_span = 3u * ring_bytes;
         uint32_t ring_off = (uint32_t)ring * ring_bytes;                   // ring position of this half-step's draw
         // My two walkers' rows and log-probabilities.  Register build: both stay in registers for the whole piece (reloading
