@@ -256,7 +256,7 @@ __device__ __forceinline__ void qws_draw_loop(const EnsembleArgs &args, unsigned
     int made = 0;
     auto draw_one = [&]() {
         if (!valid) return;
-        if ((args.groups & 2) && ++made > 3) return;     // (debug bit 1: the first three draws are reused for ever)
+        if (PROF && (args.groups & 2) && ++made > 3) return;     // (debug bit 1: the first three draws are reused for ever)
         const uint32_t w_base = (t & 1u) ? (uint32_t)H : 0u;
         if (NDRAW >= kWalkerThreads) {
             qws_draw<L>(args, sZ, sUa, sPF, w_base + (uint32_t)min(d, H - 1), bin_id, t, (uint32_t)H, ring_base + d, d < H);
@@ -303,7 +303,7 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
     const int W = cx.W, H = cx.H;
     const long long total = cx.total, ribbon_end = cx.ribbon_end;
     const bool keeping = cx.keeping, split = cx.split;
-    const bool hold = !DRAWS && qws_skewed(H, args.groups) && (args.groups & 8) == 0;     // (debug bit 3: no hold)
+    const bool hold = !DRAWS && qws_skewed(H, PROF ? args.groups : 0) && (!PROF || (args.groups & 8) == 0);     // (debug bit 3: no hold)
     const QwsSmem &lay = cx.lay;
     double *sZ = reinterpret_cast<double *>(smem_raw + lay.z);
     double *sUa = reinterpret_cast<double *>(smem_raw + lay.ua);
@@ -546,6 +546,10 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
     unsigned int owner_flag;
     asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %1, %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(owner_flag) : "r"(tid), "r"(H));
     const bool owner = owner_flag != 0u;
+    // (likewise H, the skew barrier's count: re-derived from the parameter block -- a constant-bank load and a shift of ~40
+    // cycles in front of that barrier -- unless it is opaque)
+    int h_pinned;
+    asm volatile("mov.s32 %0, %1;" : "=r"(h_pinned) : "r"(H));
     const int me = min(tid, H - 1);
     const double dim_m1 = (double)(L - 1);
     bool saw_nan = false;
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         // x, oldlnp: the row and log-probability of the walker updated in this half-step (register build: x0/lnp0 or x1/lnp1;
         // other build: always x0/lnp0, reloaded at the end of every half-step)
         auto half_step = [&](const int half, uint32_t t, double (&x)[L], double &oldlnp, unsigned int &acc) {   // half: a literal at both call sites
-            const int s_base = half ? H : 0, c_base = half ? 0 : H;           // updated half; partners come from the other one
+            const int s_base = half ? h_pinned : 0, c_base = half ? 0 : h_pinned;   // updated half; partners come from the other one
             const bool kept_step = keeping && until_keep == 1 && slot < args.keep_cap;
             long long w0 = 0;
             if constexpr (PROF) w0 = clock64();
@@ -668,15 +672,15 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
             // (the lone-CTA build only, and only when whole warps own walkers -- H a multiple of 32 -- so that every lane of warps
             // 0..3 arrives and every lane of the owning warps 4.. waits: the barrier's count is the H owning threads.  Debug bit 2
             // switches it off.)
-            const bool skew = TREG && qws_skewed(H, args.groups);
+            const bool skew = TREG && qws_skewed(h_pinned, PROF ? args.groups : 0);
             if (owner) {
-                if (skew && tid >= kWalkerThreads / 2) asm volatile("bar.sync 3, %0;" ::"r"(H) : "memory");
-                const uint32_t partner = (uint32_t)(c_base + ((args.groups & 1) ? me : (int)pf.x));   // (debug bit 0: no gather conflicts)
+                if (skew && tid >= kWalkerThreads / 2) asm volatile("bar.sync 3, %0;" ::"r"(h_pinned) : "memory");
+                const uint32_t partner = (uint32_t)(c_base + ((PROF && (args.groups & 1)) ? me : (int)pf.x));   // (debug bit 0: no gather conflicts)
                 const uint32_t crow = kPadGather ? pad_a + partner * (uint32_t)((L + 1) * 8) : pos_a + partner * (uint32_t)(L * 8);
                 double c[L];
 #pragma unroll
                 for (int l = 0; l < L; ++l) c[l] = q_lds_f64(crow + 8u * l);
-                if (skew && tid < kWalkerThreads / 2) asm volatile("bar.arrive 3, %0;" ::"r"(H) : "memory");
+                if (skew && tid < kWalkerThreads / 2) asm volatile("bar.arrive 3, %0;" ::"r"(h_pinned) : "memory");
                 const uint32_t xrow = pos_a + (uint32_t)(s_base + me) * (uint32_t)(L * 8);
                 const uint32_t nrow = pos_a + (uint32_t)(c_base + me) * (uint32_t)(L * 8);      // my walker of the other half: the next one
                 // accept for sure if lnp(q) - lnp(x) + fast > 1e-4, reject for sure if < -1e-4 (fast: the float estimate of
@@ -843,7 +847,9 @@ cudaError_t launch_ensemble_qws(const EnsembleArgs &args, const EnsembleShape &s
     if (!k || !shape.fits || !shape.qws || !args.quad || grid < 1 || grid > args.bins || (grid < args.bins && !args.progress)) return cudaErrorInvalidValue;
     EnsembleArgs copy = args;
     copy.groups = 0;
-    if (const char *dbg = getenv("MDA_QWS_DEBUG")) copy.groups = atoi(dbg);   // timing experiments only (see the kernel): wrong chains
+    // timing experiments (see the kernel; wrong chains): read by the PROFILING build only -- in the product build a test of the
+    // word in every half-step cost a constant-bank load in front of the gather
+    if (const char *dbg = getenv("MDA_QWS_DEBUG")) copy.groups = atoi(dbg);
     if (grid == args.bins) {                                 // a bin per CTA: no CTA waits for another
         k<<<grid, shape.threads, shape.smem_bytes, stream>>>(copy);
         return cudaGetLastError();
