@@ -133,6 +133,12 @@ __device__ __forceinline__ unsigned long long q_ld_acquire_u64(const unsigned lo
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long q_ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void q_fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void q_st_release_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -421,8 +427,12 @@ __device__ __forceinline__ void qws_service(const EnsembleArgs &args, const QwsC
                 // the next piece's state comes in behind this one's steps (its buffer was last read by the store of the piece
                 // before this one); a piece that continues another CTA's bin only once that CTA has published it
                 if (has_next && !next_loaded && t > t_begin) {
+                    // (a look every fourth half-step, relaxed, the acquire only once the word is there: an acquiring load
+                    // invalidates the L1 and takes an L2 round trip -- with the chain store of the same half-step that was most
+                    // of the copy thread's 1500 cycles, and the copy thread paced the CTA while it waited for a word)
                     bool ready = !next.waits;
-                    if (!ready && q_ld_acquire_u64(args.progress + next.bin) == args.launch_serial + 1ull) {
+                    if (!ready && (t & 3u) == 0u && q_ld_relaxed_u64(args.progress + next.bin) == args.launch_serial + 1ull) {
+                        q_fence_acquire_gpu();
                         asm volatile("fence.proxy.async;" ::: "memory");
                         ready = true;
                     }
@@ -639,7 +649,8 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
         // 32-bit shared-memory addresses, formed once per piece: the partner row's is then one multiply-add from the draw
         const uint32_t pos_a = q_smem_addr_once(sPos), lnp_a = q_smem_addr_once(sLnp), pad_a = q_smem_addr_once(smem_raw + lay.pad);
         const uint32_t draw_a = q_smem_addr_once(sZ) + (uint32_t)me * 8u;       // my slot of ring position 0; Ua and PF lie 3 H and 6 H doubles on
-        const uint32_t ring_bytes = (uint32_t)H * 8u, ring_span = 3u * ring_bytes;
+        uint32_t ring_bytes, ring_span;                                    // (opaque: kept, not re-derived from the parameter block)
+        asm volatile("shl.b32 %0, %2, 3;\n\tmul.lo.u32 %1, %2, 24;" : "=r"(ring_bytes), "=r"(ring_span) : "r"(h_pinned));
         uint32_t ring_off = (uint32_t)ring * ring_bytes;                   // ring position of this half-step's draw
         // My two walkers' rows and log-probabilities.  Register build: both stay in registers for the whole piece (reloading
         // the next half-step's row from shared memory at the end of every half-step cost 6 % of the step).  Other build: the
@@ -695,13 +706,16 @@ __global__ void __launch_bounds__(TREG ? kThreadsLone : kThreads, TREG ? 1 : 2) 
                     outside = outside | (q[l] < args.lo[l]) | (q[l] > args.hi[l]);   // mda.py:1575; a NaN compares false, as there
                 }
                 if constexpr (PROF) { const long long w1 = clock64(); p_w[0] += w1 - w0; w0 = w1; }
+                // chi^2 for every lane, +inf put in afterwards for the proposals outside the box: no divergence region around the sum
+                // (its reconvergence cost every warp ~50 cycles for lanes that are almost never there)
                 double chi;
-                if constexpr (TREG) chi = outside ? CUDART_INF : chi_from_factor_split<L, kSplit>(tri_regs, sTri, q);
-                else chi = outside ? CUDART_INF : chi_from_factor<L>(sTri, q);
-                saw_nan = saw_nan || (chi != chi);
+                if constexpr (TREG) chi = chi_from_factor_split<L, kSplit>(tri_regs, sTri, q);
+                else chi = chi_from_factor<L>(sTri, q);
+                asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\n@p mov.f64 %0, 0d7FF0000000000000;\n}" : "+d"(chi) : "r"(outside ? 1u : 0u));
                 if constexpr (PROF) { const long long w1 = clock64() + (long long)(chi == -1.0); p_w[1] += w1 - w0; w0 = w1; }
                 bool accept = chi < chi_accept;
-                if (!accept && !(chi > chi_reject)) {        // near a tie (or NaN): emcee's test in full precision
+                if (!accept && !(chi > chi_reject)) {        // near a tie (or NaN: both comparisons false): emcee's test in full precision
+                    saw_nan = saw_nan || (chi != chi);
                     const double newlnp = chi * -0.5;
                     const double zlog = __dmul_rn(dim_m1, log(z));
                     accept = __dsub_rn(__dadd_rn(zlog, newlnp), oldlnp) > log(q_lds_f64(draw_a + ring_span + ring_off));
