@@ -14,19 +14,26 @@
 //     gather the partner row, propose, test the box prior (mda.py:1574-1576), evaluate chi^2, decide, overwrite their row.
 //     The accept test is two thresholds on chi^2 prepared while chi^2 is being summed;
 //   * 4 DRAW warps stay two half-steps ahead with the draws (a ring of three slots in shared memory) -- work that is
-//     independent of the walker warps' chain and fills their stall slots.  One of their threads owns every bulk copy: the
-//     chain stores (issued after the half-step's barrier, waited for before the next one), the state of the next piece of
-//     work coming in and the state of the last one going back;
+//     independent of the walker warps' chain and fills their stall slots;
+//   * one thread owns every bulk copy: the chain stores (issued ~100 cycles after the half-step's barrier, waited for before
+//     the next one), the state of the next piece of work coming in and the state of the last one going back.  In the build
+//     with two CTAs per SM it is a draw thread, in the build that has its SM to itself the first thread of a fourth
+//     warpgroup that does nothing else;
 //   * one __syncthreads per half-step, as before.
 //
-// A CTA that has its SM to itself (TREG build) moves registers from the draw warps to the walker warps with setmaxnreg
-// (208 for a walker thread, 56 for a draw thread, 40 for the copy warpgroup): T (55 doubles at L = 9) and the thread's own two rows stay in registers.  The other build keeps T in
-// shared memory and fits two CTAs per SM.
+// A CTA that has its SM to itself (TREG build) moves registers from the draw and copy warps to the walker warps with
+// setmaxnreg (208 for a walker thread, 56 for a draw thread, 40 for the copy warpgroup): T (55 doubles at L = 9) and the
+// thread's own two rows stay in registers.  The other build keeps T in shared memory and fits two CTAs per SM.
 //
 // Schedule: see qws_next_unit.  With more bins than resident CTAs (C4: 200 bins on 148 SMs) every CTA carries the same
 // number of bin-steps whatever the length of the launch; a CTA's pieces of work are double-buffered in shared memory, the
 // next one's state (positions, log-probabilities, factor) arriving by bulk copy while the current one steps, and the draw
-// pipeline runs across the boundary: a switch costs two barriers.
+// pipeline runs across the boundary.  At a switch the walker warps arrive at the piece barrier and go on; the copy thread
+// waits there and stores the finished piece.
+//
+// The walker loop is written for what the profiler showed, not for looks: values the compiler would re-derive in every
+// half-step (owner test, shared addresses, barrier counts) are opaque asm results, chi^2 is summed by every lane and
+// +inf selected afterwards, the timing switches exist in the profiling build only (profiles/experiments/r02_stepper_notes.md).
 #include "philox.cuh"
 #include "quad_chi.cuh"
 
