@@ -1403,9 +1403,10 @@ int mdaEnsembleDescribe(void *ens, int nSteps, char *text, int textLen) {
     if (shape.qws) {
         snprintf(text, (size_t)textLen,
                  "ensemble_qws_kernel<L=%d,%s>: chi^2 = |T [a; -1]|^2 from the bin's triangular factor (%d multiply-adds per evaluation), 8 walker warps "
-                 "(a thread per walker of the active half) + 4 draw warps (Philox draws of the next half-step, chain stores), one barrier per half-step, "
+                 "(a thread per walker of the active half) + 4 draw warps (Philox draws two half-steps ahead)%s, one barrier per half-step, "
                  "bulk-TMA state load and chain stores, %zu B shared memory; %d CTAs for %d bins%s",
-                 s->n_l, shape.treg ? "T in registers via setmaxnreg 208/56/40" : "T in shared memory", quad_doubles(s->n_l), shape.smem_bytes,
+                 s->n_l, shape.treg ? "T in registers via setmaxnreg 208/56/40" : "T in shared memory", quad_doubles(s->n_l),
+                 shape.treg ? " + a copy warpgroup (bulk copies)" : " (one of their threads issues the bulk copies)", shape.smem_bytes,
                  qws_grid(s, shape), s->bins, qws_grid(s, shape) < s->bins ? " (every CTA carries the same number of bin-steps; cooperative launch)" : "");
     } else if (shape.quad) {
         snprintf(text, (size_t)textLen,
