@@ -214,7 +214,7 @@ class DeviceEnsemble:
 
     def describe(self, n_steps=1):
         """The stepping kernel and schedule an advance of ``n_steps`` would use (text)."""
-        buf = ct.create_string_buffer(512)
+        buf = ct.create_string_buffer(1024)
         chisq.check(self.lib, self.lib.mdaEnsembleDescribe(self.handle, int(n_steps), buf, len(buf)), "mdaEnsembleDescribe")
         return buf.value.decode()
 
