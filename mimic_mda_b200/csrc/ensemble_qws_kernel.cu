@@ -210,14 +210,14 @@ struct QwsCtx {
     QwsSmem lay{2, 1, false};
 };
 
-// The barrier that only the walker warps and the thread that copies take part in (state of a piece complete / whole-state
-// chain store read).  In the build with a copy warpgroup the draw warps do not track pieces of work at all: they count
-// half-steps (qws_draw_loop), so these hand-offs are a named barrier of the other 384 threads.
-
 // Whether the walker warps of the build with a copy warpgroup gather in two groups (see the walker warps): more than four
 // warps of owners, whole warps only.  Debug bit 2 switches it off.
 __device__ __forceinline__ bool qws_skewed(int H, int debug) { return H > kWalkerThreads / 2 && (H & 31) == 0 && (debug & 4) == 0; }
 constexpr long long kChainStoreHoldCycles = 100;  // see qws_service
+
+// The barrier that only the walker warps and the thread that copies take part in (state of a piece complete / whole-state
+// chain store read).  In the build with a copy warpgroup the draw warps do not track pieces of work at all: they count
+// half-steps (qws_draw_loop), so these hand-offs are a named barrier of the other 384 threads.
 template <bool COPYWG>
 __device__ __forceinline__ void qws_piece_barrier() {
     if constexpr (COPYWG) asm volatile("bar.sync 2, 384;" ::: "memory");
