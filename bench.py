@@ -811,10 +811,11 @@ def main():
                      "note": "this kernel obtains chi^2 from the bin's triangular factor with (L+1)(L+2) + 5 L flops per evaluation "
                              "(fp64_executed) instead of the 2 N (L+1) of SURVEY.md 8d (fp64: the ALGORITHMIC rate, which the pipe peak "
                              "does not cap), so the roofline that can bind it is HBM: the chain, 8 (L+1) bytes per evaluation, going "
-                             "out (achieved / frac).  What limits it before that is the SM's shared-memory pipe: the stretch move "
-                             "gathers a RANDOM partner row per walker and half-step, 3.7 wavefronts per half-warp access instead of 1 "
-                             "(profiles/r02_ncu_full_*: 1000 wavefronts per bin and half-step, 83 % of the pipe's peak with four bins per "
-                             "SM, where the chain reaches 56 % of the HBM rate); at C4 there are only 1.35 bins per SM to overlap"}
+                             "out (achieved / frac).  What limits it before that: a bin's half-steps are sequential, so an SM steps "
+                             "its bins one after the other at a half-step's latency (~1500 cycles at 512 x 9), most of it the "
+                             "shared-memory pipe -- the stretch move gathers a RANDOM partner row per walker and half-step, ~3 "
+                             "wavefronts per half-warp access instead of 1 (profiles/r02_ncu_full_*: 725 wavefronts per bin and "
+                             "half-step, 43 % of them bank-collision replays) -- and the fp64 dependency chains of chi^2"}
         # the triangular-factor kernel executes a tenth of the algorithmic flops: the roofline that can bind it is HBM
         # (the chain going out); its algorithmic flop rate is reported in "fp64" below, not as the headline fraction
         by_flops = f64 >= fhbm and executed_flops is None

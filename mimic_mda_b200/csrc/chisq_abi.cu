@@ -585,9 +585,12 @@ EnsembleShape ensemble_shape_for(MdaStore *s, int walkers) {
                want_qws = impl && strcmp(impl, "qws") == 0;
     EnsembleShape shape{};
     // default: the triangular-factor stepper (fewest operations per evaluation, same chains); the others on request.
-    // Warp-specialised (ensemble_qws_kernel) below two bins per SM, a plain CTA per bin and several per SM from there on.
-    if ((want_qws || (!impl && s->bins < 2 * g_rt.sm_count)) &&
-        choose_ensemble_qws_shape(s->bins, walkers, s->n_l, g_rt.sm_count, g_rt.smem_optin, &shape)) return shape;
+    // Warp-specialised (ensemble_qws_kernel): at any number of bins where T fits the walker threads' registers (one CTA per SM
+    // steps its share of the bins one after the other), else below two bins per SM; a plain CTA per bin and several per SM
+    // (ensemble_quad_kernel) from there on.
+    if ((want_qws || !impl) && choose_ensemble_qws_shape(s->bins, walkers, s->n_l, g_rt.sm_count, g_rt.smem_optin, &shape) &&
+        (want_qws || shape.treg || s->bins < 2 * g_rt.sm_count)) return shape;
+    shape = EnsembleShape{};
     if ((want_quad || want_qws || !(want_dfma || want_ws || want_mma || want_direct)) && choose_ensemble_quad_shape(walkers, s->n_l, g_rt.smem_optin, &shape)) return shape;
     if (!want_dfma) {
         const bool prefer_mma = want_mma || (!want_ws && s->bins >= 2 * g_rt.sm_count);

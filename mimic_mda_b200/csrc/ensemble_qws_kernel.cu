@@ -821,10 +821,12 @@ bool choose_ensemble_qws_shape(int bins, int walkers, int n_l, int sm_count, siz
     s.groups = 1;
     s.qws = true;
     s.quad = true;
-    // T in registers for a CTA that has its SM to itself (setmaxnreg gives the walker warps 224 registers): one CTA per SM
-    // carrying bins / SMs bins' worth of steps at 1.99 us per bin-step (512 x 9) beats two CTAs per SM (3.61 us per pair) up
-    // to 1.8 bins per SM
-    s.treg = quad_padded_doubles(n_l) <= 60 && 10LL * bins <= 18LL * sm_count;
+    // T in registers for a CTA that has its SM to itself (setmaxnreg gives the walker warps 208 registers) wherever T fits:
+    // one CTA per SM carrying bins / SMs bins' worth of steps, one after the other, at 1.51 us per bin-step (512 x 9) beats two
+    // CTAs per SM with T in shared memory (3.80 us per pair) and ensemble_quad_kernel's four (6.54 us per four) at any
+    // number of bins
+    (void)bins; (void)sm_count;
+    s.treg = quad_padded_doubles(n_l) <= 60;
     const char *force_treg = getenv("MDA_ENS_TREG");
     if (force_treg && (force_treg[0] == '0' || force_treg[0] == '1')) s.treg = quad_padded_doubles(n_l) <= 60 && force_treg[0] == '1';
     if (s.treg) s.threads = kThreadsLone;
