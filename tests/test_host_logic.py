@@ -157,3 +157,56 @@ def test_walker_starts_obey_the_box_rules():
     np.testing.assert_allclose(got[2], got[0])                                   # walker 2 from generator 0 again
     rnd = fits.gen_walker_starts(gens, 500, 2.0, 0.04, 0.02, ewsr, np.random.RandomState(1))
     assert rnd.shape == (500, 4) and np.all(rnd > 0) and np.all(rnd <= 1.0 / ewsr)
+
+
+def _ribbon_units(bins, n_steps, grid):
+    """The stepper's schedule, restated (csrc/ensemble_qws_kernel.cu: qws_next_unit and the segment bounds of the kernel): the
+    bins' step ranges laid end to end, cut into `grid` segments; per CTA the list of (bin, s0, s1, waits, signals)."""
+    total = bins * n_steps
+    out = []
+    for cta in range(grid):
+        p, r1 = cta * total // grid, (cta + 1) * total // grid
+        units = []
+        while p < r1:
+            b, o = divmod(p, n_steps)
+            length = min(n_steps - o, r1 - p)
+            if o == 0 and length == n_steps:
+                units.append((b, 0, n_steps, False, False))
+            elif o == 0:                                   # the end of the segment: the bin's LAST steps, behind another CTA's piece
+                units.append((b, n_steps - length, n_steps, True, False))
+            else:                                          # the start of the segment: its FIRST steps
+                units.append((b, 0, length, False, True))
+            p += length
+        out.append(units)
+    return out
+
+
+@pytest.mark.parametrize("bins,n_steps,grid", [(200, 20, 148), (200, 2000, 148), (200, 1, 148), (592, 20, 148), (149, 7, 148),
+                                               (5, 3, 5), (7, 1, 3), (1000, 13, 148), (25, 20, 25)])
+def test_ribbon_schedule_invariants(bins, n_steps, grid):
+    """Every bin-step exactly once and in order; equal shares; a bin in at most two pieces, the later one starting (at
+    equal speed) no earlier than the earlier one ends; at most one waiting and one signalling piece per CTA, and only at
+    the end / the start of its segment."""
+    sched = _ribbon_units(bins, n_steps, grid)
+    covered = {}
+    loads = []
+    for cta, units in enumerate(sched):
+        t = 0
+        loads.append(sum(s1 - s0 for _, s0, s1, _, _ in units))
+        for k, (b, s0, s1, waits, signals) in enumerate(units):
+            assert 0 <= s0 < s1 <= n_steps
+            assert not waits or k == len(units) - 1                # only the last piece of a segment continues another CTA's bin
+            assert not signals or k == 0                           # only the first one is continued elsewhere
+            covered.setdefault(b, []).append((s0, s1, cta, t, t + (s1 - s0), waits, signals))
+            t += s1 - s0
+    assert max(loads) - min(loads) <= 1 and sum(loads) == bins * n_steps
+    assert sorted(covered) == list(range(bins))
+    for b, pieces in covered.items():
+        pieces.sort()
+        assert len(pieces) <= 2 and pieces[0][0] == 0 and pieces[-1][1] == n_steps
+        if len(pieces) == 2:
+            first, second = pieces
+            assert first[1] == second[0] and first[6] and second[5] and first[2] == second[2] + 1
+            assert second[3] >= first[4]                           # the waiting piece starts after the other one has ended
+        else:
+            assert not pieces[0][5] and not pieces[0][6]
